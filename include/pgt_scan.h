@@ -1,0 +1,165 @@
+/*
+ * pgt_scan.h -- C ABI of libpgtscan.so: the B200 (sm_100a) windowed site-statistic scan.
+ *
+ * Drop-in boundary for the hot path of tplinderoth/PopGenomicsTools' fstWindow, hetWindow
+ * and dxyWindow.  The reference has no library API; its only internal seam is
+ *
+ *     calcWindow(buffer*, chr*, winsize, step, nsites*[, skip_missing]) -> iterator
+ *         /root/reference/fstWindow.cpp:69   (FST   = sum a / sum b over the buffered sites)
+ *         /root/reference/hetWindow.cpp:66   (het   = #g==1 / #g>=0)
+ *         /root/reference/dxyWindow.cpp:172  (dxy   = sum of per-site dxy, + neffective, nskip)
+ *
+ * driven by the flush triggers of calcFst / calcHeterozygosity / maf2dxy
+ * (fstWindow.cpp:125-152, hetWindow.cpp:123-150, dxyWindow.cpp:334-426).  This ABI replaces
+ * that pair -- "when does a window flush, over which sites, with which label" (pgt_plan_*,
+ * closed form, host) and "reduce the window" (pgt_scan_*, CUDA) -- with one columnar call:
+ *
+ *     columns + contig offsets + (W, S, mode)  ->  per-window SoA result arrays
+ *
+ * Conventions
+ *   - plain C types only; every function returns 0 on success or a negative pgt_status,
+ *     pgt_last_error() gives the message (thread-local).  The library never exits, never
+ *     prints, and has no CPU fallback: without a usable CUDA device every pgt_scan_* /
+ *     pgt_synth_* call fails with PGT_ERR_CUDA.
+ *   - the caller owns all column, output and workspace buffers.  `mem` says where columns and
+ *     outputs live: PGT_MEM_DEVICE (device pointers, work is enqueued on `stream` and not
+ *     synchronised) or PGT_MEM_HOST (host pointers, pinned preferred; the call stages
+ *     host->device->host through the workspace and returns after the results are on the host).
+ *     The workspace is always device memory of at least pgt_scan_workspace_bytes().
+ *   - `stream` is a cudaStream_t passed as void* (NULL = default stream).
+ *   - 1 <= S <= W is required (the reference has undefined behaviour otherwise:
+ *     heap corruption for S=0, segfault for S>W); violations return PGT_ERR_ARGS.
+ */
+#ifndef PGT_SCAN_H
+#define PGT_SCAN_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PGT_ABI_VERSION 1
+
+typedef enum {
+	PGT_OK = 0,
+	PGT_ERR_ARGS = -1,      /* invalid argument (message says which) */
+	PGT_ERR_CUDA = -2,      /* CUDA runtime/driver error or no device */
+	PGT_ERR_NOMEM = -3,     /* host allocation failed / workspace too small */
+	PGT_ERR_INPUT = -4      /* input violates the format contract (e.g. unsorted positions in bp mode) */
+} pgt_status;
+
+typedef enum {
+	PGT_MEM_DEVICE = 0,
+	PGT_MEM_HOST = 1
+} pgt_mem;
+
+typedef enum {
+	/* windows of W sites stepping S sites: fstWindow, hetWindow, dxyWindow -fixedsite 1
+	 * (fstWindow.cpp:6-7, hetWindow.cpp:6-7, dxyWindow.cpp:357-359,376-378) */
+	PGT_MODE_SITES = 0,
+	/* windows of W bp stepping S bp over the dense per-bp entry stream of every chromosome:
+	 * dxyWindow -fixedsite 0 (dxyWindow.cpp:336-355,363-373,407-426).  `contig_offsets` then
+	 * holds cumulative chromosome LENGTHS IN BP (from -sizefile), not site counts. */
+	PGT_MODE_BP = 1
+} pgt_mode;
+
+typedef struct pgt_plan pgt_plan; /* opaque: closed-form window enumeration + reduction geometry */
+
+/* ---- error / device ------------------------------------------------------------------ */
+const char* pgt_last_error(void);
+int pgt_abi_version(void);
+int pgt_device_count(void);            /* >= 0, or PGT_ERR_CUDA */
+int pgt_set_device(int device);
+
+/* pinned host memory for PGT_MEM_HOST callers (cudaHostAlloc / cudaFreeHost) */
+int pgt_host_alloc(void** p, size_t bytes);
+int pgt_host_free(void* p);
+
+/* ---- plan: which windows exist (replaces the flush triggers of calcFst & co.) ----------
+ *
+ * contig_offsets[ncontig+1]: cumulative sizes, contig c spans [off[c], off[c+1]) in site
+ * indices (PGT_MODE_SITES) or in entries = bp (PGT_MODE_BP).  Contigs are in file order;
+ * adjacent lines with equal names form one contig, as in the reference (chr != oldchr).
+ * unit_sites: cap on the reduction unit in sites (0 = default 256); part of the summation
+ * order, see DESIGN.md "Summation order".
+ *
+ * The enumeration reproduces, in closed form, the reference's behaviour incl. its quirks
+ * (SURVEY.md Appendix A): trailing partial window at every contig change but at EOF only if
+ * it holds > W-S sites; cross-contig carry when the buffer is exactly full at a contig
+ * change; in bp mode the stale carry of chromosomes no longer than W-S.
+ */
+int pgt_plan_create(pgt_plan** plan, pgt_mode mode, const uint64_t* contig_offsets, uint32_t ncontig,
+                    uint32_t W, uint32_t S, uint32_t unit_sites);
+void pgt_plan_destroy(pgt_plan* plan);
+
+uint64_t pgt_plan_num_windows(const pgt_plan* plan);
+uint64_t pgt_plan_num_units(const pgt_plan* plan);
+uint32_t pgt_plan_num_segments(const pgt_plan* plan);
+uint64_t pgt_plan_num_sites(const pgt_plan* plan); /* off[ncontig] */
+
+/* Host-side description of window w (tests, CLIs, sharding).  first/last are indices into the
+ * site (or entry) axis, inclusive; label = contig index of the last site (the printed name). */
+int pgt_plan_window(const pgt_plan* plan, uint64_t w, uint64_t* first, uint64_t* last, uint32_t* label);
+/* Bulk variant: fills arrays of length pgt_plan_num_windows (any pointer may be NULL). */
+int pgt_plan_windows(const pgt_plan* plan, uint64_t* first, uint64_t* last, uint32_t* label);
+/* Reduction unit j: [start, start+len) on the site/entry axis (tests, DESIGN.md geometry). */
+int pgt_plan_unit(const pgt_plan* plan, uint64_t j, uint64_t* start, uint32_t* len);
+/* Units summed for window w: [first_unit, first_unit + count). */
+int pgt_plan_window_units(const pgt_plan* plan, uint64_t w, uint64_t* first_unit, uint64_t* count);
+
+/* Sharding: split the window list into `nshards` contiguous ranges balanced by
+ * sites read; shard cuts fall on window starts, neighbours overlap by the W-S halo.
+ * Returns the window range [w_lo, w_hi) and the site/entry range [site_lo, site_hi) that shard
+ * `shard` must hold.  Results are bit-identical for any nshards. */
+int pgt_plan_shard(const pgt_plan* plan, uint32_t shard, uint32_t nshards, uint64_t* w_lo, uint64_t* w_hi,
+                   uint64_t* site_lo, uint64_t* site_hi);
+
+/* ---- scan: the hot path ----------------------------------------------------------------
+ *
+ * A scan processes windows [w_lo, w_hi) of the plan.  Column pointers address element
+ * `site_origin` of the global column (site_origin = 0 and the full window range for a
+ * single-GPU whole-genome call; the shard's site_lo otherwise).  Output arrays have
+ * w_hi - w_lo elements; any output pointer may be NULL.
+ */
+typedef struct {
+	uint64_t w_lo, w_hi;   /* window range; w_hi = 0 means "all windows" */
+	uint64_t site_origin;  /* global index of element 0 of the column pointers */
+} pgt_range;
+
+/* fstWindow.cpp:88 prints  chr start end mid fst nsites */
+typedef struct {
+	uint32_t* label;      /* contig index whose name is printed */
+	uint32_t* start_pos;  /* pos of first site */
+	uint32_t* end_pos;    /* pos of last site */
+	uint32_t* mid_pos;    /* (start+end)/2 in uint32 arithmetic (fstWindow.cpp:73) */
+	double* sum_a;
+	double* sum_b;
+	double* fst;          /* sum_b != 0 ? sum_a/sum_b : 0 (fstWindow.cpp:85) */
+	uint32_t* nsites;
+} pgt_fst_out;
+
+size_t pgt_scan_workspace_bytes(const pgt_plan* plan, const pgt_range* range);
+
+int pgt_scan_fst(const pgt_plan* plan, const pgt_range* range, const uint32_t* pos, const double* a,
+                 const double* b, const pgt_fst_out* out, void* workspace, size_t workspace_bytes, pgt_mem mem,
+                 void* stream);
+
+/* ---- synthetic inputs: on-device counter-based generator --------------- */
+/* Fills a[0..n), b[0..n) with the fst columns of global sites [site0, site0+n). Device pointers. */
+int pgt_synth_fst(uint64_t seed, uint64_t site0, uint64_t n, double* a, double* b, void* stream);
+int pgt_synth_het(uint64_t seed, uint64_t site0, uint64_t n, int8_t* geno, void* stream);
+int pgt_synth_dxy(uint64_t seed, uint64_t site0, uint64_t n, double* f1, double* f2, int32_t* n1, int32_t* n2,
+                  void* stream);
+/* pos[i] for global sites [site0, site0+n) given the genome's contig offsets (host array). */
+int pgt_synth_pos(uint64_t seed, uint64_t site0, uint64_t n, const uint64_t* contig_offsets, uint32_t ncontig,
+                  uint32_t density, uint32_t* pos, void* stream);
+
+/* number of kernels this library has launched in this process (bench.py's gpu_launches) */
+uint64_t pgt_kernel_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PGT_SCAN_H */

@@ -1,0 +1,14 @@
+"""popgenomicstools_b200 -- B200-native windowed site-statistic scan (fstWindow / hetWindow / dxyWindow hot path).
+
+Thin host layer over libpgtscan.so (hand-written sm_100a kernels behind the C ABI of
+include/pgt_scan.h).  Importing the package loads the shared library and fails loudly if it is
+not built; there is no CPU fallback anywhere in the product path.
+"""
+from . import _cabi
+from ._cabi import PgtError
+
+_cabi.load()
+
+from .scan import WindowPlan, fst_window, synth_fst, synth_pos  # noqa: E402
+
+__all__ = ["WindowPlan", "fst_window", "synth_fst", "synth_pos", "PgtError"]

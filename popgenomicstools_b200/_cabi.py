@@ -1,0 +1,91 @@
+"""ctypes binding of libpgtscan.so (include/pgt_scan.h).
+
+The shared library is built in-tree (popgenomicstools_b200/csrc/Makefile, or
+``__graft_entry__.build()``).  There is no Python/CPU fallback: a missing library raises
+ImportError here, and a missing CUDA device makes every scan call raise PgtError.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libpgtscan.so")
+
+PGT_OK, PGT_ERR_ARGS, PGT_ERR_CUDA, PGT_ERR_NOMEM, PGT_ERR_INPUT = 0, -1, -2, -3, -4
+PGT_MEM_DEVICE, PGT_MEM_HOST = 0, 1
+PGT_MODE_SITES, PGT_MODE_BP = 0, 1
+
+
+class PgtError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"libpgtscan error {code}: {msg}")
+        self.code = code
+
+
+class PgtRange(C.Structure):
+    _fields_ = [("w_lo", C.c_uint64), ("w_hi", C.c_uint64), ("site_origin", C.c_uint64)]
+
+
+class PgtFstOut(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in
+                ("label", "start_pos", "end_pos", "mid_pos", "sum_a", "sum_b", "fst", "nsites")]
+
+
+_u64p = C.POINTER(C.c_uint64)
+_u32p = C.POINTER(C.c_uint32)
+
+# name -> (restype, argtypes); every symbol include/pgt_scan.h declares
+PROTOTYPES = {
+    "pgt_last_error": (C.c_char_p, []),
+    "pgt_abi_version": (C.c_int, []),
+    "pgt_device_count": (C.c_int, []),
+    "pgt_set_device": (C.c_int, [C.c_int]),
+    "pgt_host_alloc": (C.c_int, [C.POINTER(C.c_void_p), C.c_size_t]),
+    "pgt_host_free": (C.c_int, [C.c_void_p]),
+    "pgt_plan_create": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32,
+                                  C.c_uint32]),
+    "pgt_plan_destroy": (None, [C.c_void_p]),
+    "pgt_plan_num_windows": (C.c_uint64, [C.c_void_p]),
+    "pgt_plan_num_units": (C.c_uint64, [C.c_void_p]),
+    "pgt_plan_num_segments": (C.c_uint32, [C.c_void_p]),
+    "pgt_plan_num_sites": (C.c_uint64, [C.c_void_p]),
+    "pgt_plan_window": (C.c_int, [C.c_void_p, C.c_uint64, _u64p, _u64p, _u32p]),
+    "pgt_plan_windows": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "pgt_plan_unit": (C.c_int, [C.c_void_p, C.c_uint64, _u64p, _u32p]),
+    "pgt_plan_window_units": (C.c_int, [C.c_void_p, C.c_uint64, _u64p, _u64p]),
+    "pgt_plan_shard": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, _u64p, _u64p, _u64p, _u64p]),
+    "pgt_scan_workspace_bytes": (C.c_size_t, [C.c_void_p, C.POINTER(PgtRange)]),
+    "pgt_scan_fst": (C.c_int, [C.c_void_p, C.POINTER(PgtRange), C.c_void_p, C.c_void_p, C.c_void_p,
+                               C.POINTER(PgtFstOut), C.c_void_p, C.c_size_t, C.c_int, C.c_void_p]),
+    "pgt_synth_fst": (C.c_int, [C.c_uint64, C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "pgt_synth_het": (C.c_int, [C.c_uint64, C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p]),
+    "pgt_synth_dxy": (C.c_int, [C.c_uint64, C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                C.c_void_p]),
+    "pgt_synth_pos": (C.c_int, [C.c_uint64, C.c_uint64, C.c_uint64, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p,
+                                C.c_void_p]),
+    "pgt_kernel_launch_count": (C.c_uint64, []),
+}
+
+_lib = None
+
+
+def load():
+    """Load libpgtscan.so (once) and attach prototypes.  Raises ImportError if it is not built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(
+                f"{LIB_PATH} is not built (run `make -C popgenomicstools_b200/csrc` or __graft_entry__.build()); "
+                "popgenomicstools_b200 has no CPU fallback")
+        lib = C.CDLL(LIB_PATH)
+        for name, (res, args) in PROTOTYPES.items():
+            fn = getattr(lib, name)  # AttributeError = header/library mismatch
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+    return _lib
+
+
+def check(rc):
+    if rc < 0:
+        raise PgtError(rc, load().pgt_last_error().decode(errors="replace"))
+    return rc
