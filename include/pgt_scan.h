@@ -124,27 +124,84 @@ int pgt_plan_shard(const pgt_plan* plan, uint32_t shard, uint32_t nshards, uint6
  * w_hi - w_lo elements; any output pointer may be NULL.
  */
 typedef struct {
-	uint64_t w_lo, w_hi;   /* window range; w_hi = 0 means "all windows" */
-	uint64_t site_origin;  /* global index of element 0 of the column pointers */
+	uint64_t w_lo, w_hi;   /* window range; w_lo = w_hi = 0 means "all windows" */
+	uint64_t site_origin;  /* global SITE index of element 0 of the column pointers */
+	uint64_t site_count;   /* elements the columns hold; 0 = up to the end of the genome.
+	                          Only consulted in PGT_MODE_BP (bounds the position searches). */
 } pgt_range;
 
-/* fstWindow.cpp:88 prints  chr start end mid fst nsites */
+typedef enum {
+	PGT_STAT_FST = 0,   /* fstWindow */
+	PGT_STAT_HET = 1,   /* hetWindow */
+	PGT_STAT_DXY = 2,   /* dxyWindow (-fixedsite 1: PGT_MODE_SITES plan; -fixedsite 0: PGT_MODE_BP plan) */
+	PGT_STAT_FUSED = 3  /* fst + dxy + het over one site axis in one pass (BASELINE config 5) */
+} pgt_stat;
+
+/* Input columns, one element per site; only the columns of the requested statistic are read.
+ *   pos        uint32  fstWindow.cpp:18 / hetWindow.cpp:18 / dxyWindow.cpp:26.  Gathered only at
+ *              window edges; may be NULL in PGT_MODE_SITES (positions are then not written).
+ *              Required in PGT_MODE_BP (it places sites on the bp axis; must be strictly
+ *              increasing within a chromosome and <= the chromosome length).
+ *   a, b       double  per-site FST numerator / denominator (fstWindow.cpp:19-20)
+ *   geno       int8    genotype 0/1/2, negative = missing (hetWindow.cpp:78-80; the parser
+ *              clamps wider ints: <0 -> -1, >127 -> 127)
+ *   f1,f2,n1,n2  allele frequency (double) and nInd (int32) of pop 1 / pop 2 at the synced
+ *              sites (dxyWindow.cpp:24-32,381) */
 typedef struct {
-	uint32_t* label;      /* contig index whose name is printed */
-	uint32_t* start_pos;  /* pos of first site */
-	uint32_t* end_pos;    /* pos of last site */
-	uint32_t* mid_pos;    /* (start+end)/2 in uint32 arithmetic (fstWindow.cpp:73) */
-	double* sum_a;
+	const uint32_t* pos;
+	const double* a;
+	const double* b;
+	const int8_t* geno;
+	const double* f1;
+	const double* f2;
+	const int32_t* n1;
+	const int32_t* n2;
+} pgt_columns;
+
+/* Per-window results (SoA, w_hi - w_lo elements each; any pointer may be NULL).
+ *   fstWindow.cpp:88   chr start end mid fst nsites
+ *   hetWindow.cpp:87   chr start last mid h nonmissing
+ *   dxyWindow.cpp:190  chr start end dxy neffective nskip   (+ global line, :429-433)
+ * -skip_missing 1 (dxyWindow.cpp:189) is a row filter `neffective > 0` for the caller. */
+typedef struct {
+	uint32_t* label;       /* contig index whose name is printed (contig of the last site) */
+	uint32_t* start_pos;   /* pos of first site (bp mode: first bp of the window) */
+	uint32_t* end_pos;     /* pos of last site  (bp mode: last bp of the window) */
+	uint32_t* mid_pos;     /* (start+end)/2 in uint32 arithmetic (fstWindow.cpp:73) */
+	uint32_t* nsites;      /* sites (entries) in the window */
+	double* sum_a;         /* fst */
 	double* sum_b;
-	double* fst;          /* sum_b != 0 ? sum_a/sum_b : 0 (fstWindow.cpp:85) */
-	uint32_t* nsites;
-} pgt_fst_out;
+	double* fst;           /* sum_b != 0 ? sum_a/sum_b : 0 (fstWindow.cpp:85) */
+	uint32_t* nhet;        /* het */
+	uint32_t* nonmissing;
+	double* het;           /* nonmissing ? nhet/nonmissing : 0 (hetWindow.cpp:84) */
+	double* dxy;           /* dxy: window SUM of per-site dxy (dxyWindow.cpp:179-186) */
+	uint32_t* neffective;
+	uint32_t* nskip;
+	double* dxy_global;    /* [3] = dxy_global, neffective_global, nskip_global over the units this
+	                          scan owns (all sites for an unsharded scan; dxyWindow.cpp:382-385) */
+} pgt_windows;
 
-size_t pgt_scan_workspace_bytes(const pgt_plan* plan, const pgt_range* range);
+/* Device scratch needed by a scan of `stat` over `range` with columns in `mem`. */
+size_t pgt_scan_workspace_bytes(const pgt_plan* plan, const pgt_range* range, pgt_stat stat, pgt_mem mem);
 
-int pgt_scan_fst(const pgt_plan* plan, const pgt_range* range, const uint32_t* pos, const double* a,
-                 const double* b, const pgt_fst_out* out, void* workspace, size_t workspace_bytes, pgt_mem mem,
-                 void* stream);
+/* The scan.  minind: dxyWindow -minind (ignored for fst/het).  site_offsets: PGT_MODE_BP only,
+ * host array [ncontig+1] of cumulative SITE counts per chromosome of the plan (global site
+ * indices, same origin convention as the columns); NULL in PGT_MODE_SITES. */
+int pgt_scan(const pgt_plan* plan, const pgt_range* range, pgt_stat stat, const pgt_columns* cols, int minind,
+             const uint64_t* site_offsets, const pgt_windows* out, void* workspace, size_t workspace_bytes,
+             pgt_mem mem, void* stream);
+
+/* Convenience entry points named after the tools they replace. */
+int pgt_scan_fst(const pgt_plan* plan, const pgt_range* range, const pgt_columns* cols, const pgt_windows* out,
+                 void* workspace, size_t workspace_bytes, pgt_mem mem, void* stream);
+int pgt_scan_het(const pgt_plan* plan, const pgt_range* range, const pgt_columns* cols, const pgt_windows* out,
+                 void* workspace, size_t workspace_bytes, pgt_mem mem, void* stream);
+int pgt_scan_dxy(const pgt_plan* plan, const pgt_range* range, const pgt_columns* cols, int minind,
+                 const uint64_t* site_offsets, const pgt_windows* out, void* workspace, size_t workspace_bytes,
+                 pgt_mem mem, void* stream);
+int pgt_scan_fused(const pgt_plan* plan, const pgt_range* range, const pgt_columns* cols, int minind,
+                   const pgt_windows* out, void* workspace, size_t workspace_bytes, pgt_mem mem, void* stream);
 
 /* ---- synthetic inputs: on-device counter-based generator --------------- */
 /* Fills a[0..n), b[0..n) with the fst columns of global sites [site0, site0+n). Device pointers. */

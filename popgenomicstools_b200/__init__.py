@@ -9,6 +9,8 @@ from ._cabi import PgtError
 
 _cabi.load()
 
-from .scan import WindowPlan, fst_window, synth_fst, synth_pos  # noqa: E402
+from .scan import (WindowPlan, dxy_window, fst_window, fused_window, het_window, kernel_launch_count, scan,  # noqa: E402
+                   synth_dxy, synth_fst, synth_het, synth_pos)
 
-__all__ = ["WindowPlan", "fst_window", "synth_fst", "synth_pos", "PgtError"]
+__all__ = ["WindowPlan", "scan", "fst_window", "het_window", "dxy_window", "fused_window", "synth_fst", "synth_het",
+           "synth_dxy", "synth_pos", "kernel_launch_count", "PgtError"]

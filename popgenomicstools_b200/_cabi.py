@@ -21,13 +21,24 @@ class PgtError(RuntimeError):
         self.code = code
 
 
+PGT_STAT_FST, PGT_STAT_HET, PGT_STAT_DXY, PGT_STAT_FUSED = 0, 1, 2, 3
+
+
 class PgtRange(C.Structure):
-    _fields_ = [("w_lo", C.c_uint64), ("w_hi", C.c_uint64), ("site_origin", C.c_uint64)]
+    _fields_ = [("w_lo", C.c_uint64), ("w_hi", C.c_uint64), ("site_origin", C.c_uint64), ("site_count", C.c_uint64)]
 
 
-class PgtFstOut(C.Structure):
-    _fields_ = [(n, C.c_void_p) for n in
-                ("label", "start_pos", "end_pos", "mid_pos", "sum_a", "sum_b", "fst", "nsites")]
+COLUMN_FIELDS = ("pos", "a", "b", "geno", "f1", "f2", "n1", "n2")
+WINDOW_FIELDS = ("label", "start_pos", "end_pos", "mid_pos", "nsites", "sum_a", "sum_b", "fst", "nhet", "nonmissing",
+                 "het", "dxy", "neffective", "nskip", "dxy_global")
+
+
+class PgtColumns(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in COLUMN_FIELDS]
+
+
+class PgtWindows(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in WINDOW_FIELDS]
 
 
 _u64p = C.POINTER(C.c_uint64)
@@ -53,9 +64,17 @@ PROTOTYPES = {
     "pgt_plan_unit": (C.c_int, [C.c_void_p, C.c_uint64, _u64p, _u32p]),
     "pgt_plan_window_units": (C.c_int, [C.c_void_p, C.c_uint64, _u64p, _u64p]),
     "pgt_plan_shard": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, _u64p, _u64p, _u64p, _u64p]),
-    "pgt_scan_workspace_bytes": (C.c_size_t, [C.c_void_p, C.POINTER(PgtRange)]),
-    "pgt_scan_fst": (C.c_int, [C.c_void_p, C.POINTER(PgtRange), C.c_void_p, C.c_void_p, C.c_void_p,
-                               C.POINTER(PgtFstOut), C.c_void_p, C.c_size_t, C.c_int, C.c_void_p]),
+    "pgt_scan_workspace_bytes": (C.c_size_t, [C.c_void_p, C.POINTER(PgtRange), C.c_int, C.c_int]),
+    "pgt_scan": (C.c_int, [C.c_void_p, C.POINTER(PgtRange), C.c_int, C.POINTER(PgtColumns), C.c_int, C.c_void_p,
+                           C.POINTER(PgtWindows), C.c_void_p, C.c_size_t, C.c_int, C.c_void_p]),
+    "pgt_scan_fst": (C.c_int, [C.c_void_p, C.POINTER(PgtRange), C.POINTER(PgtColumns), C.POINTER(PgtWindows),
+                               C.c_void_p, C.c_size_t, C.c_int, C.c_void_p]),
+    "pgt_scan_het": (C.c_int, [C.c_void_p, C.POINTER(PgtRange), C.POINTER(PgtColumns), C.POINTER(PgtWindows),
+                               C.c_void_p, C.c_size_t, C.c_int, C.c_void_p]),
+    "pgt_scan_dxy": (C.c_int, [C.c_void_p, C.POINTER(PgtRange), C.POINTER(PgtColumns), C.c_int, C.c_void_p,
+                               C.POINTER(PgtWindows), C.c_void_p, C.c_size_t, C.c_int, C.c_void_p]),
+    "pgt_scan_fused": (C.c_int, [C.c_void_p, C.POINTER(PgtRange), C.POINTER(PgtColumns), C.c_int,
+                                 C.POINTER(PgtWindows), C.c_void_p, C.c_size_t, C.c_int, C.c_void_p]),
     "pgt_synth_fst": (C.c_int, [C.c_uint64, C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p]),
     "pgt_synth_het": (C.c_int, [C.c_uint64, C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p]),
     "pgt_synth_dxy": (C.c_int, [C.c_uint64, C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,

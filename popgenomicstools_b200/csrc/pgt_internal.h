@@ -23,5 +23,11 @@ int pgt_set_error(int code, const std::string& msg);
 // segment index containing global window w / global unit j / global site x
 uint32_t pgt_plan_seg_of_window(const pgt_plan* p, uint64_t w);
 uint32_t pgt_plan_seg_of_unit(const pgt_plan* p, uint64_t j);
+// global index of the unit containing global site/entry x (x inside the axis)
+uint64_t pgt_plan_unit_containing(const pgt_plan* p, uint64_t x);
+// global site/entry index where global unit j starts; j == nunits gives the end of the axis
+uint64_t pgt_plan_unit_start(const pgt_plan* p, uint64_t j);
+// contig c with off[c] <= x < off[c+1]
+uint32_t pgt_plan_contig_of(const pgt_plan* p, uint64_t x);
 
 #endif

@@ -133,6 +133,26 @@ static uint32_t contig_of(const pgt_plan* p, uint64_t x) {
 	size_t c = std::upper_bound(p->off.begin(), p->off.end(), x) - p->off.begin();
 	return (uint32_t)(c - 1);
 }
+uint32_t pgt_plan_contig_of(const pgt_plan* p, uint64_t x) { return contig_of(p, x); }
+
+uint64_t pgt_plan_unit_containing(const pgt_plan* p, uint64_t x) {
+	uint32_t lo = 0, hi = (uint32_t)p->segs.size();
+	while (hi - lo > 1) {
+		uint32_t mid = lo + (hi - lo) / 2;
+		if (p->segs[mid].site_base <= x) lo = mid;
+		else hi = mid;
+	}
+	const pgt_seg& sg = p->segs[lo];
+	return sg.unit_base + pgt_unit_of_site(p->g, x - sg.site_base);
+}
+
+uint64_t pgt_plan_unit_start(const pgt_plan* p, uint64_t j) {
+	if (j >= p->nunits) return p->off[0] + p->nsites;
+	const pgt_seg& sg = p->segs[pgt_plan_seg_of_unit(p, j)];
+	uint64_t st;
+	pgt_unit_range(p->g, sg.nsites, j - sg.unit_base, &st);
+	return sg.site_base + st;
+}
 
 extern "C" int pgt_plan_window(const pgt_plan* p, uint64_t w, uint64_t* first, uint64_t* last, uint32_t* label) {
 	if (!p) return pgt_set_error(PGT_ERR_ARGS, "pgt_plan_window: plan is NULL");
@@ -214,13 +234,20 @@ extern "C" int pgt_plan_shard(const pgt_plan* p, uint32_t shard, uint32_t nshard
 	};
 	uint64_t lo = cut(shard), hi = cut(shard + 1);
 	if (hi < lo) hi = lo;
-	uint64_t slo = 0, shi = 0;
+	// Site range.  The shard holding window 0 also owns the axis head, the shard holding the last
+	// window also owns the tail outside any window (dropped EOF partial): those sites count
+	// towards dxyWindow's global line (dxyWindow.cpp:382-385).  Shards without windows hold nothing,
+	// except shard 0 of a plan without any window (it owns the whole axis).
+	const uint64_t end = origin + p->nsites;
+	uint64_t slo = end, shi = end;
 	if (hi > lo) {
 		uint64_t f, l;
 		pgt_plan_window(p, lo, &f, nullptr, nullptr);
 		pgt_plan_window(p, hi - 1, nullptr, &l, nullptr);
-		slo = f;
-		shi = l + 1;
+		slo = lo == 0 ? origin : f;
+		shi = hi == p->nwin ? end : l + 1;
+	} else if (p->nwin == 0 && shard == 0) {
+		slo = origin;
 	}
 	if (w_lo) *w_lo = lo;
 	if (w_hi) *w_hi = hi;

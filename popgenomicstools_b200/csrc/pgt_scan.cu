@@ -9,18 +9,25 @@
 //                              warp-shuffle butterfly) into one partial per *unit* (pgt_geom.h).
 //   level 2  k_windows<Stat> : every window is the sum of its consecutive unit partials (the
 //                              carry across overlapping windows: W/S-fold overlap costs re-reads
-//                              of 16-byte partials from L2, never of sites), plus the epilogue
+//                              of small partials from L2, never of sites), plus the epilogue
 //                              (ratio, position gather at the two window edges, label lookup).
+//   (dxy)    k_global<Stat>  : dxyWindow's global line from the same unit partials.
+//   (bp)     k_bp_bounds     : dxyWindow -fixedsite 0: the reference materialises one buffer entry
+//                              per bp (dxyWindow.cpp:365-372); here units live on the bp axis and
+//                              each unit's site range is found by binary search in `pos` (sparse,
+//                              O(#sites) instead of O(chromosome length)).
 //
 // There is no CPU fallback: every entry point fails with PGT_ERR_CUDA when no device is usable.
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <atomic>
+#include <cstddef>
 #include <cstdio>
 #include <cstring>
 #include <string>
+#include <vector>
 
-#include "../../include/pgt_synth.h"
 #include "pgt_internal.h"
 
 // ----------------------------------------------------------------------------- utilities
@@ -32,10 +39,15 @@ void pgt_count_launch() { g_launches++; }
 static int cuda_fail(cudaError_t e, const char* what) {
 	return pgt_set_error(PGT_ERR_CUDA, std::string(what) + ": " + cudaGetErrorName(e) + " (" + cudaGetErrorString(e) + ")");
 }
-#define PGT_CUDA(call)                                   \
-	do {                                                 \
-		cudaError_t e__ = (call);                        \
-		if (e__ != cudaSuccess) return cuda_fail(e__, #call); \
+#define PGT_CUDA(call)                                         \
+	do {                                                       \
+		cudaError_t e__ = (call);                              \
+		if (e__ != cudaSuccess) return cuda_fail(e__, #call);  \
+	} while (0)
+#define PGT_TRY(call)                    \
+	do {                                 \
+		int rc__ = (call);               \
+		if (rc__ != PGT_OK) return rc__; \
 	} while (0)
 
 extern "C" int pgt_device_count(void) {
@@ -58,27 +70,40 @@ extern "C" int pgt_host_free(void* p) {
 	return PGT_OK;
 }
 
-static int g_num_sms = 0;
 static int num_sms() {
-	if (g_num_sms == 0) {
-		int dev = 0;
-		if (cudaGetDevice(&dev) != cudaSuccess) return 0;
-		cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
-	}
-	return g_num_sms;
+	int dev = 0, n = 0;
+	if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+	cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+	return n;
 }
 
+static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
 // ----------------------------------------------------------------------------- device plan
+
+struct Cols {
+	const uint32_t* pos;
+	const double* a;
+	const double* b;
+	const int8_t* g;
+	const double* f1;
+	const double* f2;
+	const int32_t* n1;
+	const int32_t* n2;
+	int minind;
+};
 
 struct DevPlan {
 	pgt_geom g;
 	const pgt_seg* segs;
-	const uint64_t* off;  // contig offsets
+	const uint64_t* off;       // contig offsets on the plan axis (sites, or bp entries)
+	const uint64_t* site_off;  // bp mode: cumulative site counts per chromosome (global site indices)
 	uint32_t nseg;
 	uint32_t ncontig;
-	uint64_t unit_lo, unit_hi;  // global unit range of this scan
+	uint64_t unit_lo, unit_hi;  // global unit range reduced by this launch
 	uint64_t win_lo, win_hi;    // global window range of this scan
 	uint64_t site_origin;       // global index of element 0 of the columns
+	uint64_t nunits_total;
 	int mode;
 };
 
@@ -107,17 +132,16 @@ __device__ __forceinline__ uint32_t find_contig(const uint64_t* off, uint32_t c0
 }
 
 __device__ __forceinline__ double shfl_xor_f64(double v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }
+__device__ __forceinline__ uint32_t shfl_xor_u32(uint32_t v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }
 
 // ----------------------------------------------------------------------------- statistics
 //
-// A Stat describes: the input columns (In), the unit partial (Acc, stored as-is in the unit
-// array), how one site is folded into a lane's partial, and the butterfly combine.
+// A Stat describes: the per-site record loaded from the columns (Site), the unit partial (Acc,
+// stored as-is in the unit array), how one site is folded into a lane's partial (the per-site
+// statistic), the combine used by the butterflies, and the window epilogue.
 
+// --- fstWindow: asum += a; bsum += b (fstWindow.cpp:80-83); fst = bsum != 0 ? asum/bsum : 0 (:85)
 struct FstStat {
-	struct In {
-		const double* a;
-		const double* b;
-	};
 	struct Acc {
 		double a, b;
 	};
@@ -125,10 +149,8 @@ struct FstStat {
 		double a, b;
 	};
 	static __device__ __forceinline__ Acc zero() { return Acc{0.0, 0.0}; }
-	static __device__ __forceinline__ Site load(const In& in, uint64_t i) { return Site{__ldg(in.a + i), __ldg(in.b + i)}; }
-	static __device__ __forceinline__ Site none() { return Site{0.0, 0.0}; }
-	// fstWindow.cpp:80-83: asum += a; bsum += b  (plain adds; order is the unit tree)
-	static __device__ __forceinline__ void fold(Acc& acc, const Site& s) {
+	static __device__ __forceinline__ Site load(const Cols& c, uint64_t i) { return Site{__ldg(c.a + i), __ldg(c.b + i)}; }
+	static __device__ __forceinline__ void fold(Acc& acc, const Site& s, int) {
 		acc.a = __dadd_rn(acc.a, s.a);
 		acc.b = __dadd_rn(acc.b, s.b);
 	}
@@ -137,6 +159,114 @@ struct FstStat {
 		acc.b = __dadd_rn(acc.b, o.b);
 	}
 	static __device__ __forceinline__ Acc shfl_xor(const Acc& v, int m) { return Acc{shfl_xor_f64(v.a, m), shfl_xor_f64(v.b, m)}; }
+	static __device__ __forceinline__ void emit(const pgt_windows& out, uint64_t o, const Acc& acc) {
+		if (out.sum_a) out.sum_a[o] = acc.a;
+		if (out.sum_b) out.sum_b[o] = acc.b;
+		if (out.fst) out.fst[o] = acc.b != 0.0 ? __ddiv_rn(acc.a, acc.b) : 0.0;
+	}
+};
+
+// --- hetWindow: nonmissing += (g >= 0); nhet += (g == 1) (hetWindow.cpp:77-82); h = nhet/nonmissing (:84)
+struct HetStat {
+	struct Acc {
+		uint32_t nonmissing, nhet;
+	};
+	struct Site {
+		int g;
+	};
+	static __device__ __forceinline__ Acc zero() { return Acc{0u, 0u}; }
+	static __device__ __forceinline__ Site load(const Cols& c, uint64_t i) { return Site{(int)__ldg(c.g + i)}; }
+	static __device__ __forceinline__ void fold(Acc& acc, const Site& s, int) {
+		acc.nonmissing += (s.g >= 0);
+		acc.nhet += (s.g == 1);
+	}
+	static __device__ __forceinline__ void add(Acc& acc, const Acc& o) {
+		acc.nonmissing += o.nonmissing;
+		acc.nhet += o.nhet;
+	}
+	static __device__ __forceinline__ Acc shfl_xor(const Acc& v, int m) { return Acc{shfl_xor_u32(v.nonmissing, m), shfl_xor_u32(v.nhet, m)}; }
+	static __device__ __forceinline__ void emit(const pgt_windows& out, uint64_t o, const Acc& acc) {
+		if (out.nhet) out.nhet[o] = acc.nhet;
+		if (out.nonmissing) out.nonmissing[o] = acc.nonmissing;
+		if (out.het) out.het[o] = acc.nonmissing != 0 ? __ddiv_rn((double)acc.nhet, (double)acc.nonmissing) : 0.0;
+	}
+};
+
+// --- dxyWindow: per-site dxy (dxyWindow.cpp:381) with explicit non-fused IEEE ops so the value is
+// bit-identical to the x86-64 reference (no FMA there); window fold dxyWindow.cpp:179-186:
+// v >= 0 -> dxy += v, ++neffective; v == -9 -> ++nskip.
+__device__ __forceinline__ double dxy_site_value(double f1, double f2, int n1, int n2, int minind) {
+	return (n1 >= minind && n2 >= minind) ? __dadd_rn(__dmul_rn(f1, __dsub_rn(1.0, f2)), __dmul_rn(f2, __dsub_rn(1.0, f1))) : -9.0;
+}
+struct DxyStat {
+	struct Acc {
+		double dxy;
+		uint32_t neff, nskip;
+	};
+	struct Site {
+		double f1, f2;
+		int n1, n2;
+	};
+	static __device__ __forceinline__ Acc zero() { return Acc{0.0, 0u, 0u}; }
+	static __device__ __forceinline__ Site load(const Cols& c, uint64_t i) {
+		return Site{__ldg(c.f1 + i), __ldg(c.f2 + i), __ldg(c.n1 + i), __ldg(c.n2 + i)};
+	}
+	static __device__ __forceinline__ void fold(Acc& acc, const Site& s, int minind) {
+		const double v = dxy_site_value(s.f1, s.f2, s.n1, s.n2, minind);
+		if (v >= 0.0) {
+			acc.dxy = __dadd_rn(acc.dxy, v);
+			++acc.neff;
+		} else if (v == -9.0) {
+			++acc.nskip;
+		}
+	}
+	static __device__ __forceinline__ void add(Acc& acc, const Acc& o) {
+		acc.dxy = __dadd_rn(acc.dxy, o.dxy);
+		acc.neff += o.neff;
+		acc.nskip += o.nskip;
+	}
+	static __device__ __forceinline__ Acc shfl_xor(const Acc& v, int m) {
+		return Acc{shfl_xor_f64(v.dxy, m), shfl_xor_u32(v.neff, m), shfl_xor_u32(v.nskip, m)};
+	}
+	static __device__ __forceinline__ void emit(const pgt_windows& out, uint64_t o, const Acc& acc) {
+		if (out.dxy) out.dxy[o] = acc.dxy;
+		if (out.neffective) out.neffective[o] = acc.neff;
+		if (out.nskip) out.nskip[o] = acc.nskip;
+	}
+};
+
+// --- fused fst + dxy + het over one site axis (BASELINE config 5): one pass, 41 B/site
+struct FusedStat {
+	struct Acc {
+		FstStat::Acc fst;
+		DxyStat::Acc dxy;
+		HetStat::Acc het;
+	};
+	struct Site {
+		FstStat::Site fst;
+		DxyStat::Site dxy;
+		HetStat::Site het;
+	};
+	static __device__ __forceinline__ Acc zero() { return Acc{FstStat::zero(), DxyStat::zero(), HetStat::zero()}; }
+	static __device__ __forceinline__ Site load(const Cols& c, uint64_t i) { return Site{FstStat::load(c, i), DxyStat::load(c, i), HetStat::load(c, i)}; }
+	static __device__ __forceinline__ void fold(Acc& acc, const Site& s, int minind) {
+		FstStat::fold(acc.fst, s.fst, minind);
+		DxyStat::fold(acc.dxy, s.dxy, minind);
+		HetStat::fold(acc.het, s.het, minind);
+	}
+	static __device__ __forceinline__ void add(Acc& acc, const Acc& o) {
+		FstStat::add(acc.fst, o.fst);
+		DxyStat::add(acc.dxy, o.dxy);
+		HetStat::add(acc.het, o.het);
+	}
+	static __device__ __forceinline__ Acc shfl_xor(const Acc& v, int m) {
+		return Acc{FstStat::shfl_xor(v.fst, m), DxyStat::shfl_xor(v.dxy, m), HetStat::shfl_xor(v.het, m)};
+	}
+	static __device__ __forceinline__ void emit(const pgt_windows& out, uint64_t o, const Acc& acc) {
+		FstStat::emit(out, o, acc.fst);
+		DxyStat::emit(out, o, acc.dxy);
+		HetStat::emit(out, o, acc.het);
+	}
 };
 
 template <class Stat>
@@ -148,11 +278,12 @@ __device__ __forceinline__ typename Stat::Acc warp_butterfly(typename Stat::Acc 
 
 // ----------------------------------------------------------------------------- level 1
 
-// One warp per unit, persistent grid-stride over the scan's unit range.  Lane l folds sites
-// l, l+32, l+64, ... of the unit in that order (all loads of a unit are issued before the
-// first add: UPL independent 8-byte loads per column per lane in flight), then the butterfly.
-template <class Stat, int UPL>
-__global__ void __launch_bounds__(256) k_units(DevPlan P, typename Stat::In in, typename Stat::Acc* __restrict__ units) {
+// One warp per unit, persistent grid-stride over the launch's unit range.  Lane l folds sites
+// l, l+32, l+64, ... of the unit in that order (all loads of a unit are issued before the first
+// fold: UPL independent loads per column per lane in flight), then the butterfly.
+// INDIRECT (bp mode): the unit's site range comes from `bounds` instead of the closed form.
+template <class Stat, int UPL, bool INDIRECT>
+__global__ void __launch_bounds__(256) k_units(DevPlan P, Cols cols, typename Stat::Acc* __restrict__ units, const uint64_t* __restrict__ bounds) {
 	const uint32_t lane = threadIdx.x & 31u;
 	const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
 	const uint64_t nwarp = ((uint64_t)gridDim.x * blockDim.x) >> 5;
@@ -161,100 +292,229 @@ __global__ void __launch_bounds__(256) k_units(DevPlan P, typename Stat::In in, 
 	sg.unit_base = 0;
 	sg.nunits = 0;
 	for (uint64_t j = P.unit_lo + warp; j < P.unit_hi; j += nwarp) {
-		if (si == 0xffffffffu || j - sg.unit_base >= sg.nunits) {
-			si = find_seg<true>(P, j);
-			sg = P.segs[si];
+		uint64_t i0;
+		uint32_t len;
+		if (INDIRECT) {
+			const uint64_t b0 = bounds[j - P.unit_lo], b1 = bounds[j - P.unit_lo + 1];
+			i0 = b0 + lane;
+			len = (uint32_t)(b1 - b0);
+		} else {
+			if (si == 0xffffffffu || j - sg.unit_base >= sg.nunits) {
+				si = find_seg<true>(P, j);
+				sg = P.segs[si];
+			}
+			uint64_t st;
+			len = pgt_unit_range(P.g, sg.nsites, j - sg.unit_base, &st);
+			i0 = sg.site_base + st - P.site_origin + lane;
 		}
-		uint64_t st;
-		const uint32_t len = pgt_unit_range(P.g, sg.nsites, j - sg.unit_base, &st);
-		const uint64_t i0 = sg.site_base + st - P.site_origin + lane;
 		typename Stat::Acc acc = Stat::zero();
-		if (UPL > 0) {
+		if (UPL > 0 && len <= 32u * UPL) {
 			typename Stat::Site v[UPL > 0 ? UPL : 1];
 #pragma unroll
-			for (int t = 0; t < UPL; ++t) v[t] = (lane + 32u * t < len) ? Stat::load(in, i0 + 32u * t) : Stat::none();
+			for (int t = 0; t < UPL; ++t)
+				if (lane + 32u * t < len) v[t] = Stat::load(cols, i0 + 32u * t);
 #pragma unroll
-			for (int t = 0; t < UPL; ++t) Stat::fold(acc, v[t]);
+			for (int t = 0; t < UPL; ++t)
+				if (lane + 32u * t < len) Stat::fold(acc, v[t], cols.minind);
 		} else {
-			for (uint32_t x = lane; x < len; x += 32u) Stat::fold(acc, Stat::load(in, i0 + (x - lane)));
+			for (uint32_t x = lane; x < len; x += 32u) Stat::fold(acc, Stat::load(cols, i0 + (x - lane)), cols.minind);
 		}
 		acc = warp_butterfly<Stat>(acc);
 		if (lane == 0) units[j - P.unit_lo] = acc;
 	}
 }
 
-// ----------------------------------------------------------------------------- level 2
+// bp mode: bounds[t] = index (relative to the columns' element 0) of the first site at or after
+// the first bp of unit unit_lo+t, t in [0, unit_hi-unit_lo]; the unit's bp -> (chromosome, pos) is
+// closed form, the site is a lower_bound in that chromosome's slice of `pos`.
+__global__ void __launch_bounds__(256) k_bp_bounds(DevPlan P, const uint32_t* __restrict__ pos, uint64_t ndata, uint64_t* __restrict__ bounds) {
+	const uint64_t nb = P.unit_hi - P.unit_lo + 1;
+	const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+	for (uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; t < nb; t += stride) {
+		const uint64_t j = P.unit_lo + t;
+		uint64_t res;
+		if (j >= P.nunits_total) {
+			res = P.site_off[P.ncontig];
+		} else {
+			const pgt_seg sg = P.segs[find_seg<true>(P, j)];
+			uint64_t st;
+			pgt_unit_range(P.g, sg.nsites, j - sg.unit_base, &st);
+			const uint64_t e = sg.site_base + st;  // global bp entry
+			const uint32_t c = find_contig(P.off, sg.first_contig, sg.ncontig, e);
+			const uint32_t p = (uint32_t)(e - P.off[c]) + 1u;  // 1-based position on chromosome c
+			uint64_t lo = P.site_off[c], hi = P.site_off[c + 1];
+			// clip to the sites this call holds
+			if (lo < P.site_origin) lo = P.site_origin;
+			if (hi > P.site_origin + ndata) hi = P.site_origin + ndata;
+			if (hi < lo) hi = lo;
+			while (lo < hi) {
+				const uint64_t mid = lo + ((hi - lo) >> 1);
+				if (__ldg(pos + (mid - P.site_origin)) < p) lo = mid + 1;
+				else hi = mid;
+			}
+			res = lo;
+		}
+		if (res < P.site_origin) res = P.site_origin;
+		if (res > P.site_origin + ndata) res = P.site_origin + ndata;
+		bounds[t] = res - P.site_origin;
+	}
+}
 
-struct WinInfo {
-	uint64_t first, last;  // global site (entry) indices, inclusive
-	uint32_t nsites;
-	uint32_t label;
-};
+// ----------------------------------------------------------------------------- level 2
 
 // One warp per window: lane l adds unit partials l, l+32, ... (from +0.0, so a window of
 // -0.0 values sums to +0.0 exactly as the reference's `double asum = 0`), then the butterfly.
+// units_base = global index of units[0].
 template <class Stat>
-__device__ __forceinline__ typename Stat::Acc window_reduce(const DevPlan& P, const typename Stat::Acc* __restrict__ units, uint64_t w,
-                                                            uint32_t lane, WinInfo* wi) {
-	const uint32_t si = find_seg<false>(P, w);
-	const pgt_seg sg = P.segs[si];
-	const uint64_t k = w - sg.win_base;
-	uint64_t fu;
-	const uint64_t cnt = pgt_window_units(P.g, sg, k, &fu);
-	const typename Stat::Acc* up = units + (sg.unit_base + fu - P.unit_lo);
-	typename Stat::Acc acc = Stat::zero();
-	for (uint64_t x = lane; x < cnt; x += 32u) Stat::add(acc, up[x]);
-	acc = warp_butterfly<Stat>(acc);
-	uint64_t fs;
-	wi->nsites = pgt_window_sites(P.g, sg, k, &fs);
-	wi->first = sg.site_base + fs;
-	wi->last = wi->first + wi->nsites - 1;
-	wi->label = find_contig(P.off, sg.first_contig, sg.ncontig, wi->last);
-	return acc;
-}
-
-__global__ void __launch_bounds__(256) k_windows_fst(DevPlan P, const FstStat::Acc* __restrict__ units, const uint32_t* __restrict__ pos,
-                                                      pgt_fst_out out) {
+__global__ void __launch_bounds__(256) k_windows(DevPlan P, const typename Stat::Acc* __restrict__ units, uint64_t units_base,
+                                                  const uint32_t* __restrict__ pos, pgt_windows out) {
 	const uint32_t lane = threadIdx.x & 31u;
 	const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
 	const uint64_t nwarp = ((uint64_t)gridDim.x * blockDim.x) >> 5;
 	for (uint64_t w = P.win_lo + warp; w < P.win_hi; w += nwarp) {
-		WinInfo wi;
-		FstStat::Acc acc = window_reduce<FstStat>(P, units, w, lane, &wi);
+		const pgt_seg sg = P.segs[find_seg<false>(P, w)];
+		const uint64_t k = w - sg.win_base;
+		uint64_t fu;
+		const uint64_t cnt = pgt_window_units(P.g, sg, k, &fu);
+		const typename Stat::Acc* up = units + (sg.unit_base + fu - units_base);
+		typename Stat::Acc acc = Stat::zero();
+		for (uint64_t x = lane; x < cnt; x += 32u) Stat::add(acc, up[x]);
+		acc = warp_butterfly<Stat>(acc);
 		if (lane == 0) {
 			const uint64_t o = w - P.win_lo;
-			if (out.label) out.label[o] = wi.label;
-			if (pos) {
-				// fstWindow.cpp:71-73 (uint32 arithmetic for the midpoint)
-				const uint32_t sp = pos[wi.first - P.site_origin], ep = pos[wi.last - P.site_origin];
+			uint64_t fs;
+			const uint32_t nsites = pgt_window_sites(P.g, sg, k, &fs);
+			const uint64_t first = sg.site_base + fs, last = first + nsites - 1;
+			const uint32_t label = find_contig(P.off, sg.first_contig, sg.ncontig, last);
+			if (out.label) out.label[o] = label;
+			if (out.nsites) out.nsites[o] = nsites;
+			uint32_t sp = 0, ep = 0;
+			bool have = false;
+			if (P.mode == PGT_MODE_BP) {
+				// dxyWindow.cpp:190 prints the bp position of the first / last buffer entry
+				const uint32_t cf = find_contig(P.off, sg.first_contig, sg.ncontig, first);
+				sp = (uint32_t)(first - P.off[cf]) + 1u;
+				ep = (uint32_t)(last - P.off[label]) + 1u;
+				have = true;
+			} else if (pos) {
+				sp = __ldg(pos + (first - P.site_origin));
+				ep = __ldg(pos + (last - P.site_origin));
+				have = true;
+			}
+			if (have) {
 				if (out.start_pos) out.start_pos[o] = sp;
 				if (out.end_pos) out.end_pos[o] = ep;
-				if (out.mid_pos) out.mid_pos[o] = (sp + ep) / 2u;
+				if (out.mid_pos) out.mid_pos[o] = (sp + ep) / 2u;  // uint32 arithmetic, fstWindow.cpp:73
 			}
-			if (out.sum_a) out.sum_a[o] = acc.a;
-			if (out.sum_b) out.sum_b[o] = acc.b;
-			if (out.fst) out.fst[o] = acc.b != 0.0 ? __ddiv_rn(acc.a, acc.b) : 0.0;  // fstWindow.cpp:85
-			if (out.nsites) out.nsites[o] = wi.nsites;
+			Stat::emit(out, o, acc);
+		}
+	}
+}
+
+// dxyWindow's global line (dxyWindow.cpp:382-385,429-433) over the unit partials [0, n): one
+// block; thread t adds partials t, t+1024, ...; warp butterflies; counts in 64 bit.
+template <class Stat>
+struct GlobalOf;
+template <>
+struct GlobalOf<DxyStat> {
+	static __device__ __forceinline__ const DxyStat::Acc& get(const DxyStat::Acc& a) { return a; }
+};
+template <>
+struct GlobalOf<FusedStat> {
+	static __device__ __forceinline__ const DxyStat::Acc& get(const FusedStat::Acc& a) { return a.dxy; }
+};
+
+template <class Stat>
+__global__ void __launch_bounds__(1024) k_global(const typename Stat::Acc* __restrict__ units, uint64_t n, double* __restrict__ global3) {
+	__shared__ double s_d[32];
+	__shared__ unsigned long long s_e[32], s_k[32];
+	double d = 0.0;
+	unsigned long long ne = 0, nk = 0;
+	for (uint64_t i = threadIdx.x; i < n; i += 1024u) {
+		const DxyStat::Acc& a = GlobalOf<Stat>::get(units[i]);
+		d = __dadd_rn(d, a.dxy);
+		ne += a.neff;
+		nk += a.nskip;
+	}
+#pragma unroll
+	for (int m = 16; m >= 1; m >>= 1) {
+		d = __dadd_rn(d, shfl_xor_f64(d, m));
+		ne += __shfl_xor_sync(0xffffffffu, ne, m);
+		nk += __shfl_xor_sync(0xffffffffu, nk, m);
+	}
+	if ((threadIdx.x & 31u) == 0) {
+		s_d[threadIdx.x >> 5] = d;
+		s_e[threadIdx.x >> 5] = ne;
+		s_k[threadIdx.x >> 5] = nk;
+	}
+	__syncthreads();
+	if (threadIdx.x < 32) {
+		d = s_d[threadIdx.x];
+		ne = s_e[threadIdx.x];
+		nk = s_k[threadIdx.x];
+#pragma unroll
+		for (int m = 16; m >= 1; m >>= 1) {
+			d = __dadd_rn(d, shfl_xor_f64(d, m));
+			ne += __shfl_xor_sync(0xffffffffu, ne, m);
+			nk += __shfl_xor_sync(0xffffffffu, nk, m);
+		}
+		if (threadIdx.x == 0) {
+			global3[0] = d;
+			global3[1] = (double)ne;
+			global3[2] = (double)nk;
 		}
 	}
 }
 
 // ----------------------------------------------------------------------------- host side of a scan
 
-static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+static const uint64_t kSlabSites = 1ull << 22;  // PGT_MEM_HOST: sites (entries) staged per slab
+static const uint64_t kSlabSlack = 8192;         // >= 2 units
 
-struct ScanCtx {
-	DevPlan P;
-	char* ws;          // device workspace
-	size_t units_off;  // byte offset of the unit array
-	uint64_t nunits, nwin;
+struct ColDesc {
+	const void* ptr;        // host pointer (PGT_MEM_HOST) or device pointer
+	size_t elem;            // bytes per site
+	size_t offset_in_cols;  // byte offset of the pointer member inside Cols
 };
 
-static const size_t kMaxAccBytes = 48;  // largest Stat::Acc (fused)
+// the columns a statistic reads, in staging order; `c` may be NULL (sizing only)
+static int stat_columns(pgt_stat stat, pgt_mode mode, const pgt_columns* c, ColDesc* d) {
+	int n = 0;
+	auto put = [&](const void* p, size_t e, size_t off) { d[n++] = ColDesc{p, e, off}; };
+	if (mode == PGT_MODE_BP) put(c ? c->pos : nullptr, 4, offsetof(Cols, pos));
+	if (stat == PGT_STAT_FST || stat == PGT_STAT_FUSED) {
+		put(c ? c->a : nullptr, 8, offsetof(Cols, a));
+		put(c ? c->b : nullptr, 8, offsetof(Cols, b));
+	}
+	if (stat == PGT_STAT_DXY || stat == PGT_STAT_FUSED) {
+		put(c ? c->f1 : nullptr, 8, offsetof(Cols, f1));
+		put(c ? c->f2 : nullptr, 8, offsetof(Cols, f2));
+		put(c ? c->n1 : nullptr, 4, offsetof(Cols, n1));
+		put(c ? c->n2 : nullptr, 4, offsetof(Cols, n2));
+	}
+	if (stat == PGT_STAT_HET || stat == PGT_STAT_FUSED) put(c ? c->geno : nullptr, 1, offsetof(Cols, g));
+	return n;
+}
 
-static int resolve_range(const pgt_plan* plan, const pgt_range* range, uint64_t* w_lo, uint64_t* w_hi, uint64_t* u_lo,
-                         uint64_t* u_hi, uint64_t* origin) {
+static size_t acc_bytes(pgt_stat stat) {
+	switch (stat) {
+		case PGT_STAT_FST: return sizeof(FstStat::Acc);
+		case PGT_STAT_HET: return sizeof(HetStat::Acc);
+		case PGT_STAT_DXY: return sizeof(DxyStat::Acc);
+		default: return sizeof(FusedStat::Acc);
+	}
+}
+
+struct Layout {
+	uint64_t w_lo, w_hi, u_lo, u_hi, g_hi, origin;
+	size_t segs_off, off_off, siteoff_off, units_off, bounds_off, stage_off, outs_off, total;
+	size_t stage_col_bytes[8];
+	uint64_t slab_sites;
+};
+
+static int make_layout(const pgt_plan* plan, const pgt_range* range, pgt_stat stat, pgt_mem mem, Layout* L) {
 	if (!plan) return pgt_set_error(PGT_ERR_ARGS, "plan is NULL");
+	if ((int)stat < 0 || (int)stat > (int)PGT_STAT_FUSED) return pgt_set_error(PGT_ERR_ARGS, "unknown statistic");
 	uint64_t lo = 0, hi = plan->nwin, org = plan->off[0];
 	if (range) {
 		if (range->w_hi != 0 || range->w_lo != 0) {
@@ -264,109 +524,407 @@ static int resolve_range(const pgt_plan* plan, const pgt_range* range, uint64_t*
 		org = range->site_origin;
 	}
 	if (lo > hi || hi > plan->nwin) return pgt_set_error(PGT_ERR_ARGS, "window range out of bounds");
-	*w_lo = lo;
-	*w_hi = hi;
-	*origin = org;
-	*u_lo = *u_hi = 0;
-	if (hi > lo) {
-		uint64_t f, c;
-		pgt_plan_window_units(plan, lo, &f, &c);
-		*u_lo = f;
-		pgt_plan_window_units(plan, hi - 1, &f, &c);
-		*u_hi = f + c;
-		uint64_t fs;
-		pgt_plan_window(plan, lo, &fs, nullptr, nullptr);
-		if (fs < org) return pgt_set_error(PGT_ERR_ARGS, "site_origin lies after the first site of the window range");
+	memset(L, 0, sizeof(*L));
+	L->w_lo = lo;
+	L->w_hi = hi;
+	L->origin = org;
+	uint64_t f, c;
+	// units reduced: from the first unit of window w_lo (axis head for w_lo == 0) to the last unit
+	// of window w_hi-1 (axis tail for w_hi == nwin); units owned for the global line end where
+	// the next shard's first window starts.
+	if (hi == lo && plan->nwin != 0) {
+		L->u_lo = L->u_hi = L->g_hi = 0;
+	} else {
+		if (lo == 0) L->u_lo = 0;
+		else {
+			pgt_plan_window_units(plan, lo, &f, &c);
+			L->u_lo = f;
+		}
+		if (hi == plan->nwin) L->u_hi = L->g_hi = plan->nunits;
+		else {
+			pgt_plan_window_units(plan, hi - 1, &f, &c);
+			L->u_hi = f + c;
+			pgt_plan_window_units(plan, hi, &f, &c);
+			L->g_hi = f;
+		}
 	}
+	const uint64_t nunits = L->u_hi - L->u_lo;
+	size_t o = 0;
+	L->segs_off = o;
+	o += align_up(plan->segs.size() * sizeof(pgt_seg) + 8, 256);
+	L->off_off = o;
+	o += align_up(plan->off.size() * sizeof(uint64_t), 256);
+	L->siteoff_off = o;
+	if (plan->mode == PGT_MODE_BP) o += align_up(plan->off.size() * sizeof(uint64_t), 256);
+	L->units_off = o;
+	o += align_up((size_t)nunits * acc_bytes(stat) + 8, 256);
+	L->bounds_off = o;
+	if (plan->mode == PGT_MODE_BP) o += align_up((size_t)(nunits + 1) * sizeof(uint64_t), 256);
+	L->stage_off = o;
+	L->outs_off = o;
+	if (mem == PGT_MEM_HOST) {
+		L->slab_sites = std::min<uint64_t>(kSlabSites, std::max<uint64_t>(plan->nsites, 1)) + kSlabSlack;
+		ColDesc d[8];
+		const int nc = stat_columns(stat, plan->mode, nullptr, d);
+		for (int i = 0; i < nc; ++i) L->stage_col_bytes[i] = align_up((size_t)L->slab_sites * d[i].elem, 256);
+		for (int s = 0; s < 2; ++s)
+			for (int i = 0; i < nc; ++i) o += L->stage_col_bytes[i];
+		L->outs_off = o;
+		o += 12 * align_up((size_t)(hi - lo) * 8 + 8, 256);  // staged per-window outputs + global[3]
+	}
+	L->total = o + 256;
 	return PGT_OK;
 }
 
-extern "C" size_t pgt_scan_workspace_bytes(const pgt_plan* plan, const pgt_range* range) {
-	uint64_t wl, wh, ul, uh, org;
-	if (resolve_range(plan, range, &wl, &wh, &ul, &uh, &org) != PGT_OK) return 0;
-	size_t b = 0;
-	b += align_up(plan->segs.size() * sizeof(pgt_seg), 256);
-	b += align_up(plan->off.size() * sizeof(uint64_t), 256);
-	b += align_up((size_t)(uh - ul) * kMaxAccBytes, 256);
-	return b + 256;
+extern "C" size_t pgt_scan_workspace_bytes(const pgt_plan* plan, const pgt_range* range, pgt_stat stat, pgt_mem mem) {
+	Layout L;
+	if (make_layout(plan, range, stat, mem, &L) != PGT_OK) return 0;
+	return L.total;
 }
 
-// Uploads the plan tables to the head of the workspace and fills ctx.
-static int begin_scan(const pgt_plan* plan, const pgt_range* range, void* workspace, size_t workspace_bytes, cudaStream_t st,
-                      ScanCtx* ctx) {
-	uint64_t wl, wh, ul, uh, org;
-	int rc = resolve_range(plan, range, &wl, &wh, &ul, &uh, &org);
-	if (rc != PGT_OK) return rc;
-	int ndev = 0;
-	cudaError_t e = cudaGetDeviceCount(&ndev);
-	if (e != cudaSuccess || ndev == 0) return pgt_set_error(PGT_ERR_CUDA, "no usable CUDA device (this library has no CPU fallback)");
-	if (!workspace) return pgt_set_error(PGT_ERR_ARGS, "workspace is NULL");
-	if (workspace_bytes < pgt_scan_workspace_bytes(plan, range)) return pgt_set_error(PGT_ERR_NOMEM, "workspace too small, see pgt_scan_workspace_bytes");
-	char* ws = (char*)workspace;
-	size_t o = 0;
-	const size_t seg_bytes = plan->segs.size() * sizeof(pgt_seg);
-	const size_t off_bytes = plan->off.size() * sizeof(uint64_t);
-	if (seg_bytes) PGT_CUDA(cudaMemcpyAsync(ws + o, plan->segs.data(), seg_bytes, cudaMemcpyHostToDevice, st));
-	ctx->P.segs = (const pgt_seg*)(ws + o);
-	o += align_up(seg_bytes, 256);
-	PGT_CUDA(cudaMemcpyAsync(ws + o, plan->off.data(), off_bytes, cudaMemcpyHostToDevice, st));
-	ctx->P.off = (const uint64_t*)(ws + o);
-	o += align_up(off_bytes, 256);
-	ctx->P.g = plan->g;
-	ctx->P.nseg = (uint32_t)plan->segs.size();
-	ctx->P.ncontig = (uint32_t)plan->off.size() - 1;
-	ctx->P.unit_lo = ul;
-	ctx->P.unit_hi = uh;
-	ctx->P.win_lo = wl;
-	ctx->P.win_hi = wh;
-	ctx->P.site_origin = org;
-	ctx->P.mode = (int)plan->mode;
-	ctx->ws = ws;
-	ctx->units_off = o;
-	ctx->nunits = uh - ul;
-	ctx->nwin = wh - wl;
+template <class Stat>
+static int launch_units(const DevPlan& P, const Cols& cols, typename Stat::Acc* units, const uint64_t* bounds, cudaStream_t st) {
+	const uint64_t nunits = P.unit_hi - P.unit_lo;
+	if (nunits == 0) return PGT_OK;
+	const int threads = 256;
+	const uint64_t want = (nunits + 7) / 8;  // one warp per unit, 8 warps per block
+	const uint32_t upl = P.g.u / 32u;
+	void (*kern)(DevPlan, Cols, typename Stat::Acc*, const uint64_t*);
+	if (bounds) kern = upl == 8 ? k_units<Stat, 8, true> : k_units<Stat, 0, true>;
+	else kern = upl == 8 ? k_units<Stat, 8, false> : (upl == 4 ? k_units<Stat, 4, false> : k_units<Stat, 0, false>);
+	int per_sm = 0;
+	PGT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, 0));
+	const uint64_t cap = (uint64_t)num_sms() * (per_sm > 0 ? per_sm : 1);
+	const unsigned grid = (unsigned)(want < cap ? want : cap);
+	kern<<<grid, threads, 0, st>>>(P, cols, units, bounds);
+	g_launches++;
+	PGT_CUDA(cudaGetLastError());
+	return PGT_OK;
+}
+
+static int launch_bounds_kernel(const DevPlan& P, const uint32_t* pos, uint64_t ndata, uint64_t* bounds, cudaStream_t st) {
+	const uint64_t nb = P.unit_hi - P.unit_lo + 1;
+	const uint64_t want = (nb + 255) / 256;
+	const uint64_t cap = (uint64_t)num_sms() * 8;
+	k_bp_bounds<<<(unsigned)(want < cap ? want : cap), 256, 0, st>>>(P, pos, ndata, bounds);
+	g_launches++;
+	PGT_CUDA(cudaGetLastError());
 	return PGT_OK;
 }
 
 template <class Stat>
-static int launch_units(const ScanCtx& c, typename Stat::In in, cudaStream_t st) {
-	if (c.nunits == 0) return PGT_OK;
-	typename Stat::Acc* units = (typename Stat::Acc*)(c.ws + c.units_off);
-	const int threads = 256;
-	const uint64_t want = (c.nunits + 7) / 8;  // one warp per unit, 8 warps per block
-	int per_sm = 0;
-	const uint32_t upl = c.P.g.u / 32u;
-	void (*kern)(DevPlan, typename Stat::In, typename Stat::Acc*) = upl == 8 ? k_units<Stat, 8> : (upl == 4 ? k_units<Stat, 4> : k_units<Stat, 0>);
-	PGT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, 0));
-	uint64_t cap = (uint64_t)num_sms() * (per_sm > 0 ? per_sm : 1);
-	const unsigned grid = (unsigned)(want < cap ? want : cap);
-	kern<<<grid, threads, 0, st>>>(c.P, in, units);
+static int launch_windows(const DevPlan& P, const typename Stat::Acc* units, uint64_t units_base, const uint32_t* pos,
+                          const pgt_windows& out, cudaStream_t st) {
+	const uint64_t nwin = P.win_hi - P.win_lo;
+	if (nwin == 0) return PGT_OK;
+	const uint64_t want = (nwin + 7) / 8;
+	const uint64_t cap = (uint64_t)num_sms() * 8;
+	k_windows<Stat><<<(unsigned)(want < cap ? want : cap), 256, 0, st>>>(P, units, units_base, pos, out);
 	g_launches++;
 	PGT_CUDA(cudaGetLastError());
 	return PGT_OK;
 }
 
-static unsigned window_grid(const ScanCtx& c, int per_sm_hint) {
-	const uint64_t want = (c.nwin + 7) / 8;
-	const uint64_t cap = (uint64_t)num_sms() * per_sm_hint;
-	return (unsigned)(want < cap ? want : cap);
+template <class Stat>
+static int launch_global(const typename Stat::Acc*, uint64_t, double*, cudaStream_t) {
+	return PGT_OK;
+}
+template <>
+int launch_global<DxyStat>(const DxyStat::Acc* units, uint64_t n, double* g3, cudaStream_t st) {
+	k_global<DxyStat><<<1, 1024, 0, st>>>(units, n, g3);
+	g_launches++;
+	PGT_CUDA(cudaGetLastError());
+	return PGT_OK;
+}
+template <>
+int launch_global<FusedStat>(const FusedStat::Acc* units, uint64_t n, double* g3, cudaStream_t st) {
+	k_global<FusedStat><<<1, 1024, 0, st>>>(units, n, g3);
+	g_launches++;
+	PGT_CUDA(cudaGetLastError());
+	return PGT_OK;
 }
 
-extern "C" int pgt_scan_fst(const pgt_plan* plan, const pgt_range* range, const uint32_t* pos, const double* a, const double* b,
-                            const pgt_fst_out* out, void* workspace, size_t workspace_bytes, pgt_mem mem, void* stream) {
-	if (!a || !b || !out) return pgt_set_error(PGT_ERR_ARGS, "pgt_scan_fst: a, b and out must not be NULL");
-	if (mem != PGT_MEM_DEVICE) return pgt_set_error(PGT_ERR_ARGS, "pgt_scan_fst: PGT_MEM_HOST not implemented yet");
-	if (plan && plan->mode != PGT_MODE_SITES) return pgt_set_error(PGT_ERR_ARGS, "pgt_scan_fst: plan must be PGT_MODE_SITES");
+// host-side lower bound of bp entry e on the site axis (bp mode, PGT_MEM_HOST)
+static uint64_t host_site_lower_bound(const pgt_plan* plan, const uint64_t* site_off, const uint32_t* pos, uint64_t origin,
+                                      uint64_t ndata, uint64_t e) {
+	const uint32_t nc = (uint32_t)plan->off.size() - 1;
+	uint64_t res;
+	if (e >= plan->off[nc]) {
+		res = site_off[nc];
+	} else {
+		const uint32_t c = pgt_plan_contig_of(plan, e);
+		const uint32_t p = (uint32_t)(e - plan->off[c]) + 1u;
+		uint64_t lo = std::max(site_off[c], origin), hi = std::min(site_off[c + 1], origin + ndata);
+		if (hi < lo) hi = lo;
+		const uint32_t* b = pos + (lo - origin);
+		res = lo + (uint64_t)(std::lower_bound(b, pos + (hi - origin), p) - b);
+	}
+	return std::min(std::max(res, origin), origin + ndata);
+}
+
+struct HostStreams {
+	cudaStream_t copy = nullptr;
+	cudaEvent_t ready[2] = {nullptr, nullptr};
+	cudaEvent_t freed[2] = {nullptr, nullptr};
+	~HostStreams() {
+		for (int i = 0; i < 2; ++i) {
+			if (ready[i]) cudaEventDestroy(ready[i]);
+			if (freed[i]) cudaEventDestroy(freed[i]);
+		}
+		if (copy) cudaStreamDestroy(copy);
+	}
+};
+
+template <class Stat>
+static int run_scan(const pgt_plan* plan, const pgt_range* range, pgt_stat stat, const pgt_columns* cols, int minind,
+                    const uint64_t* site_offsets, const pgt_windows* out, void* workspace, size_t workspace_bytes, pgt_mem mem,
+                    cudaStream_t st) {
+	int ndev = 0;
+	if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+		return pgt_set_error(PGT_ERR_CUDA, "no usable CUDA device (libpgtscan has no CPU fallback)");
+	Layout L;
+	PGT_TRY(make_layout(plan, range, stat, mem, &L));
+	if (!workspace) return pgt_set_error(PGT_ERR_ARGS, "workspace is NULL");
+	if (workspace_bytes < L.total) return pgt_set_error(PGT_ERR_NOMEM, "workspace too small, see pgt_scan_workspace_bytes");
+	const bool bp = plan->mode == PGT_MODE_BP;
+	if (bp && stat != PGT_STAT_DXY) return pgt_set_error(PGT_ERR_ARGS, "PGT_MODE_BP plans are for PGT_STAT_DXY only");
+	if (bp && (!site_offsets || !cols->pos)) return pgt_set_error(PGT_ERR_ARGS, "bp mode needs site_offsets and pos");
+	ColDesc cd[8];
+	const int ncol = stat_columns(stat, plan->mode, cols, cd);
+	for (int i = 0; i < ncol; ++i)
+		if (!cd[i].ptr) return pgt_set_error(PGT_ERR_ARGS, "a column required by this statistic is NULL");
+	const uint64_t nunits = L.u_hi - L.u_lo;
+	const uint64_t nwin = L.w_hi - L.w_lo;
+	if (nunits == 0 && nwin == 0) return PGT_OK;
+	if (!bp && nunits > 0 && pgt_plan_unit_start(plan, L.u_lo) < L.origin)
+		return pgt_set_error(PGT_ERR_ARGS, "site_origin lies after the first site this scan must read");
+
+	char* ws = (char*)workspace;
+	const size_t seg_bytes = plan->segs.size() * sizeof(pgt_seg);
+	const size_t off_bytes = plan->off.size() * sizeof(uint64_t);
+	if (seg_bytes) PGT_CUDA(cudaMemcpyAsync(ws + L.segs_off, plan->segs.data(), seg_bytes, cudaMemcpyHostToDevice, st));
+	PGT_CUDA(cudaMemcpyAsync(ws + L.off_off, plan->off.data(), off_bytes, cudaMemcpyHostToDevice, st));
+	if (bp) PGT_CUDA(cudaMemcpyAsync(ws + L.siteoff_off, site_offsets, off_bytes, cudaMemcpyHostToDevice, st));
+
+	DevPlan P;
+	P.g = plan->g;
+	P.segs = (const pgt_seg*)(ws + L.segs_off);
+	P.off = (const uint64_t*)(ws + L.off_off);
+	P.site_off = bp ? (const uint64_t*)(ws + L.siteoff_off) : nullptr;
+	P.nseg = (uint32_t)plan->segs.size();
+	P.ncontig = (uint32_t)plan->off.size() - 1;
+	P.unit_lo = L.u_lo;
+	P.unit_hi = L.u_hi;
+	P.win_lo = L.w_lo;
+	P.win_hi = L.w_hi;
+	P.site_origin = L.origin;
+	P.nunits_total = plan->nunits;
+	P.mode = (int)plan->mode;
+
+	typename Stat::Acc* units = (typename Stat::Acc*)(ws + L.units_off);
+	uint64_t* bounds = bp ? (uint64_t*)(ws + L.bounds_off) : nullptr;
+	uint64_t ndata = 0;  // bp mode: sites the columns hold
+	if (bp) {
+		if (site_offsets[P.ncontig] < L.origin) return pgt_set_error(PGT_ERR_ARGS, "site_origin beyond the last site");
+		ndata = (range && range->site_count) ? range->site_count : site_offsets[P.ncontig] - L.origin;
+	}
+	const bool want_global = out->dxy_global && (stat == PGT_STAT_DXY || stat == PGT_STAT_FUSED);
+	const uint64_t nglobal = L.g_hi > L.u_lo ? L.g_hi - L.u_lo : 0;
+
+	if (mem == PGT_MEM_DEVICE) {
+		Cols C;
+		memset(&C, 0, sizeof(C));
+		C.pos = cols->pos;
+		C.a = cols->a;
+		C.b = cols->b;
+		C.g = cols->geno;
+		C.f1 = cols->f1;
+		C.f2 = cols->f2;
+		C.n1 = cols->n1;
+		C.n2 = cols->n2;
+		C.minind = minind;
+		if (bp && nunits) PGT_TRY(launch_bounds_kernel(P, cols->pos, ndata, bounds, st));
+		PGT_TRY(launch_units<Stat>(P, C, units, bounds, st));
+		PGT_TRY(launch_windows<Stat>(P, units, L.u_lo, cols->pos, *out, st));
+		if (want_global) PGT_TRY(launch_global<Stat>(units, nglobal, out->dxy_global, st));
+		return PGT_OK;
+	}
+
+	// ---- PGT_MEM_HOST: slabs of the axis are staged H2D on a copy stream (double-buffered) while
+	// the previous slab is reduced; only unit partials stay on the device.  Positions are not
+	// copied in site mode: the two edge positions per window are gathered on the host.
+	HostStreams hs;
+	PGT_CUDA(cudaStreamCreateWithFlags(&hs.copy, cudaStreamNonBlocking));
+	for (int i = 0; i < 2; ++i) {
+		PGT_CUDA(cudaEventCreateWithFlags(&hs.ready[i], cudaEventDisableTiming));
+		PGT_CUDA(cudaEventCreateWithFlags(&hs.freed[i], cudaEventDisableTiming));
+	}
+	// the copy stream must not start before the caller's stream reaches this point
+	PGT_CUDA(cudaEventRecord(hs.freed[0], st));
+	PGT_CUDA(cudaStreamWaitEvent(hs.copy, hs.freed[0], 0));
+	char* stage[2][8];
+	{
+		size_t o = L.stage_off;
+		for (int s = 0; s < 2; ++s)
+			for (int i = 0; i < ncol; ++i) {
+				stage[s][i] = ws + o;
+				o += L.stage_col_bytes[i];
+			}
+	}
+	const uint64_t slab_target = L.slab_sites - kSlabSlack;
+	const uint64_t axis_end = plan->off[0] + plan->nsites;
+	uint64_t ua = L.u_lo;
+	int slot = 0;
+	bool slot_used[2] = {false, false};
+	while (ua < L.u_hi) {
+		const uint64_t e0 = pgt_plan_unit_start(plan, ua);
+		uint64_t ub;
+		if (e0 + slab_target >= axis_end) ub = L.u_hi;
+		else ub = std::min<uint64_t>(L.u_hi, pgt_plan_unit_containing(plan, e0 + slab_target));
+		if (ub <= ua) ub = ua + 1;
+		const uint64_t e1 = pgt_plan_unit_start(plan, ub);
+		uint64_t s0 = e0, s1 = e1;  // data-site range of this slab
+		if (bp) {
+			s0 = host_site_lower_bound(plan, site_offsets, cols->pos, L.origin, ndata, e0);
+			s1 = host_site_lower_bound(plan, site_offsets, cols->pos, L.origin, ndata, e1);
+		}
+		const uint64_t ns = s1 - s0;
+		if (ns > L.slab_sites) return pgt_set_error(PGT_ERR_INPUT, "bp mode: more sites than bp in a slab (positions not strictly increasing?)");
+		if (slot_used[slot]) PGT_CUDA(cudaStreamWaitEvent(hs.copy, hs.freed[slot], 0));
+		Cols C;
+		memset(&C, 0, sizeof(C));
+		C.minind = minind;
+		for (int i = 0; i < ncol; ++i) {
+			if (ns)
+				PGT_CUDA(cudaMemcpyAsync(stage[slot][i], (const char*)cd[i].ptr + (s0 - L.origin) * cd[i].elem, ns * cd[i].elem,
+				                         cudaMemcpyHostToDevice, hs.copy));
+			const void* p = stage[slot][i];
+			memcpy((char*)&C + cd[i].offset_in_cols, &p, sizeof(p));
+		}
+		PGT_CUDA(cudaEventRecord(hs.ready[slot], hs.copy));
+		PGT_CUDA(cudaStreamWaitEvent(st, hs.ready[slot], 0));
+		DevPlan Ps = P;
+		Ps.unit_lo = ua;
+		Ps.unit_hi = ub;
+		Ps.site_origin = s0;
+		uint64_t* sb = bounds ? bounds + (ua - L.u_lo) : nullptr;
+		// bp: bounds are relative to the staged slice.  Slab i writes entries [ua, ub]; the shared
+		// entry ub is rewritten by slab i+1 relative to ITS slice, after slab i's unit kernel
+		// (stream order on `st`).
+		if (bp) PGT_TRY(launch_bounds_kernel(Ps, C.pos, ns, sb, st));
+		PGT_TRY(launch_units<Stat>(Ps, C, units + (ua - L.u_lo), sb, st));
+		PGT_CUDA(cudaEventRecord(hs.freed[slot], st));
+		slot_used[slot] = true;
+		slot ^= 1;
+		ua = ub;
+	}
+
+	// per-window values are produced into device staging, then copied back
+	pgt_windows dev;
+	memset(&dev, 0, sizeof(dev));
+	const size_t ob = align_up((size_t)nwin * 8 + 8, 256);
+	char* ob0 = ws + L.outs_off;
+	int k = 0;
+	auto dptr = [&](const void* want) -> void* {
+		void* r = want ? (void*)(ob0 + ob * k) : nullptr;
+		++k;
+		return r;
+	};
+	dev.sum_a = (double*)dptr(out->sum_a);
+	dev.sum_b = (double*)dptr(out->sum_b);
+	dev.fst = (double*)dptr(out->fst);
+	dev.nhet = (uint32_t*)dptr(out->nhet);
+	dev.nonmissing = (uint32_t*)dptr(out->nonmissing);
+	dev.het = (double*)dptr(out->het);
+	dev.dxy = (double*)dptr(out->dxy);
+	dev.neffective = (uint32_t*)dptr(out->neffective);
+	dev.nskip = (uint32_t*)dptr(out->nskip);
+	dev.dxy_global = want_global ? (double*)(ob0 + ob * 11) : nullptr;
+	PGT_TRY(launch_windows<Stat>(P, units, L.u_lo, nullptr, dev, st));
+	if (want_global) PGT_TRY(launch_global<Stat>(units, nglobal, dev.dxy_global, st));
+	auto back = [&](void* h, const void* d, size_t elem) -> cudaError_t {
+		return (h && d && nwin) ? cudaMemcpyAsync(h, d, nwin * elem, cudaMemcpyDeviceToHost, st) : cudaSuccess;
+	};
+	PGT_CUDA(back(out->sum_a, dev.sum_a, 8));
+	PGT_CUDA(back(out->sum_b, dev.sum_b, 8));
+	PGT_CUDA(back(out->fst, dev.fst, 8));
+	PGT_CUDA(back(out->nhet, dev.nhet, 4));
+	PGT_CUDA(back(out->nonmissing, dev.nonmissing, 4));
+	PGT_CUDA(back(out->het, dev.het, 8));
+	PGT_CUDA(back(out->dxy, dev.dxy, 8));
+	PGT_CUDA(back(out->neffective, dev.neffective, 4));
+	PGT_CUDA(back(out->nskip, dev.nskip, 4));
+	if (want_global) PGT_CUDA(cudaMemcpyAsync(out->dxy_global, dev.dxy_global, 3 * sizeof(double), cudaMemcpyDeviceToHost, st));
+
+	// window bookkeeping on the host while the device drains: label, nsites, edge positions
+	if (nwin && (out->label || out->nsites || out->start_pos || out->end_pos || out->mid_pos)) {
+		uint32_t si = pgt_plan_seg_of_window(plan, L.w_lo);
+		for (uint64_t w = L.w_lo; w < L.w_hi; ++w) {
+			while (w >= plan->segs[si].win_base + plan->segs[si].nwin) ++si;
+			const pgt_seg& sg = plan->segs[si];
+			uint64_t fs;
+			const uint32_t n = pgt_window_sites(plan->g, sg, w - sg.win_base, &fs);
+			const uint64_t first = sg.site_base + fs, last = first + n - 1;
+			const uint32_t label = pgt_plan_contig_of(plan, last);
+			const uint64_t o = w - L.w_lo;
+			if (out->label) out->label[o] = label;
+			if (out->nsites) out->nsites[o] = n;
+			uint32_t sp = 0, ep = 0;
+			bool have = false;
+			if (bp) {
+				sp = (uint32_t)(first - plan->off[pgt_plan_contig_of(plan, first)]) + 1u;
+				ep = (uint32_t)(last - plan->off[label]) + 1u;
+				have = true;
+			} else if (cols->pos) {
+				sp = cols->pos[first - L.origin];
+				ep = cols->pos[last - L.origin];
+				have = true;
+			}
+			if (have) {
+				if (out->start_pos) out->start_pos[o] = sp;
+				if (out->end_pos) out->end_pos[o] = ep;
+				if (out->mid_pos) out->mid_pos[o] = (sp + ep) / 2u;
+			}
+		}
+	}
+	PGT_CUDA(cudaStreamSynchronize(st));
+	PGT_CUDA(cudaStreamSynchronize(hs.copy));
+	return PGT_OK;
+}
+
+extern "C" int pgt_scan(const pgt_plan* plan, const pgt_range* range, pgt_stat stat, const pgt_columns* cols, int minind,
+                        const uint64_t* site_offsets, const pgt_windows* out, void* workspace, size_t workspace_bytes, pgt_mem mem,
+                        void* stream) {
+	if (!plan || !cols || !out) return pgt_set_error(PGT_ERR_ARGS, "pgt_scan: plan, cols and out must not be NULL");
+	if (mem != PGT_MEM_DEVICE && mem != PGT_MEM_HOST) return pgt_set_error(PGT_ERR_ARGS, "pgt_scan: unknown memory space");
 	cudaStream_t st = (cudaStream_t)stream;
-	ScanCtx c{};
-	int rc = begin_scan(plan, range, workspace, workspace_bytes, st, &c);
-	if (rc != PGT_OK) return rc;
-	if (c.nwin == 0) return PGT_OK;
-	FstStat::In in{a, b};
-	rc = launch_units<FstStat>(c, in, st);
-	if (rc != PGT_OK) return rc;
-	k_windows_fst<<<window_grid(c, 8), 256, 0, st>>>(c.P, (const FstStat::Acc*)(c.ws + c.units_off), pos, *out);
-	g_launches++;
-	PGT_CUDA(cudaGetLastError());
-	return PGT_OK;
+	switch (stat) {
+		case PGT_STAT_FST: return run_scan<FstStat>(plan, range, stat, cols, minind, site_offsets, out, workspace, workspace_bytes, mem, st);
+		case PGT_STAT_HET: return run_scan<HetStat>(plan, range, stat, cols, minind, site_offsets, out, workspace, workspace_bytes, mem, st);
+		case PGT_STAT_DXY:
+			if (minind < 1) return pgt_set_error(PGT_ERR_ARGS, "-minind must be at least 1");
+			return run_scan<DxyStat>(plan, range, stat, cols, minind, site_offsets, out, workspace, workspace_bytes, mem, st);
+		case PGT_STAT_FUSED:
+			if (minind < 1) return pgt_set_error(PGT_ERR_ARGS, "-minind must be at least 1");
+			return run_scan<FusedStat>(plan, range, stat, cols, minind, site_offsets, out, workspace, workspace_bytes, mem, st);
+	}
+	return pgt_set_error(PGT_ERR_ARGS, "pgt_scan: unknown statistic");
+}
+
+extern "C" int pgt_scan_fst(const pgt_plan* plan, const pgt_range* range, const pgt_columns* cols, const pgt_windows* out,
+                            void* workspace, size_t workspace_bytes, pgt_mem mem, void* stream) {
+	return pgt_scan(plan, range, PGT_STAT_FST, cols, 1, nullptr, out, workspace, workspace_bytes, mem, stream);
+}
+extern "C" int pgt_scan_het(const pgt_plan* plan, const pgt_range* range, const pgt_columns* cols, const pgt_windows* out,
+                            void* workspace, size_t workspace_bytes, pgt_mem mem, void* stream) {
+	return pgt_scan(plan, range, PGT_STAT_HET, cols, 1, nullptr, out, workspace, workspace_bytes, mem, stream);
+}
+extern "C" int pgt_scan_dxy(const pgt_plan* plan, const pgt_range* range, const pgt_columns* cols, int minind,
+                            const uint64_t* site_offsets, const pgt_windows* out, void* workspace, size_t workspace_bytes, pgt_mem mem,
+                            void* stream) {
+	return pgt_scan(plan, range, PGT_STAT_DXY, cols, minind, site_offsets, out, workspace, workspace_bytes, mem, stream);
+}
+extern "C" int pgt_scan_fused(const pgt_plan* plan, const pgt_range* range, const pgt_columns* cols, int minind,
+                              const pgt_windows* out, void* workspace, size_t workspace_bytes, pgt_mem mem, void* stream) {
+	return pgt_scan(plan, range, PGT_STAT_FUSED, cols, minind, nullptr, out, workspace, workspace_bytes, mem, stream);
 }

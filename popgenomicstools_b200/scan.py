@@ -12,7 +12,7 @@ import ctypes as C
 import numpy as np
 
 from . import _cabi
-from ._cabi import PgtFstOut, PgtRange, check
+from ._cabi import COLUMN_FIELDS, WINDOW_FIELDS, PgtColumns, PgtRange, PgtWindows, check
 
 
 def _torch():
@@ -91,66 +91,154 @@ class WindowPlan:
         check(self._lib.pgt_plan_shard(self._h, rank, nranks, *[C.byref(x) for x in v]))
         return tuple(x.value for x in v)
 
-    def workspace_bytes(self, window_range=None, site_origin=0):
-        r = _range(self, window_range, site_origin)
-        return int(self._lib.pgt_scan_workspace_bytes(self._h, C.byref(r)))
+    def workspace_bytes(self, stat, mem, window_range=None, site_origin=0, site_count=0):
+        r = _range(self, window_range, site_origin, site_count)
+        return int(self._lib.pgt_scan_workspace_bytes(self._h, C.byref(r), stat, mem))
 
-    def workspace(self, device, window_range=None, site_origin=0):
-        """Device scratch for a scan, cached per (device, range)."""
+    def workspace(self, device, stat, mem, window_range=None, site_origin=0, site_count=0):
+        """Device scratch for a scan, cached per (device, stat, mem, range)."""
         torch = _torch()
-        key = (str(device), window_range, site_origin)
+        key = (str(device), stat, mem, window_range, site_origin, site_count)
         ws = self._workspaces.get(key)
         if ws is None:
-            ws = torch.empty(self.workspace_bytes(window_range, site_origin), dtype=torch.uint8, device=device)
+            ws = torch.empty(self.workspace_bytes(stat, mem, window_range, site_origin, site_count), dtype=torch.uint8,
+                             device=device)
             self._workspaces[key] = ws
         return ws
 
 
-def _range(plan, window_range, site_origin):
+def _range(plan, window_range, site_origin, site_count=0):
     lo, hi = (0, plan.num_windows) if window_range is None else window_range
-    return PgtRange(int(lo), int(hi), int(site_origin))
+    return PgtRange(int(lo), int(hi), int(site_origin), int(site_count))
 
 
-def _dev_ptr(t, dtype, name):
+_COL_DTYPES = {"pos": "uint32", "a": "float64", "b": "float64", "geno": "int8", "f1": "float64", "f2": "float64",
+               "n1": "int32", "n2": "int32"}
+_F64_OUT = ("sum_a", "sum_b", "fst", "het", "dxy")
+_STAT_COLS = {
+    _cabi.PGT_STAT_FST: ("a", "b"),
+    _cabi.PGT_STAT_HET: ("geno",),
+    _cabi.PGT_STAT_DXY: ("f1", "f2", "n1", "n2"),
+    _cabi.PGT_STAT_FUSED: ("a", "b", "geno", "f1", "f2", "n1", "n2"),
+}
+_STAT_OUTS = {
+    _cabi.PGT_STAT_FST: ("label", "start_pos", "end_pos", "mid_pos", "nsites", "sum_a", "sum_b", "fst"),
+    _cabi.PGT_STAT_HET: ("label", "start_pos", "end_pos", "mid_pos", "nsites", "nhet", "nonmissing", "het"),
+    _cabi.PGT_STAT_DXY: ("label", "start_pos", "end_pos", "nsites", "dxy", "neffective", "nskip", "dxy_global"),
+    _cabi.PGT_STAT_FUSED: WINDOW_FIELDS,
+}
+
+
+def _is_tensor(x):
     torch = _torch()
-    if t is None:
-        return None
-    if not isinstance(t, torch.Tensor) or not t.is_cuda:
-        raise TypeError(f"{name}: expected a CUDA tensor")
-    if t.dtype != dtype or not t.is_contiguous():
-        raise TypeError(f"{name}: expected contiguous {dtype}, got {t.dtype}")
-    return t.data_ptr()
+    return isinstance(x, torch.Tensor)
 
 
-def fst_window(plan, pos, a, b, window_range=None, site_origin=0, out=None):
-    """Sliding-window FST = sum(a)/sum(b) (fstWindow.cpp:69-107) over device columns.
-
-    pos: uint32/int32 CUDA tensor (may be None: positions are then not gathered), a, b: float64
-    CUDA tensors holding global sites [site_origin, ...).  Returns a dict of CUDA tensors, one
-    element per window of `window_range` (default: all windows): label, start_pos, end_pos,
-    mid_pos, sum_a, sum_b, fst, nsites.  Enqueued on the current stream, not synchronised.
-    """
+def scan(plan, stat, cols, minind=1, site_offsets=None, window_range=None, site_origin=0, site_count=0, out=None,
+         device=None):
+    """Generic entry (pgt_scan).  `cols`: dict name -> column.  CUDA tensors select
+    PGT_MEM_DEVICE (enqueued on the current stream, returns CUDA tensors, not synchronised);
+    numpy arrays select PGT_MEM_HOST (staged through the device, returns numpy arrays)."""
     torch = _torch()
     lib = plan._lib
-    dev = a.device
-    r = _range(plan, window_range, site_origin)
+    need = _STAT_COLS[stat]
+    for k in need:
+        if cols.get(k) is None:
+            raise ValueError(f"column {k!r} is required")
+    sample = cols[need[0]]
+    on_device = _is_tensor(sample) and sample.is_cuda
+    r = _range(plan, window_range, site_origin, site_count)
     nwin = r.w_hi - r.w_lo
+    c = PgtColumns()
+    keep = []
+    for k in COLUMN_FIELDS:
+        v = cols.get(k)
+        if v is None or (k != "pos" and k not in need):
+            continue
+        want = _COL_DTYPES[k]
+        if on_device:
+            if not (_is_tensor(v) and v.is_cuda and v.is_contiguous()):
+                raise TypeError(f"{k}: expected a contiguous CUDA tensor")
+            if k == "pos" and v.dtype == torch.int32:
+                v = v.view(torch.uint32)
+            if str(v.dtype) != "torch." + want:
+                raise TypeError(f"{k}: expected {want}, got {v.dtype}")
+            setattr(c, k, v.data_ptr())
+        else:
+            if _is_tensor(v):
+                v = v.numpy()
+            if k == "pos" and v.dtype == np.int32:
+                v = v.view(np.uint32)
+            if v.dtype != np.dtype(want) or not v.flags["C_CONTIGUOUS"]:
+                raise TypeError(f"{k}: expected contiguous {want}, got {v.dtype}")
+            setattr(c, k, v.ctypes.data)
+        keep.append(v)
+    if on_device:
+        dev = sample.device
+    else:
+        dev = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+    names = _STAT_OUTS[stat]
     if out is None:
-        out = {k: torch.empty(nwin, dtype=torch.uint32, device=dev) for k in ("label", "start_pos", "end_pos", "mid_pos", "nsites")}
-        out.update({k: torch.empty(nwin, dtype=torch.float64, device=dev) for k in ("sum_a", "sum_b", "fst")})
-    if pos is not None and pos.dtype == torch.int32:
-        pos = pos.view(torch.uint32)
-    o = PgtFstOut(*[out[k].data_ptr() if k in out and out[k] is not None else None for k, _ in PgtFstOut._fields_])
-    ws = plan.workspace(dev, window_range, site_origin)
+        out = {}
+        for k in names:
+            n = 3 if k == "dxy_global" else nwin
+            f64 = k in _F64_OUT or k == "dxy_global"
+            if on_device:
+                out[k] = torch.empty(n, dtype=torch.float64 if f64 else torch.uint32, device=dev)
+            else:
+                out[k] = np.empty(n, np.float64 if f64 else np.uint32)
+    w = PgtWindows()
+    for k in WINDOW_FIELDS:
+        v = out.get(k)
+        if v is not None:
+            setattr(w, k, v.data_ptr() if on_device else v.ctypes.data)
+    so = None
+    if site_offsets is not None:
+        so = np.ascontiguousarray(site_offsets, dtype=np.uint64)
+        keep.append(so)
+    mem = _cabi.PGT_MEM_DEVICE if on_device else _cabi.PGT_MEM_HOST
+    ws = plan.workspace(dev, stat, mem, window_range, site_origin, site_count)
     with torch.cuda.device(dev):
         stream = torch.cuda.current_stream(dev).cuda_stream
-        check(lib.pgt_scan_fst(plan.handle, C.byref(r), _dev_ptr(pos, torch.uint32, "pos"), _dev_ptr(a, torch.float64, "a"),
-                               _dev_ptr(b, torch.float64, "b"), C.byref(o), ws.data_ptr(), ws.numel(), _cabi.PGT_MEM_DEVICE,
-                               C.c_void_p(stream)))
+        check(lib.pgt_scan(plan.handle, C.byref(r), stat, C.byref(c), int(minind), so.ctypes.data if so is not None else None,
+                           C.byref(w), ws.data_ptr(), ws.numel(), mem, C.c_void_p(stream)))
     return out
 
 
+def fst_window(plan, pos, a, b, **kw):
+    """Sliding-window FST = sum(a)/sum(b) (/root/reference/fstWindow.cpp:69-107).
+    Returns label, start_pos, end_pos, mid_pos, nsites, sum_a, sum_b, fst per window."""
+    return scan(plan, _cabi.PGT_STAT_FST, dict(pos=pos, a=a, b=b), **kw)
+
+
+def het_window(plan, pos, geno, **kw):
+    """Sliding-window heterozygosity = #(g==1) / #(g>=0) (/root/reference/hetWindow.cpp:66-105).
+    Returns label, start_pos, end_pos, mid_pos, nsites, nhet, nonmissing, het per window."""
+    return scan(plan, _cabi.PGT_STAT_HET, dict(pos=pos, geno=geno), **kw)
+
+
+def dxy_window(plan, pos, f1, f2, n1, n2, minind=1, site_offsets=None, **kw):
+    """Sliding-window dxy = sum of f1(1-f2)+f2(1-f1) over sites with nInd >= minind in both
+    populations (/root/reference/dxyWindow.cpp:172-209,381).  plan mode 'sites' = -fixedsite 1,
+    'bp' = -fixedsite 0 (then site_offsets = cumulative sites per chromosome).  -skip_missing 1
+    is the row filter ``neffective > 0``.  Returns label, start_pos, end_pos, nsites, dxy,
+    neffective, nskip per window and dxy_global[3]."""
+    return scan(plan, _cabi.PGT_STAT_DXY, dict(pos=pos, f1=f1, f2=f2, n1=n1, n2=n2), minind=minind,
+                site_offsets=site_offsets, **kw)
+
+
+def fused_window(plan, pos, a, b, geno, f1, f2, n1, n2, minind=1, **kw):
+    """fst + dxy + het over one site axis in a single pass (BASELINE config 5)."""
+    return scan(plan, _cabi.PGT_STAT_FUSED, dict(pos=pos, a=a, b=b, geno=geno, f1=f1, f2=f2, n1=n1, n2=n2),
+                minind=minind, **kw)
+
+
 # ---- synthetic inputs (device) -------------------------------------------------------------
+
+def _stream(t):
+    torch = _torch()
+    return C.c_void_p(torch.cuda.current_stream(t.device).cuda_stream)
+
 
 def synth_fst(seed, site0, n, device="cuda"):
     torch = _torch()
@@ -158,9 +246,29 @@ def synth_fst(seed, site0, n, device="cuda"):
     a = torch.empty(n, dtype=torch.float64, device=device)
     b = torch.empty(n, dtype=torch.float64, device=device)
     with torch.cuda.device(a.device):
-        st = torch.cuda.current_stream(a.device).cuda_stream
-        check(lib.pgt_synth_fst(seed, site0, n, a.data_ptr(), b.data_ptr(), C.c_void_p(st)))
+        check(lib.pgt_synth_fst(seed, site0, n, a.data_ptr(), b.data_ptr(), _stream(a)))
     return a, b
+
+
+def synth_het(seed, site0, n, device="cuda"):
+    torch = _torch()
+    lib = _cabi.load()
+    g = torch.empty(n, dtype=torch.int8, device=device)
+    with torch.cuda.device(g.device):
+        check(lib.pgt_synth_het(seed, site0, n, g.data_ptr(), _stream(g)))
+    return g
+
+
+def synth_dxy(seed, site0, n, device="cuda"):
+    torch = _torch()
+    lib = _cabi.load()
+    f1 = torch.empty(n, dtype=torch.float64, device=device)
+    f2 = torch.empty(n, dtype=torch.float64, device=device)
+    n1 = torch.empty(n, dtype=torch.int32, device=device)
+    n2 = torch.empty(n, dtype=torch.int32, device=device)
+    with torch.cuda.device(f1.device):
+        check(lib.pgt_synth_dxy(seed, site0, n, f1.data_ptr(), f2.data_ptr(), n1.data_ptr(), n2.data_ptr(), _stream(f1)))
+    return f1, f2, n1, n2
 
 
 def synth_pos(seed, site0, n, contig_offsets, density=1, device="cuda"):
@@ -169,6 +277,9 @@ def synth_pos(seed, site0, n, contig_offsets, density=1, device="cuda"):
     off = np.ascontiguousarray(contig_offsets, dtype=np.uint64)
     pos = torch.empty(n, dtype=torch.uint32, device=device)
     with torch.cuda.device(pos.device):
-        st = torch.cuda.current_stream(pos.device).cuda_stream
-        check(lib.pgt_synth_pos(seed, site0, n, off.ctypes.data, len(off) - 1, density, pos.data_ptr(), C.c_void_p(st)))
+        check(lib.pgt_synth_pos(seed, site0, n, off.ctypes.data, len(off) - 1, density, pos.data_ptr(), _stream(pos)))
     return pos
+
+
+def kernel_launch_count():
+    return int(_cabi.load().pgt_kernel_launch_count())

@@ -93,9 +93,7 @@ def test_synthetic_vs_oracle(pgt, W, S, unit):
     out = pgt.fst_window(plan, gp, ga, gb)
     torch.cuda.synchronize()
     res = {k: v.cpu().numpy() for k, v in out.items()}
-    ref = check_against_oracle(res, lengths, pos, a, b, W, S)
-    if (W, S) == (50000, 10000):
-        assert len(ref["n"]) >= 96
+    check_against_oracle(res, lengths, pos, a, b, W, S)
 
 
 def test_c1_exact_shape(pgt):
