@@ -213,6 +213,13 @@ int pgt_synth_dxy(uint64_t seed, uint64_t site0, uint64_t n, double* f1, double*
 int pgt_synth_pos(uint64_t seed, uint64_t site0, uint64_t n, const uint64_t* contig_offsets, uint32_t ncontig,
                   uint32_t density, uint32_t* pos, void* stream);
 
+/* Optional per-kernel device timing (bench.py's roofline): while enabled, every level-1 (unit
+ * reduction) and level-2 (window combine) launch is bracketed by CUDA events on its stream.
+ * pgt_profile_read synchronises those events, returns summed milliseconds / launch counts since
+ * the last read, and clears them. */
+int pgt_profile(int enable);
+int pgt_profile_read(double* units_ms, uint64_t* units_launches, double* windows_ms, uint64_t* windows_launches);
+
 /* number of kernels this library has launched in this process (bench.py's gpu_launches) */
 uint64_t pgt_kernel_launch_count(void);
 

@@ -81,6 +81,8 @@ PROTOTYPES = {
                                 C.c_void_p]),
     "pgt_synth_pos": (C.c_int, [C.c_uint64, C.c_uint64, C.c_uint64, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p,
                                 C.c_void_p]),
+    "pgt_profile": (C.c_int, [C.c_int]),
+    "pgt_profile_read": (C.c_int, [C.POINTER(C.c_double), _u64p, C.POINTER(C.c_double), _u64p]),
     "pgt_kernel_launch_count": (C.c_uint64, []),
 }
 

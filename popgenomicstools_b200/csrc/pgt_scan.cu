@@ -70,6 +70,63 @@ extern "C" int pgt_host_free(void* p) {
 	return PGT_OK;
 }
 
+// ---- optional per-kernel timing (bench.py roofline): CUDA events on the launching stream
+struct ProfEvent {
+	cudaEvent_t a, b;
+	int kind;  // 0 = level 1 (k_units), 1 = level 2 (k_windows)
+};
+static bool g_profile = false;
+static std::vector<ProfEvent> g_prof_events;
+
+struct ProfScope {
+	cudaStream_t st;
+	ProfEvent ev;
+	bool on;
+	ProfScope(int kind, cudaStream_t s) : st(s), on(g_profile) {
+		if (!on) return;
+		ev.kind = kind;
+		if (cudaEventCreate(&ev.a) != cudaSuccess || cudaEventCreate(&ev.b) != cudaSuccess) {
+			on = false;
+			return;
+		}
+		cudaEventRecord(ev.a, st);
+	}
+	~ProfScope() {
+		if (!on) return;
+		cudaEventRecord(ev.b, st);
+		g_prof_events.push_back(ev);
+	}
+};
+
+extern "C" int pgt_profile(int enable) {
+	g_profile = enable != 0;
+	return PGT_OK;
+}
+
+extern "C" int pgt_profile_read(double* units_ms, uint64_t* units_launches, double* windows_ms, uint64_t* windows_launches) {
+	double ms[2] = {0, 0};
+	uint64_t n[2] = {0, 0};
+	for (ProfEvent& e : g_prof_events) {
+		float t = 0;
+		cudaError_t err = cudaEventSynchronize(e.b);
+		if (err == cudaSuccess) err = cudaEventElapsedTime(&t, e.a, e.b);
+		cudaEventDestroy(e.a);
+		cudaEventDestroy(e.b);
+		if (err != cudaSuccess) {
+			g_prof_events.clear();
+			return cuda_fail(err, "pgt_profile_read");
+		}
+		ms[e.kind] += t;
+		n[e.kind]++;
+	}
+	g_prof_events.clear();
+	if (units_ms) *units_ms = ms[0];
+	if (units_launches) *units_launches = n[0];
+	if (windows_ms) *windows_ms = ms[1];
+	if (windows_launches) *windows_launches = n[1];
+	return PGT_OK;
+}
+
 static int num_sms() {
 	int dev = 0, n = 0;
 	if (cudaGetDevice(&dev) != cudaSuccess) return 0;
@@ -596,7 +653,10 @@ static int launch_units(const DevPlan& P, const Cols& cols, typename Stat::Acc* 
 	PGT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, 0));
 	const uint64_t cap = (uint64_t)num_sms() * (per_sm > 0 ? per_sm : 1);
 	const unsigned grid = (unsigned)(want < cap ? want : cap);
-	kern<<<grid, threads, 0, st>>>(P, cols, units, bounds);
+	{
+		ProfScope prof(0, st);
+		kern<<<grid, threads, 0, st>>>(P, cols, units, bounds);
+	}
 	g_launches++;
 	PGT_CUDA(cudaGetLastError());
 	return PGT_OK;
@@ -619,7 +679,10 @@ static int launch_windows(const DevPlan& P, const typename Stat::Acc* units, uin
 	if (nwin == 0) return PGT_OK;
 	const uint64_t want = (nwin + 7) / 8;
 	const uint64_t cap = (uint64_t)num_sms() * 8;
-	k_windows<Stat><<<(unsigned)(want < cap ? want : cap), 256, 0, st>>>(P, units, units_base, pos, out);
+	{
+		ProfScope prof(1, st);
+		k_windows<Stat><<<(unsigned)(want < cap ? want : cap), 256, 0, st>>>(P, units, units_base, pos, out);
+	}
 	g_launches++;
 	PGT_CUDA(cudaGetLastError());
 	return PGT_OK;

@@ -283,3 +283,16 @@ def synth_pos(seed, site0, n, contig_offsets, density=1, device="cuda"):
 
 def kernel_launch_count():
     return int(_cabi.load().pgt_kernel_launch_count())
+
+
+def profile(enable):
+    """Bracket every level-1 / level-2 launch with CUDA events (see pgt_profile)."""
+    check(_cabi.load().pgt_profile(1 if enable else 0))
+
+
+def profile_read():
+    """-> dict(units_ms, units_launches, windows_ms, windows_launches) since the last read."""
+    um, wm = C.c_double(), C.c_double()
+    un, wn = C.c_uint64(), C.c_uint64()
+    check(_cabi.load().pgt_profile_read(C.byref(um), C.byref(un), C.byref(wm), C.byref(wn)))
+    return dict(units_ms=um.value, units_launches=un.value, windows_ms=wm.value, windows_launches=wn.value)
