@@ -76,6 +76,12 @@ int pgt_set_device(int device);
 /* pinned host memory for PGT_MEM_HOST callers (cudaHostAlloc / cudaFreeHost) */
 int pgt_host_alloc(void** p, size_t bytes);
 int pgt_host_free(void* p);
+/* page-lock / unlock an existing host allocation (cudaHostRegister) */
+int pgt_host_register(void* p, size_t bytes);
+int pgt_host_unregister(void* p);
+/* device memory for the workspace of callers that do not link the CUDA runtime (the CLIs) */
+int pgt_device_alloc(void** p, size_t bytes);
+int pgt_device_free(void* p);
 
 /* ---- plan: which windows exist (replaces the flush triggers of calcFst & co.) ----------
  *

@@ -52,6 +52,10 @@ PROTOTYPES = {
     "pgt_set_device": (C.c_int, [C.c_int]),
     "pgt_host_alloc": (C.c_int, [C.POINTER(C.c_void_p), C.c_size_t]),
     "pgt_host_free": (C.c_int, [C.c_void_p]),
+    "pgt_host_register": (C.c_int, [C.c_void_p, C.c_size_t]),
+    "pgt_host_unregister": (C.c_int, [C.c_void_p]),
+    "pgt_device_alloc": (C.c_int, [C.POINTER(C.c_void_p), C.c_size_t]),
+    "pgt_device_free": (C.c_int, [C.c_void_p]),
     "pgt_plan_create": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32,
                                   C.c_uint32]),
     "pgt_plan_destroy": (None, [C.c_void_p]),

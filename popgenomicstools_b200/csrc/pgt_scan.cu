@@ -69,6 +69,23 @@ extern "C" int pgt_host_free(void* p) {
 	PGT_CUDA(cudaFreeHost(p));
 	return PGT_OK;
 }
+extern "C" int pgt_device_alloc(void** p, size_t bytes) {
+	if (!p) return pgt_set_error(PGT_ERR_ARGS, "pgt_device_alloc: NULL");
+	PGT_CUDA(cudaMalloc(p, bytes ? bytes : 1));
+	return PGT_OK;
+}
+extern "C" int pgt_device_free(void* p) {
+	PGT_CUDA(cudaFree(p));
+	return PGT_OK;
+}
+extern "C" int pgt_host_register(void* p, size_t bytes) {
+	PGT_CUDA(cudaHostRegister(p, bytes, cudaHostRegisterDefault));
+	return PGT_OK;
+}
+extern "C" int pgt_host_unregister(void* p) {
+	PGT_CUDA(cudaHostUnregister(p));
+	return PGT_OK;
+}
 
 // ---- optional per-kernel timing (bench.py roofline): CUDA events on the launching stream
 struct ProfEvent {

@@ -1,0 +1,300 @@
+// pgt_cli.h -- host plumbing shared by the drop-in CLIs (fstWindow, hetWindow, dxyWindow):
+// whole-file input (mmap, or zlib inflate for .gz), multi-threaded line parsing with
+// std::from_chars (correctly rounded like libstdc++'s num_get -> strtod that the reference
+// uses, /root/reference/fstWindow.cpp:141), contig run-length bookkeeping, %g output
+// formatting (the reference prints doubles with default ostream settings == printf("%g"),
+// fstWindow.cpp:88) and the timing report.  No arithmetic of the hot path happens here: the
+// columns go to libpgtscan.so (pgt_scan, PGT_MEM_HOST).
+#ifndef PGT_CLI_H
+#define PGT_CLI_H
+
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
+#include <zlib.h>
+
+#include <algorithm>
+#include <charconv>
+#include <chrono>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "../../../include/pgt_scan.h"
+
+namespace pgtcli {
+
+inline double now_ms() {
+	using namespace std::chrono;
+	return duration<double, std::milli>(steady_clock::now().time_since_epoch()).count();
+}
+
+// ---- input -----------------------------------------------------------------------------
+
+struct Input {
+	const char* data = nullptr;
+	size_t size = 0;
+	void* map = nullptr;
+	size_t map_size = 0;
+	std::vector<char> owned;
+	~Input() {
+		if (map) munmap(map, map_size);
+	}
+};
+
+// 0 ok, -1 cannot open
+inline int read_input(const char* path, Input* in, bool allow_gzip) {
+	int fd = open(path, O_RDONLY);
+	if (fd < 0) return -1;
+	struct stat st;
+	if (fstat(fd, &st) != 0 || !S_ISREG(st.st_mode)) {
+		// pipes / process substitution: slurp
+		std::vector<char> buf;
+		char tmp[1 << 16];
+		ssize_t k;
+		while ((k = read(fd, tmp, sizeof(tmp))) > 0) buf.insert(buf.end(), tmp, tmp + k);
+		close(fd);
+		in->owned.swap(buf);
+		in->data = in->owned.data();
+		in->size = in->owned.size();
+	} else {
+		in->size = (size_t)st.st_size;
+		if (in->size) {
+			in->map = mmap(nullptr, in->size, PROT_READ, MAP_PRIVATE, fd, 0);
+			if (in->map == MAP_FAILED) {
+				in->map = nullptr;
+				close(fd);
+				return -1;
+			}
+			in->map_size = in->size;
+			madvise(in->map, in->size, MADV_SEQUENTIAL | MADV_WILLNEED);
+			in->data = (const char*)in->map;
+		}
+		close(fd);
+	}
+	// gzip magic sniff as the reference does (dxyWindow.cpp:82-83)
+	if (allow_gzip && in->size >= 2 && (unsigned char)in->data[0] == 0x1f && (unsigned char)in->data[1] == 0x8b) {
+		std::vector<char> out;
+		out.resize(std::max<size_t>(in->size * 4, 1 << 16));
+		z_stream zs;
+		memset(&zs, 0, sizeof(zs));
+		if (inflateInit2(&zs, 15 + 32) != Z_OK) return -1;
+		zs.next_in = (Bytef*)in->data;
+		size_t in_left = in->size, produced = 0;
+		for (;;) {
+			if (zs.avail_in == 0 && in_left) {
+				uInt c = (uInt)std::min<size_t>(in_left, 1u << 30);
+				zs.avail_in = c;
+				in_left -= c;
+			}
+			if (out.size() - produced < (1 << 16)) out.resize(out.size() * 2);
+			zs.next_out = (Bytef*)out.data() + produced;
+			uInt room = (uInt)std::min<size_t>(out.size() - produced, 1u << 30);
+			zs.avail_out = room;
+			int rc = inflate(&zs, Z_NO_FLUSH);
+			produced += room - zs.avail_out;
+			if (rc == Z_STREAM_END) {
+				if (zs.avail_in == 0 && in_left == 0) break;
+				inflateReset(&zs);  // concatenated members (bgzip)
+			} else if (rc != Z_OK && rc != Z_BUF_ERROR) {
+				break;
+			} else if (rc == Z_BUF_ERROR && zs.avail_in == 0 && in_left == 0) {
+				break;
+			}
+		}
+		inflateEnd(&zs);
+		out.resize(produced);
+		if (in->map) munmap(in->map, in->map_size);
+		in->map = nullptr;
+		in->owned.swap(out);
+		in->data = in->owned.data();
+		in->size = in->owned.size();
+	}
+	return 0;
+}
+
+// ---- tokenising ------------------------------------------------------------------------
+
+inline bool is_ws(char c) { return c == ' ' || c == '\t' || c == '\r' || c == '\v' || c == '\f'; }
+
+inline const char* skip_ws(const char* p, const char* e) {
+	while (p < e && is_ws(*p)) ++p;
+	return p;
+}
+inline const char* token_end(const char* p, const char* e) {
+	while (p < e && !is_ws(*p)) ++p;
+	return p;
+}
+
+// `ss >> unsigned int` (optional sign, digits)
+inline bool parse_u32(const char*& p, const char* e, uint32_t* v) {
+	p = skip_ws(p, e);
+	bool neg = false;
+	if (p < e && (*p == '+' || *p == '-')) neg = (*p++ == '-');
+	uint64_t x = 0;
+	auto r = std::from_chars(p, e, x);
+	if (r.ec != std::errc() || r.ptr == p) return false;
+	p = r.ptr;
+	if (x > 0xffffffffull) x = 0xffffffffull;
+	*v = neg ? (uint32_t)(0u - (uint32_t)x) : (uint32_t)x;
+	return true;
+}
+inline bool parse_i32(const char*& p, const char* e, int32_t* v) {
+	p = skip_ws(p, e);
+	bool neg = false;
+	if (p < e && (*p == '+' || *p == '-')) neg = (*p++ == '-');
+	uint64_t x = 0;
+	auto r = std::from_chars(p, e, x);
+	if (r.ec != std::errc() || r.ptr == p) return false;
+	p = r.ptr;
+	if (x > 0x7fffffffull) x = 0x7fffffffull;
+	*v = neg ? -(int32_t)x : (int32_t)x;
+	return true;
+}
+inline bool parse_f64(const char*& p, const char* e, double* v) {
+	p = skip_ws(p, e);
+	if (p < e && *p == '+') ++p;
+	auto r = std::from_chars(p, e, *v, std::chars_format::general);
+	if (r.ec == std::errc::result_out_of_range) {
+		// strtod semantics: +-HUGE_VAL or (sub)zero; let strtod decide
+		std::string tmp(p, r.ptr);
+		*v = strtod(tmp.c_str(), nullptr);
+		p = r.ptr;
+		return true;
+	}
+	if (r.ec != std::errc() || r.ptr == p) return false;
+	p = r.ptr;
+	return true;
+}
+
+// ---- line-chunked parallel parsing ------------------------------------------------------
+
+struct ContigRun {
+	std::string name;
+	uint64_t count;
+};
+
+// The reference stops at the first EMPTY line (fstWindow.cpp:125 `while (!sitedata.empty())`).
+inline size_t effective_size(const char* d, size_t n) {
+	if (n == 0) return 0;
+	if (d[0] == '\n') return 0;
+	const char* p = d;
+	const char* e = d + n;
+	while (p < e) {
+		const char* q = (const char*)memchr(p, '\n', (size_t)(e - p));
+		if (!q) break;
+		if (q + 1 < e && q[1] == '\n') return (size_t)(q + 1 - d);
+		p = q + 1;
+	}
+	return n;
+}
+
+inline std::vector<size_t> chunk_starts(const char* d, size_t begin, size_t n, unsigned nthreads) {
+	std::vector<size_t> st;
+	st.push_back(begin);
+	for (unsigned t = 1; t < nthreads; ++t) {
+		size_t guess = begin + (n - begin) / nthreads * t;
+		if (guess <= st.back()) continue;
+		const char* q = (const char*)memchr(d + guess, '\n', n - guess);
+		if (!q) break;
+		size_t s = (size_t)(q + 1 - d);
+		if (s > st.back() && s < n) st.push_back(s);
+	}
+	st.push_back(n);
+	return st;
+}
+
+inline unsigned parse_threads() {
+	const char* env = getenv("PGT_THREADS");
+	unsigned n = env ? (unsigned)atoi(env) : std::thread::hardware_concurrency();
+	if (n < 1) n = 1;
+	if (n > 64) n = 64;
+	return n;
+}
+
+inline void append_runs(std::vector<ContigRun>& dst, const std::vector<ContigRun>& src) {
+	for (const ContigRun& r : src) {
+		if (!dst.empty() && dst.back().name == r.name) dst.back().count += r.count;
+		else dst.push_back(r);
+	}
+}
+
+// ---- output ----------------------------------------------------------------------------
+
+inline char* put_u32(char* p, uint32_t v) { return std::to_chars(p, p + 12, v).ptr; }
+inline char* put_i32(char* p, int32_t v) { return std::to_chars(p, p + 12, v).ptr; }
+inline char* put_g(char* p, double v) { return p + snprintf(p, 32, "%g", v); }
+
+// format rows [lo, hi) with `fn(char* p, uint64_t row) -> char*` on several threads, write in order
+template <class Fn>
+inline void write_rows(FILE* f, uint64_t nrows, size_t max_row_bytes, Fn fn) {
+	if (nrows == 0) return;
+	unsigned nt = parse_threads();
+	if (nrows < 4096) nt = 1;
+	const uint64_t block = 1u << 16;
+	std::vector<std::vector<char>> bufs(nt);
+	for (uint64_t base = 0; base < nrows; base += block * nt) {
+		std::vector<std::thread> th;
+		std::vector<size_t> used(nt, 0);
+		for (unsigned t = 0; t < nt; ++t) {
+			uint64_t lo = base + block * t, hi = std::min<uint64_t>(nrows, lo + block);
+			if (lo >= hi) break;
+			auto work = [&, t, lo, hi]() {
+				bufs[t].resize((size_t)(hi - lo) * max_row_bytes);
+				char* p = bufs[t].data();
+				for (uint64_t r = lo; r < hi; ++r) p = fn(p, r);
+				used[t] = (size_t)(p - bufs[t].data());
+			};
+			if (nt == 1) work();
+			else th.emplace_back(work);
+		}
+		for (auto& x : th) x.join();
+		for (unsigned t = 0; t < nt; ++t)
+			if (used[t]) fwrite(bufs[t].data(), 1, used[t], f);
+	}
+}
+
+// ---- device ----------------------------------------------------------------------------
+
+struct DeviceWorkspace {
+	void* p = nullptr;
+	size_t bytes = 0;
+	~DeviceWorkspace() {
+		if (p) pgt_device_free(p);
+	}
+};
+
+inline int select_device() {
+	const char* env = getenv("PGT_DEVICE");
+	int n = pgt_device_count();
+	if (n <= 0) {
+		fprintf(stderr, "No usable CUDA device: %s\n", n < 0 ? pgt_last_error() : "device count is 0");
+		return -1;
+	}
+	if (pgt_set_device(env ? atoi(env) : 0) != PGT_OK) {
+		fprintf(stderr, "%s\n", pgt_last_error());
+		return -1;
+	}
+	return 0;
+}
+
+struct Timing {
+	double parse_ms = 0, scan_ms = 0, format_ms = 0, total_ms = 0;
+	uint64_t sites = 0, windows = 0;
+	unsigned threads = 0;
+	void report(const char* tool) const {
+		if (!getenv("PGT_TIMING")) return;
+		fprintf(stderr,
+		        "{\"tool\":\"%s\",\"sites\":%llu,\"windows\":%llu,\"parse_ms\":%.3f,\"scan_ms\":%.3f,\"format_ms\":%.3f,"
+		        "\"total_ms\":%.3f,\"parse_threads\":%u}\n",
+		        tool, (unsigned long long)sites, (unsigned long long)windows, parse_ms, scan_ms, format_ms, total_ms, threads);
+	}
+};
+
+}  // namespace pgtcli
+#endif

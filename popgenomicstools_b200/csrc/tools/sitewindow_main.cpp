@@ -1,0 +1,262 @@
+// sitewindow_main.cpp -- drop-in `fstWindow` (-DPGT_TOOL_FST) and `hetWindow` (-DPGT_TOOL_HET).
+//
+// Same argv grammar, defaults, usage text, messages, stdout columns and exit codes as
+//   /root/reference/fstWindow.cpp:23-67,158-177   and   /root/reference/hetWindow.cpp:20-64,156-175
+// The line loop + calcWindow of the reference (fstWindow.cpp:109-155, 69-107) is replaced by:
+// parse the text into columns (multi-threaded), ask libpgtscan for the closed-form window plan
+// and run the CUDA scan (pgt_scan, PGT_MEM_HOST), print the rows.
+//
+// Documented deviations (the reference has undefined behaviour there):
+//   * step size <= 0: the reference prints the message and carries on into heap corruption;
+//     we print the same message and exit 255.
+//   * step size > window size: the reference segfaults; we print an error and exit 255.
+//   * a line that does not parse: the reference silently reuses stale values; we report it.
+//   * the input file is opened read-only (the reference needs write permission, fstWindow.cpp:45).
+// Set PGT_TIMING=1 for a JSON timing line on stderr (parse / scan / format, opt-in so stderr
+// stays byte-identical by default); PGT_DEVICE selects the GPU, PGT_THREADS the parser threads.
+#include <atomic>
+
+#include "pgt_cli.h"
+
+using namespace pgtcli;
+
+#if defined(PGT_TOOL_FST)
+static const char* kTool = "fstWindow";
+static const char* kUsageLine = "fstWindow [ANGSD fst variance component file] [window size (number sites)] [step size (number sites)]\n";
+static const char* kStatName = "(5) Fst\n";
+static const char* kOpenErr = "Unable to open Fst variance components file ";
+#elif defined(PGT_TOOL_HET)
+static const char* kTool = "hetWindow";
+static const char* kUsageLine = "hetWindow [genotypes file] [window size (number sites)] [step size (number sites)]\n";
+static const char* kStatName = "(5) heterozygosity\n";
+static const char* kOpenErr = "Unable to open genotypes file ";
+#else
+#error "define PGT_TOOL_FST or PGT_TOOL_HET"
+#endif
+
+// fstWindow.cpp:23-35 / hetWindow.cpp:20-32
+static void info(unsigned winsize, unsigned stepsize) {
+	printf("\nUsage:\n%sdefault window size: %u\ndefault step size: %u\n\nOutput:\n(1) chromosome\n(2) window start\n(3) window end\n"
+	       "(4) window midpoint position\n%s(6) Number sites in window\n\n",
+	       kUsageLine, winsize, stepsize, kStatName);
+}
+
+struct Chunk {
+	size_t begin, end;      // byte range
+	uint64_t nlines = 0;    // lines in the chunk
+	uint64_t row0 = 0;      // first output row
+	std::vector<ContigRun> runs;
+	long bad_line = -1;     // chunk-local index of the first malformed line
+};
+
+int main(int argc, char** argv) {
+	unsigned winsize = 1, stepsize = 1;  // fstWindow.cpp:161-162
+	if (argc < 2) {
+		info(winsize, stepsize);
+		return 0;
+	}
+	const double t_start = now_ms();
+	Input in;
+	if (read_input(argv[1], &in, false) != 0) {
+		fprintf(stderr, "%s%s\n", kOpenErr, argv[1]);
+		return -1;
+	}
+	if (argc > 2) {
+		int w = atoi(argv[2]);
+		if (w <= 0) {
+			fprintf(stderr, "Window size must be a positive integer\n");
+			return -1;
+		}
+		winsize = (unsigned)w;
+	}
+	if (argc > 3) {
+		int s = atoi(argv[3]);
+		if (s <= 0) {
+			fprintf(stderr, "Step size must be a positive integer\n");
+			return -1;
+		}
+		stepsize = (unsigned)s;
+	}
+	if (stepsize > winsize) {
+		fprintf(stderr, "Step size must not exceed window size\n");
+		return -1;
+	}
+
+	// ---- parse (timed separately from compute) --------------------------------------------
+	Timing tm;
+	const size_t n_eff = effective_size(in.data, in.size);
+	const unsigned nt = n_eff < (1u << 20) ? 1 : parse_threads();
+	tm.threads = nt;
+	std::vector<size_t> starts = chunk_starts(in.data, 0, n_eff, nt);
+	std::vector<Chunk> chunks(starts.size() - 1);
+	for (size_t i = 0; i + 1 < starts.size(); ++i) {
+		chunks[i].begin = starts[i];
+		chunks[i].end = starts[i + 1];
+	}
+	auto count_lines = [&](Chunk& c) {
+		const char* p = in.data + c.begin;
+		const char* e = in.data + c.end;
+		uint64_t k = 0;
+		while (p < e) {
+			const char* q = (const char*)memchr(p, '\n', (size_t)(e - p));
+			++k;
+			if (!q) break;
+			p = q + 1;
+		}
+		c.nlines = k;
+	};
+	{
+		std::vector<std::thread> th;
+		for (Chunk& c : chunks) th.emplace_back(count_lines, std::ref(c));
+		for (auto& x : th) x.join();
+	}
+	uint64_t n = 0;
+	for (Chunk& c : chunks) {
+		c.row0 = n;
+		n += c.nlines;
+	}
+	uint32_t* pos = (uint32_t*)malloc(std::max<uint64_t>(n, 1) * sizeof(uint32_t));
+#if defined(PGT_TOOL_FST)
+	double* col_a = (double*)malloc(std::max<uint64_t>(n, 1) * sizeof(double));
+	double* col_b = (double*)malloc(std::max<uint64_t>(n, 1) * sizeof(double));
+	if (!pos || !col_a || !col_b) {
+#else
+	int8_t* geno = (int8_t*)malloc(std::max<uint64_t>(n, 1));
+	if (!pos || !geno) {
+#endif
+		fprintf(stderr, "%s: out of memory for %llu sites\n", kTool, (unsigned long long)n);
+		return -1;
+	}
+	auto parse_chunk = [&](Chunk& c) {
+		const char* p = in.data + c.begin;
+		const char* e = in.data + c.end;
+		uint64_t row = c.row0;
+		const char* prev_name = nullptr;
+		size_t prev_len = 0;
+		long li = 0;
+		while (p < e) {
+			const char* q = (const char*)memchr(p, '\n', (size_t)(e - p));
+			const char* le = q ? q : e;
+			const char* s = skip_ws(p, le);
+			const char* t = token_end(s, le);
+			bool ok = t > s;
+			const char* cur = t;
+			if (ok) ok = parse_u32(cur, le, &pos[row]);
+#if defined(PGT_TOOL_FST)
+			if (ok) ok = parse_f64(cur, le, &col_a[row]);
+			if (ok) ok = parse_f64(cur, le, &col_b[row]);
+#else
+			int32_t g = 0;
+			if (ok) ok = parse_i32(cur, le, &g);
+			// hetWindow.cpp:78-80 only distinguishes g < 0, g == 1, other
+			geno[row] = (int8_t)(g < 0 ? -1 : (g > 127 ? 127 : g));
+#endif
+			if (!ok && c.bad_line < 0) c.bad_line = li;
+			if (!prev_name || (size_t)(t - s) != prev_len || memcmp(prev_name, s, prev_len) != 0) {
+				c.runs.push_back(ContigRun{std::string(s, t), 0});
+				prev_name = s;
+				prev_len = (size_t)(t - s);
+			}
+			c.runs.back().count++;
+			++row;
+			++li;
+			if (!q) break;
+			p = q + 1;
+		}
+	};
+	{
+		std::vector<std::thread> th;
+		for (Chunk& c : chunks) th.emplace_back(parse_chunk, std::ref(c));
+		for (auto& x : th) x.join();
+	}
+	std::vector<ContigRun> runs;
+	for (Chunk& c : chunks) {
+		if (c.bad_line >= 0) {
+			fprintf(stderr, "%s: cannot parse line %llu of %s\n", kTool, (unsigned long long)(c.row0 + c.bad_line + 1), argv[1]);
+			return -1;
+		}
+		append_runs(runs, c.runs);
+	}
+	tm.sites = n;
+	tm.parse_ms = now_ms() - t_start;
+	if (n == 0) {
+		tm.total_ms = now_ms() - t_start;
+		tm.report(kTool);
+		return 0;
+	}
+
+	// ---- plan + scan (libpgtscan, CUDA) ------------------------------------------------------
+	const double t_scan = now_ms();
+	std::vector<uint64_t> off(runs.size() + 1, 0);
+	for (size_t i = 0; i < runs.size(); ++i) off[i + 1] = off[i] + runs[i].count;
+	pgt_plan* plan = nullptr;
+	if (pgt_plan_create(&plan, PGT_MODE_SITES, off.data(), (uint32_t)runs.size(), winsize, stepsize, 0) != PGT_OK) {
+		fprintf(stderr, "%s\n", pgt_last_error());
+		return -1;
+	}
+	const uint64_t nwin = pgt_plan_num_windows(plan);
+	std::vector<uint32_t> label(nwin), startp(nwin), endp(nwin), midp(nwin), cnt(nwin);
+	std::vector<double> stat(nwin);
+	if (nwin) {
+		if (select_device() != 0) return -1;
+		pgt_columns cols;
+		memset(&cols, 0, sizeof(cols));
+		cols.pos = pos;
+		pgt_windows out;
+		memset(&out, 0, sizeof(out));
+		out.label = label.data();
+		out.start_pos = startp.data();
+		out.end_pos = endp.data();
+		out.mid_pos = midp.data();
+#if defined(PGT_TOOL_FST)
+		cols.a = col_a;
+		cols.b = col_b;
+		out.fst = stat.data();
+		out.nsites = cnt.data();  // fstWindow.cpp:88 prints *nsites
+		const pgt_stat which = PGT_STAT_FST;
+#else
+		cols.geno = geno;
+		out.het = stat.data();
+		out.nonmissing = cnt.data();  // hetWindow.cpp:87 prints nonmissing
+		const pgt_stat which = PGT_STAT_HET;
+#endif
+		DeviceWorkspace ws;
+		ws.bytes = pgt_scan_workspace_bytes(plan, nullptr, which, PGT_MEM_HOST);
+		if (pgt_device_alloc(&ws.p, ws.bytes) != PGT_OK || pgt_scan(plan, nullptr, which, &cols, 1, nullptr, &out, ws.p, ws.bytes, PGT_MEM_HOST, nullptr) != PGT_OK) {
+			fprintf(stderr, "%s: %s\n", kTool, pgt_last_error());
+			return -1;
+		}
+	}
+	tm.windows = nwin;
+	tm.scan_ms = now_ms() - t_scan;
+
+	// ---- print -----------------------------------------------------------------------------
+	const double t_fmt = now_ms();
+	size_t maxname = 0;
+	for (const ContigRun& r : runs) maxname = std::max(maxname, r.name.size());
+	static char obuf[1 << 20];
+	setvbuf(stdout, obuf, _IOFBF, sizeof(obuf));
+	write_rows(stdout, nwin, maxname + 96, [&](char* p, uint64_t w) {
+		const std::string& nm = runs[label[w]].name;
+		memcpy(p, nm.data(), nm.size());
+		p += nm.size();
+		*p++ = '\t';
+		p = put_u32(p, startp[w]);
+		*p++ = '\t';
+		p = put_u32(p, endp[w]);
+		*p++ = '\t';
+		p = put_u32(p, midp[w]);
+		*p++ = '\t';
+		p = put_g(p, stat[w]);
+		*p++ = '\t';
+		p = put_u32(p, cnt[w]);
+		*p++ = '\n';
+		return p;
+	});
+	fflush(stdout);
+	tm.format_ms = now_ms() - t_fmt;
+	tm.total_ms = now_ms() - t_start;
+	tm.report(kTool);
+	pgt_plan_destroy(plan);
+	return 0;
+}
