@@ -266,33 +266,18 @@ def run_b200(args):
     torch.cuda.synchronize()
 
     # ---- outputs live in one packed buffer so the gather to rank 0 is a single NCCL call
-    from popgenomicstools_b200.scan import _STAT_OUTS, _F64_OUT
+    from popgenomicstools_b200.scan import _STAT_OUTS
+    from popgenomicstools_b200.sharding import PackedWindows, shard_counts
     fields = [k for k in _STAT_OUTS[stat] if k != "dxy_global"]
-    counts = [nwin_local]
-    if world > 1:
-        t = torch.tensor([nwin_local], device=dev, dtype=torch.int64)
-        allc = [torch.zeros_like(t) for _ in range(world)]
-        dist.all_gather(allc, t)
-        counts = [int(x.item()) for x in allc]
-    maxwin = max(max(counts), 1)
-    f64 = [k for k in fields if k in _F64_OUT]
-    u32 = [k for k in fields if k not in _F64_OUT]
-    packed = torch.zeros(maxwin * (8 * len(f64) + 4 * len(u32)) + 64, dtype=torch.uint8, device=dev)
-    out, o = {}, 0
-    for k in f64:
-        out[k] = packed[o:o + 8 * maxwin].view(torch.float64)[:nwin_local]
-        o += 8 * maxwin
-    for k in u32:
-        out[k] = packed[o:o + 4 * maxwin].view(torch.uint32)[:nwin_local]
-        o += 4 * maxwin
-    if fused:
-        out["dxy_global"] = packed[o:o + 24].view(torch.float64)
-    gather_list = [torch.empty_like(packed) for _ in range(world)] if (world > 1 and rank == 0) else None
+    counts = shard_counts(dist, nwin_local, world, dev, torch)
+    pw = PackedWindows(_STAT_OUTS[stat], nwin_local, max(counts), dev, torch)
+    out = pw.views
+    gathered = [None]
 
     def step():
         pgt.scan(plan, stat, cols, minind=5, window_range=(w_lo, w_hi), site_origin=s_lo, out=out)
         if world > 1:
-            dist.gather(packed, gather_list, dst=0)
+            gathered[0] = pw.gather(dist, rank, world, gathered[0])
 
     def barrier():
         if world > 1:

@@ -39,7 +39,11 @@ FLOAT_COL = {"fstWindow": {4}, "hetWindow": {4}, "dxyWindow": {3}}
 
 def test_golden_transcripts_through_the_clis(golden_cases, tmp_path):
     ties = 0
+    # every 3rd transcript through a fresh CLI process (each pays ~1 s of CUDA start-up); ALL
+    # transcripts go through the library in test_fst_gpu.py / test_stats_gpu.py
     for i, c in enumerate(golden_cases):
+        if i % 3:
+            continue
         d = tmp_path / f"c{i}"
         d.mkdir()
         write_case(c, str(d))
@@ -54,7 +58,7 @@ def test_golden_transcripts_through_the_clis(golden_cases, tmp_path):
             ties += P.rows_match_modulo_ties(err.splitlines(), c["stderr"].splitlines(), {0})
         else:
             assert err == c["stderr"]
-    assert ties <= 4, f"{ties} last-digit %g ties over {len(golden_cases)} transcripts"
+    assert ties <= 3, f"{ties} last-digit %g ties"
 
 
 needs_ref = pytest.mark.skipif(O.ref_binary("fstWindow") is None, reason="oracle/_ref not built")
