@@ -226,6 +226,11 @@ int pgt_synth_pos(uint64_t seed, uint64_t site0, uint64_t n, const uint64_t* con
 int pgt_profile(int enable);
 int pgt_profile_read(double* units_ms, uint64_t* units_launches, double* windows_ms, uint64_t* windows_launches);
 
+/* Tuning knobs for tests and experiments (never needed for correct results):
+ *   "level1": 0 auto | 1 direct warp-per-unit kernel (long units only) | 2 tiled TMA-staged kernel
+ *   "level2": 0 auto | 1 always warp-per-window */
+int pgt_tune(const char* key, int value);
+
 /* number of kernels this library has launched in this process (bench.py's gpu_launches) */
 uint64_t pgt_kernel_launch_count(void);
 

@@ -10,7 +10,7 @@ from ._cabi import PgtError
 _cabi.load()
 
 from .scan import (WindowPlan, dxy_window, fst_window, fused_window, het_window, kernel_launch_count, scan,  # noqa: E402
-                   synth_dxy, synth_fst, synth_het, synth_pos, profile, profile_read)
+                   synth_dxy, synth_fst, synth_het, synth_pos, profile, profile_read, tune)
 
 __all__ = ["WindowPlan", "scan", "fst_window", "het_window", "dxy_window", "fused_window", "synth_fst", "synth_het",
            "synth_dxy", "synth_pos", "kernel_launch_count", "PgtError"]

@@ -87,6 +87,7 @@ PROTOTYPES = {
                                 C.c_void_p]),
     "pgt_profile": (C.c_int, [C.c_int]),
     "pgt_profile_read": (C.c_int, [C.POINTER(C.c_double), _u64p, C.POINTER(C.c_double), _u64p]),
+    "pgt_tune": (C.c_int, [C.c_char_p, C.c_int]),
     "pgt_kernel_launch_count": (C.c_uint64, []),
 }
 

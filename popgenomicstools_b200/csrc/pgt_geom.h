@@ -30,6 +30,8 @@ struct pgt_geom {
 	uint32_t upb;     // units in piece B = ceil((S - r) / u)
 	uint32_t upp;     // units per pair   = upa + upb
 	uint32_t wunits;  // units per full window = q * upp + upa
+	uint32_t ueff;    // longest unit = min(u, max(r, S - r))
+	uint32_t gw;      // lanes that reduce one unit: min(32, pow2ceil(ceil(ueff / 8)))
 	uint32_t pad;
 };
 
@@ -56,14 +58,31 @@ PGT_GEOM_HD pgt_geom pgt_make_geom(uint32_t W, uint32_t S, uint32_t u) {
 	g.upb = (S - g.r + u - 1) / u;
 	g.upp = g.upa + g.upb;
 	g.wunits = g.q * g.upp + g.upa;
+	const uint32_t piece = g.r > S - g.r ? g.r : S - g.r;
+	g.ueff = piece < u ? piece : u;
+	uint32_t need = (g.ueff + 7) / 8, gw = 1;
+	while (gw < need && gw < 32) gw <<= 1;
+	g.gw = gw;
 	g.pad = 0;
 	return g;
 }
 
 // Unit j (segment-local) of a segment with N sites: [*start, *start + len) segment-local.
 PGT_GEOM_HD uint32_t pgt_unit_range(const pgt_geom& g, uint64_t N, uint64_t j, uint64_t* start) {
-	uint64_t k = j / g.upp;
-	uint32_t s = (uint32_t)(j - k * g.upp);
+	uint64_t k;
+	uint32_t s;
+	if (g.upp == 1) {  // every piece is one unit (r == 0 and S <= u): no division
+		k = j;
+		s = 0;
+	} else if ((j >> 32) == 0) {
+		const uint32_t jj = (uint32_t)j;
+		const uint32_t kk = jj / g.upp;
+		k = kk;
+		s = jj - kk * g.upp;
+	} else {
+		k = j / g.upp;
+		s = (uint32_t)(j - k * g.upp);
+	}
 	uint64_t st, bound;
 	if (s < g.upa) {
 		st = k * g.S + (uint64_t)s * g.u;

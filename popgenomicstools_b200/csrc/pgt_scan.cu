@@ -11,7 +11,7 @@
 //                              carry across overlapping windows: W/S-fold overlap costs re-reads
 //                              of small partials from L2, never of sites), plus the epilogue
 //                              (ratio, position gather at the two window edges, label lookup).
-//   (dxy)    k_global<Stat>  : dxyWindow's global line from the same unit partials.
+//   (dxy)    k_global_*      : dxyWindow's global line from the same unit partials (two stages).
 //   (bp)     k_bp_bounds     : dxyWindow -fixedsite 0: the reference materialises one buffer entry
 //                              per bp (dxyWindow.cpp:365-372); here units live on the bp axis and
 //                              each unit's site range is found by binary search in `pos` (sparse,
@@ -224,6 +224,10 @@ struct FstStat {
 	};
 	static __device__ __forceinline__ Acc zero() { return Acc{0.0, 0.0}; }
 	static __device__ __forceinline__ Site load(const Cols& c, uint64_t i) { return Site{__ldg(c.a + i), __ldg(c.b + i)}; }
+	// tile columns in staging order (a, b); generic loads: the tile lives in shared memory
+	static __device__ __forceinline__ Site load_tile(const char* const* cp, uint32_t i) {
+		return Site{((const double*)cp[0])[i], ((const double*)cp[1])[i]};
+	}
 	static __device__ __forceinline__ void fold(Acc& acc, const Site& s, int) {
 		acc.a = __dadd_rn(acc.a, s.a);
 		acc.b = __dadd_rn(acc.b, s.b);
@@ -250,6 +254,7 @@ struct HetStat {
 	};
 	static __device__ __forceinline__ Acc zero() { return Acc{0u, 0u}; }
 	static __device__ __forceinline__ Site load(const Cols& c, uint64_t i) { return Site{(int)__ldg(c.g + i)}; }
+	static __device__ __forceinline__ Site load_tile(const char* const* cp, uint32_t i) { return Site{(int)((const int8_t*)cp[0])[i]}; }
 	static __device__ __forceinline__ void fold(Acc& acc, const Site& s, int) {
 		acc.nonmissing += (s.g >= 0);
 		acc.nhet += (s.g == 1);
@@ -284,6 +289,9 @@ struct DxyStat {
 	static __device__ __forceinline__ Acc zero() { return Acc{0.0, 0u, 0u}; }
 	static __device__ __forceinline__ Site load(const Cols& c, uint64_t i) {
 		return Site{__ldg(c.f1 + i), __ldg(c.f2 + i), __ldg(c.n1 + i), __ldg(c.n2 + i)};
+	}
+	static __device__ __forceinline__ Site load_tile(const char* const* cp, uint32_t i) {
+		return Site{((const double*)cp[0])[i], ((const double*)cp[1])[i], ((const int32_t*)cp[2])[i], ((const int32_t*)cp[3])[i]};
 	}
 	static __device__ __forceinline__ void fold(Acc& acc, const Site& s, int minind) {
 		const double v = dxy_site_value(s.f1, s.f2, s.n1, s.n2, minind);
@@ -323,6 +331,10 @@ struct FusedStat {
 	};
 	static __device__ __forceinline__ Acc zero() { return Acc{FstStat::zero(), DxyStat::zero(), HetStat::zero()}; }
 	static __device__ __forceinline__ Site load(const Cols& c, uint64_t i) { return Site{FstStat::load(c, i), DxyStat::load(c, i), HetStat::load(c, i)}; }
+	// staging order: a, b, f1, f2, n1, n2, geno
+	static __device__ __forceinline__ Site load_tile(const char* const* cp, uint32_t i) {
+		return Site{FstStat::load_tile(cp, i), DxyStat::load_tile(cp + 2, i), HetStat::load_tile(cp + 6, i)};
+	}
 	static __device__ __forceinline__ void fold(Acc& acc, const Site& s, int minind) {
 		FstStat::fold(acc.fst, s.fst, minind);
 		DxyStat::fold(acc.dxy, s.dxy, minind);
@@ -347,6 +359,13 @@ template <class Stat>
 __device__ __forceinline__ typename Stat::Acc warp_butterfly(typename Stat::Acc acc) {
 #pragma unroll
 	for (int m = 16; m >= 1; m >>= 1) Stat::add(acc, Stat::shfl_xor(acc, m));
+	return acc;
+}
+// butterfly inside aligned groups of G lanes
+template <class Stat, int G>
+__device__ __forceinline__ typename Stat::Acc group_butterfly(typename Stat::Acc acc) {
+#pragma unroll
+	for (int m = G / 2; m >= 1; m >>= 1) Stat::add(acc, Stat::shfl_xor(acc, m));
 	return acc;
 }
 
@@ -398,6 +417,210 @@ __global__ void __launch_bounds__(256) k_units(DevPlan P, Cols cols, typename St
 	}
 }
 
+// ----------------------------------------------------------------------------- level 1, tiled
+//
+// Persistent CTAs (one per SM) walk tiles of `m` consecutive units.  Warp 0 is the producer: it
+// stages the tile's slice of every column in shared memory with 1-D bulk async copies
+// (cp.async.bulk -> UBLKCP, completion on an mbarrier), two stages deep, so the bytes in flight
+// per SM are one whole tile (64-96 KB) and cost no registers.  Warps 1..15 are consumers: groups
+// of G lanes reduce one unit each straight from shared memory (lane g of a group folds sites
+// g, g+G, g+2G, ... in that order, then a log2(G)-level butterfly), so the summation order is the
+// same function of (W, S, u) as in k_units and does not depend on tiles, CTAs or shards.  G is
+// small when units are short (pgt_geom.gw), which keeps all lanes busy for fine windows.
+// Only the 16-byte-aligned interior of a slice is bulk-copied; the <16-byte head and tail are
+// copied by the producer's lanes, so nothing outside [column, column + n) is ever read.
+
+static constexpr int kTileThreads = 512;
+static constexpr int kTileConsumerWarps = kTileThreads / 32 - 1;
+static constexpr int kMaxTileCols = 7;
+static constexpr uint32_t kTileCtlBytes = 256;
+
+struct TileCfg {
+	const char* gcol[kMaxTileCols];  // global column pointers (element 0 = site_origin), staging order
+	uint32_t elem[kMaxTileCols];     // bytes per site
+	uint32_t col_off[kMaxTileCols];  // byte offset of the column's region inside a stage
+	uint32_t col_cap[kMaxTileCols];  // capacity of that region in bytes
+	uint32_t ncol;
+	uint32_t m;            // units per tile
+	uint32_t stage_bytes;
+	int minind;
+};
+
+struct TileCtl {
+	uint64_t full[2];
+	uint64_t empty[2];
+	uint64_t s0[2];                       // column element index of the tile's first site
+	const char* cp[2][kMaxTileCols];      // where site s0 of each column lives (shared, or global if unstaged)
+};
+static_assert(sizeof(TileCtl) <= kTileCtlBytes, "control block");
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+	asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+	asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+	asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+	asm volatile(
+	    "{\n"
+	    ".reg .pred P1;\n"
+	    "LAB_WAIT:\n"
+	    "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+	    "@P1 bra DONE;\n"
+	    "bra LAB_WAIT;\n"
+	    "DONE:\n"
+	    "}\n" ::"r"(smem_u32(bar)),
+	    "r"(parity)
+	    : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+	asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)), "l"(src),
+	             "r"(bytes), "r"(smem_u32(bar))
+	             : "memory");
+}
+
+// global site (entry) index where global unit j starts / ends
+__device__ __forceinline__ uint64_t unit_bounds_global(const DevPlan& P, uint64_t j, uint64_t* end) {
+	const pgt_seg sg = P.segs[find_seg<true>(P, j)];
+	uint64_t st;
+	const uint32_t len = pgt_unit_range(P.g, sg.nsites, j - sg.unit_base, &st);
+	*end = sg.site_base + st + len;
+	return sg.site_base + st;
+}
+
+template <class Stat, int G, bool INDIRECT>
+__global__ void __launch_bounds__(kTileThreads, 1)
+    k_units_tiled(DevPlan P, TileCfg tc, typename Stat::Acc* __restrict__ units, const uint64_t* __restrict__ bounds) {
+	extern __shared__ __align__(128) unsigned char smem[];
+	TileCtl* ctl = reinterpret_cast<TileCtl*>(smem);
+	unsigned char* stages = smem + kTileCtlBytes;
+	const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+	const uint64_t nunits = P.unit_hi - P.unit_lo;
+	const uint64_t ntiles = (nunits + tc.m - 1) / tc.m;
+
+	if (threadIdx.x == 0) {
+		for (int s = 0; s < 2; ++s) {
+			mbar_init(&ctl->full[s], 2);
+			mbar_init(&ctl->empty[s], kTileConsumerWarps);
+		}
+		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+	}
+	__syncthreads();
+
+	if (warp == 0) {
+		// ------------------------------------------------------------------ producer
+		uint32_t it = 0;
+		for (uint64_t t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
+			const uint32_t stg = it & 1u;
+			if (it >= 2) mbar_wait(&ctl->empty[stg], ((it >> 1) - 1u) & 1u);
+			// generic-proxy reads of this stage are done; order them before the async-proxy writes
+			asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+			const uint64_t j0 = P.unit_lo + t * tc.m;
+			const uint64_t j1 = (P.unit_hi - j0 < tc.m) ? P.unit_hi : j0 + tc.m;
+			uint64_t s0, s1;  // element range of the tile in the columns
+			if (INDIRECT) {
+				s0 = bounds[j0 - P.unit_lo];
+				s1 = bounds[j1 - P.unit_lo];
+			} else {
+				uint64_t e;
+				s0 = unit_bounds_global(P, j0, &e) - P.site_origin;
+				unit_bounds_global(P, j1 - 1, &e);
+				s1 = e - P.site_origin;
+			}
+			unsigned char* stage = stages + (size_t)stg * tc.stage_bytes;
+			uint32_t tx = 0;
+			for (uint32_t c = 0; c < tc.ncol; ++c) {
+				const char* A = tc.gcol[c] + s0 * tc.elem[c];
+				const uint64_t nbytes = (s1 - s0) * tc.elem[c];
+				const uint32_t pad = (uint32_t)((uintptr_t)A & 15u);
+				const bool staged = pad + nbytes <= tc.col_cap[c];
+				unsigned char* region = stage + tc.col_off[c];
+				if (lane == 0) ctl->cp[stg][c] = staged ? (const char*)(region + pad) : A;
+				if (!staged) continue;  // oversized slice (bp mode, more sites than bp): consumers read global memory
+				const char* A0 = (const char*)(((uintptr_t)A + 15u) & ~(uintptr_t)15u);
+				const char* A1 = (const char*)(((uintptr_t)(A + nbytes)) & ~(uintptr_t)15u);
+				uint32_t nh, ntl;
+				if (A1 > A0) {
+					tx += (uint32_t)(A1 - A0);
+					nh = (uint32_t)(A0 - A);
+					ntl = (uint32_t)((A + nbytes) - A1);
+				} else {
+					nh = (uint32_t)nbytes;  // < 32 bytes in total: no aligned interior
+					ntl = 0;
+				}
+				if (lane < nh) region[pad + lane] = (unsigned char)__ldg((const unsigned char*)A + lane);
+				if (lane < ntl) region[pad + (uint32_t)(A1 - A) + lane] = (unsigned char)__ldg((const unsigned char*)A1 + lane);
+			}
+			if (lane == 0) {
+				ctl->s0[stg] = s0;
+				mbar_arrive_expect_tx(&ctl->full[stg], tx);
+				for (uint32_t c = 0; c < tc.ncol; ++c) {
+					const char* A = tc.gcol[c] + s0 * tc.elem[c];
+					const uint64_t nbytes = (s1 - s0) * tc.elem[c];
+					const uint32_t pad = (uint32_t)((uintptr_t)A & 15u);
+					if (pad + nbytes > tc.col_cap[c]) continue;
+					const char* A0 = (const char*)(((uintptr_t)A + 15u) & ~(uintptr_t)15u);
+					const char* A1 = (const char*)(((uintptr_t)(A + nbytes)) & ~(uintptr_t)15u);
+					if (A1 > A0) bulk_g2s(stage + tc.col_off[c] + pad + (uint32_t)(A0 - A), A0, (uint32_t)(A1 - A0), &ctl->full[stg]);
+				}
+			}
+			__syncwarp();
+			if (lane == 0) mbar_arrive(&ctl->full[stg]);  // head/tail bytes and the control words are in place
+		}
+	} else {
+		// ------------------------------------------------------------------ consumers
+		constexpr uint32_t GPW = 32u / G;  // groups per warp
+		const uint32_t gl = lane % G;      // lane inside its group
+		const uint32_t wgroup0 = (warp - 1u) * GPW;
+		constexpr uint32_t NGROUPS = kTileConsumerWarps * GPW;
+		uint32_t si = 0xffffffffu;
+		pgt_seg sg;
+		sg.unit_base = 0;
+		sg.nunits = 0;
+		uint32_t it = 0;
+		for (uint64_t t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
+			const uint32_t stg = it & 1u;
+			mbar_wait(&ctl->full[stg], (it >> 1) & 1u);
+			const uint64_t s0 = ctl->s0[stg];
+			const char* cp[kMaxTileCols];
+#pragma unroll
+			for (int c = 0; c < kMaxTileCols; ++c) cp[c] = ctl->cp[stg][c];
+			const uint64_t j0 = P.unit_lo + t * tc.m;
+			const uint32_t cnt = (uint32_t)((P.unit_hi - j0 < tc.m) ? (P.unit_hi - j0) : tc.m);
+			for (uint32_t base = wgroup0; base < cnt; base += NGROUPS) {  // warp-uniform trip count
+				const uint32_t ul = base + lane / G;
+				const bool active = ul < cnt;
+				const uint64_t j = j0 + (active ? ul : 0u);
+				uint32_t rel, len;
+				if (INDIRECT) {
+					const uint64_t b0 = bounds[j - P.unit_lo], b1 = bounds[j - P.unit_lo + 1];
+					rel = (uint32_t)(b0 - s0);
+					len = (uint32_t)(b1 - b0);
+				} else {
+					if (si == 0xffffffffu || j - sg.unit_base >= sg.nunits) {
+						si = find_seg<true>(P, j);
+						sg = P.segs[si];
+					}
+					uint64_t st;
+					len = pgt_unit_range(P.g, sg.nsites, j - sg.unit_base, &st);
+					rel = (uint32_t)(sg.site_base + st - P.site_origin - s0);
+				}
+				if (!active) len = 0;
+				typename Stat::Acc acc = Stat::zero();
+				for (uint32_t x = gl; x < len; x += G) Stat::fold(acc, Stat::load_tile(cp, rel + x), tc.minind);
+				acc = group_butterfly<Stat, G>(acc);
+				if (active && gl == 0) units[j - P.unit_lo] = acc;
+			}
+			__syncwarp();
+			if (lane == 0) mbar_arrive(&ctl->empty[stg]);
+		}
+	}
+}
+
 // bp mode: bounds[t] = index (relative to the columns' element 0) of the first site at or after
 // the first bp of unit unit_lo+t, t in [0, unit_hi-unit_lo]; the unit's bp -> (chromosome, pos) is
 // closed form, the site is a lower_bound in that chromosome's slice of `pos`.
@@ -436,6 +659,10 @@ __global__ void __launch_bounds__(256) k_bp_bounds(DevPlan P, const uint32_t* __
 
 // ----------------------------------------------------------------------------- level 2
 
+template <class Stat>
+__device__ __forceinline__ void emit_window(const DevPlan& P, const pgt_seg& sg, uint64_t w, uint64_t k, const typename Stat::Acc& acc,
+                                            const uint32_t* __restrict__ pos, const pgt_windows& out);
+
 // One warp per window: lane l adds unit partials l, l+32, ... (from +0.0, so a window of
 // -0.0 values sums to +0.0 exactly as the reference's `double asum = 0`), then the butterfly.
 // units_base = global index of units[0].
@@ -454,34 +681,80 @@ __global__ void __launch_bounds__(256) k_windows(DevPlan P, const typename Stat:
 		typename Stat::Acc acc = Stat::zero();
 		for (uint64_t x = lane; x < cnt; x += 32u) Stat::add(acc, up[x]);
 		acc = warp_butterfly<Stat>(acc);
-		if (lane == 0) {
-			const uint64_t o = w - P.win_lo;
-			uint64_t fs;
-			const uint32_t nsites = pgt_window_sites(P.g, sg, k, &fs);
-			const uint64_t first = sg.site_base + fs, last = first + nsites - 1;
-			const uint32_t label = find_contig(P.off, sg.first_contig, sg.ncontig, last);
-			if (out.label) out.label[o] = label;
-			if (out.nsites) out.nsites[o] = nsites;
-			uint32_t sp = 0, ep = 0;
-			bool have = false;
-			if (P.mode == PGT_MODE_BP) {
-				// dxyWindow.cpp:190 prints the bp position of the first / last buffer entry
-				const uint32_t cf = find_contig(P.off, sg.first_contig, sg.ncontig, first);
-				sp = (uint32_t)(first - P.off[cf]) + 1u;
-				ep = (uint32_t)(last - P.off[label]) + 1u;
-				have = true;
-			} else if (pos) {
-				sp = __ldg(pos + (first - P.site_origin));
-				ep = __ldg(pos + (last - P.site_origin));
-				have = true;
-			}
-			if (have) {
-				if (out.start_pos) out.start_pos[o] = sp;
-				if (out.end_pos) out.end_pos[o] = ep;
-				if (out.mid_pos) out.mid_pos[o] = (sp + ep) / 2u;  // uint32 arithmetic, fstWindow.cpp:73
-			}
-			Stat::emit(out, o, acc);
+		if (lane == 0) emit_window<Stat>(P, sg, w, k, acc, pos, out);
+	}
+}
+
+// Fine windows (<= 32 units each): one THREAD per window, outputs written coalesced.  The value is
+// bit-identical to k_windows: leaf i is (+0.0 + unit i) for i < cnt and +0.0 beyond, combined in
+// the butterfly's order V(i, s) = V(i, 2s) + V(i + s, 2s), evaluated depth-first so only log2(P2)
+// partials are live.
+template <class Stat, int P2, int S>
+struct SmallTree {
+	static __device__ __forceinline__ typename Stat::Acc eval(const typename Stat::Acc* __restrict__ up, uint32_t i, uint32_t cnt) {
+		typename Stat::Acc a = SmallTree<Stat, P2, S * 2>::eval(up, i, cnt);
+		if (i + S < cnt) Stat::add(a, SmallTree<Stat, P2, S * 2>::eval(up, i + S, cnt));  // adding the +0.0 subtree is the identity
+		return a;
+	}
+};
+template <class Stat, int P2>
+struct SmallTree<Stat, P2, P2> {
+	static __device__ __forceinline__ typename Stat::Acc eval(const typename Stat::Acc* __restrict__ up, uint32_t i, uint32_t cnt) {
+		typename Stat::Acc a = Stat::zero();
+		if (i < cnt) Stat::add(a, up[i]);
+		return a;
+	}
+};
+
+template <class Stat>
+__device__ __forceinline__ void emit_window(const DevPlan& P, const pgt_seg& sg, uint64_t w, uint64_t k, const typename Stat::Acc& acc,
+                                            const uint32_t* __restrict__ pos, const pgt_windows& out) {
+	const uint64_t o = w - P.win_lo;
+	uint64_t fs;
+	const uint32_t nsites = pgt_window_sites(P.g, sg, k, &fs);
+	const uint64_t first = sg.site_base + fs, last = first + nsites - 1;
+	const uint32_t label = find_contig(P.off, sg.first_contig, sg.ncontig, last);
+	if (out.label) out.label[o] = label;
+	if (out.nsites) out.nsites[o] = nsites;
+	uint32_t sp = 0, ep = 0;
+	bool have = false;
+	if (P.mode == PGT_MODE_BP) {
+		// dxyWindow.cpp:190 prints the bp position of the first / last buffer entry
+		const uint32_t cf = find_contig(P.off, sg.first_contig, sg.ncontig, first);
+		sp = (uint32_t)(first - P.off[cf]) + 1u;
+		ep = (uint32_t)(last - P.off[label]) + 1u;
+		have = true;
+	} else if (pos) {
+		sp = __ldg(pos + (first - P.site_origin));
+		ep = __ldg(pos + (last - P.site_origin));
+		have = true;
+	}
+	if (have) {
+		if (out.start_pos) out.start_pos[o] = sp;
+		if (out.end_pos) out.end_pos[o] = ep;
+		if (out.mid_pos) out.mid_pos[o] = (sp + ep) / 2u;  // uint32 arithmetic, fstWindow.cpp:73
+	}
+	Stat::emit(out, o, acc);
+}
+
+template <class Stat, int P2>
+__global__ void __launch_bounds__(256) k_windows_small(DevPlan P, const typename Stat::Acc* __restrict__ units, uint64_t units_base,
+                                                        const uint32_t* __restrict__ pos, pgt_windows out) {
+	const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+	uint32_t si = 0xffffffffu;
+	pgt_seg sg;
+	sg.win_base = 0;
+	sg.nwin = 0;
+	for (uint64_t w = P.win_lo + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; w < P.win_hi; w += stride) {
+		if (si == 0xffffffffu || w - sg.win_base >= sg.nwin) {
+			si = find_seg<false>(P, w);
+			sg = P.segs[si];
 		}
+		const uint64_t k = w - sg.win_base;
+		uint64_t fu;
+		const uint32_t cnt = (uint32_t)pgt_window_units(P.g, sg, k, &fu);
+		const typename Stat::Acc acc = SmallTree<Stat, P2, 1>::eval(units + (sg.unit_base + fu - units_base), 0u, cnt);
+		emit_window<Stat>(P, sg, w, k, acc, pos, out);
 	}
 }
 
@@ -498,18 +771,11 @@ struct GlobalOf<FusedStat> {
 	static __device__ __forceinline__ const DxyStat::Acc& get(const FusedStat::Acc& a) { return a.dxy; }
 };
 
-template <class Stat>
-__global__ void __launch_bounds__(1024) k_global(const typename Stat::Acc* __restrict__ units, uint64_t n, double* __restrict__ global3) {
+static constexpr int kGlobalBlocks = 256;  // fixed (part of the summation order of the global line)
+
+__device__ __forceinline__ void block_reduce_global(double d, unsigned long long ne, unsigned long long nk, double* __restrict__ out3) {
 	__shared__ double s_d[32];
 	__shared__ unsigned long long s_e[32], s_k[32];
-	double d = 0.0;
-	unsigned long long ne = 0, nk = 0;
-	for (uint64_t i = threadIdx.x; i < n; i += 1024u) {
-		const DxyStat::Acc& a = GlobalOf<Stat>::get(units[i]);
-		d = __dadd_rn(d, a.dxy);
-		ne += a.neff;
-		nk += a.nskip;
-	}
 #pragma unroll
 	for (int m = 16; m >= 1; m >>= 1) {
 		d = __dadd_rn(d, shfl_xor_f64(d, m));
@@ -523,9 +789,10 @@ __global__ void __launch_bounds__(1024) k_global(const typename Stat::Acc* __res
 	}
 	__syncthreads();
 	if (threadIdx.x < 32) {
-		d = s_d[threadIdx.x];
-		ne = s_e[threadIdx.x];
-		nk = s_k[threadIdx.x];
+		const uint32_t nw = blockDim.x >> 5;
+		d = threadIdx.x < nw ? s_d[threadIdx.x] : 0.0;
+		ne = threadIdx.x < nw ? s_e[threadIdx.x] : 0ull;
+		nk = threadIdx.x < nw ? s_k[threadIdx.x] : 0ull;
 #pragma unroll
 		for (int m = 16; m >= 1; m >>= 1) {
 			d = __dadd_rn(d, shfl_xor_f64(d, m));
@@ -533,11 +800,30 @@ __global__ void __launch_bounds__(1024) k_global(const typename Stat::Acc* __res
 			nk += __shfl_xor_sync(0xffffffffu, nk, m);
 		}
 		if (threadIdx.x == 0) {
-			global3[0] = d;
-			global3[1] = (double)ne;
-			global3[2] = (double)nk;
+			out3[0] = d;
+			out3[1] = (double)ne;
+			out3[2] = (double)nk;
 		}
 	}
+}
+
+// stage 1: block b adds partials b*1024 + t + k*(256*1024) per thread t, then reduces the block
+template <class Stat>
+__global__ void __launch_bounds__(1024) k_global_partial(const typename Stat::Acc* __restrict__ units, uint64_t n, double* __restrict__ partial3) {
+	double d = 0.0;
+	unsigned long long ne = 0, nk = 0;
+	for (uint64_t i = (uint64_t)blockIdx.x * 1024u + threadIdx.x; i < n; i += (uint64_t)kGlobalBlocks * 1024u) {
+		const DxyStat::Acc& a = GlobalOf<Stat>::get(units[i]);
+		d = __dadd_rn(d, a.dxy);
+		ne += a.neff;
+		nk += a.nskip;
+	}
+	block_reduce_global(d, ne, nk, partial3 + 3 * blockIdx.x);
+}
+// stage 2: one block over the 256 block partials
+__global__ void __launch_bounds__(kGlobalBlocks) k_global_final(const double* __restrict__ partial3, double* __restrict__ global3) {
+	block_reduce_global(partial3[3 * threadIdx.x], (unsigned long long)partial3[3 * threadIdx.x + 1],
+	                    (unsigned long long)partial3[3 * threadIdx.x + 2], global3);
 }
 
 // ----------------------------------------------------------------------------- host side of a scan
@@ -581,7 +867,7 @@ static size_t acc_bytes(pgt_stat stat) {
 
 struct Layout {
 	uint64_t w_lo, w_hi, u_lo, u_hi, g_hi, origin;
-	size_t segs_off, off_off, siteoff_off, units_off, bounds_off, stage_off, outs_off, total;
+	size_t segs_off, off_off, siteoff_off, gpart_off, units_off, bounds_off, stage_off, outs_off, total;
 	size_t stage_col_bytes[8];
 	uint64_t slab_sites;
 };
@@ -630,6 +916,8 @@ static int make_layout(const pgt_plan* plan, const pgt_range* range, pgt_stat st
 	o += align_up(plan->off.size() * sizeof(uint64_t), 256);
 	L->siteoff_off = o;
 	if (plan->mode == PGT_MODE_BP) o += align_up(plan->off.size() * sizeof(uint64_t), 256);
+	L->gpart_off = o;
+	o += align_up((size_t)kGlobalBlocks * 3 * sizeof(double), 256);
 	L->units_off = o;
 	o += align_up((size_t)nunits * acc_bytes(stat) + 8, 256);
 	L->bounds_off = o;
@@ -656,10 +944,96 @@ extern "C" size_t pgt_scan_workspace_bytes(const pgt_plan* plan, const pgt_range
 	return L.total;
 }
 
+// tuning knobs (tests / experiments): level1 = 0 auto, 1 force the direct kernel (k_units, only
+// valid when pgt_geom.gw == 32), 2 force the tiled kernel (k_units_tiled)
+static int g_tune_level1 = 0;
+static int g_tune_level2 = 0;  // 0 auto, 1 force warp-per-window
+extern "C" int pgt_tune(const char* key, int value) {
+	if (key && strcmp(key, "level1") == 0) g_tune_level1 = value;
+	else if (key && strcmp(key, "level2") == 0) g_tune_level2 = value;
+	else return pgt_set_error(PGT_ERR_ARGS, "pgt_tune: unknown key");
+	return PGT_OK;
+}
+
+struct StatCols {
+	const void* ptr[kMaxTileCols];
+	uint32_t elem[kMaxTileCols];
+	uint32_t n;
+};
+template <class Stat>
+static StatCols tile_columns(const Cols& c);
+template <>
+StatCols tile_columns<FstStat>(const Cols& c) { return StatCols{{c.a, c.b}, {8, 8}, 2}; }
+template <>
+StatCols tile_columns<HetStat>(const Cols& c) { return StatCols{{c.g}, {1}, 1}; }
+template <>
+StatCols tile_columns<DxyStat>(const Cols& c) { return StatCols{{c.f1, c.f2, c.n1, c.n2}, {8, 8, 4, 4}, 4}; }
+template <>
+StatCols tile_columns<FusedStat>(const Cols& c) { return StatCols{{c.a, c.b, c.f1, c.f2, c.n1, c.n2, c.g}, {8, 8, 8, 8, 4, 4, 1}, 7}; }
+
+template <class Stat, bool INDIRECT>
+static int launch_units_tiled(const DevPlan& P, const Cols& cols, typename Stat::Acc* units, const uint64_t* bounds, cudaStream_t st) {
+	const uint64_t nunits = P.unit_hi - P.unit_lo;
+	const StatCols sc = tile_columns<Stat>(cols);
+	uint32_t bps = 0;
+	for (uint32_t c = 0; c < sc.n; ++c) bps += sc.elem[c];
+	const int nsm = num_sms();
+	// two stages of <= 96 KB; tiles of whole units; at least ~4 tiles per SM when the input allows
+	const uint32_t stage_budget = 96u * 1024u;
+	uint32_t tsites = (stage_budget - 48u * sc.n) / bps;
+	if (tsites > 16384u) tsites = 16384u;
+	uint32_t m = tsites / P.g.ueff;
+	if (m < 1) m = 1;
+	const uint64_t want_tiles = (uint64_t)nsm * 4;
+	if ((nunits + m - 1) / m < want_tiles) {
+		uint64_t mm = (nunits + want_tiles - 1) / want_tiles;
+		m = (uint32_t)(mm < 1 ? 1 : mm);
+	}
+	TileCfg tc;
+	memset(&tc, 0, sizeof(tc));
+	tc.ncol = sc.n;
+	tc.m = m;
+	tc.minind = cols.minind;
+	uint32_t o = 0;
+	for (uint32_t c = 0; c < sc.n; ++c) {
+		tc.gcol[c] = (const char*)sc.ptr[c];
+		tc.elem[c] = sc.elem[c];
+		tc.col_off[c] = o;
+		tc.col_cap[c] = (uint32_t)align_up((size_t)m * P.g.ueff * sc.elem[c] + 32, 16);
+		o += tc.col_cap[c];
+	}
+	tc.stage_bytes = (uint32_t)align_up(o, 128);
+	const size_t smem = kTileCtlBytes + 2 * (size_t)tc.stage_bytes;
+	void (*kern)(DevPlan, TileCfg, typename Stat::Acc*, const uint64_t*);
+	switch (P.g.gw) {
+		case 1: kern = k_units_tiled<Stat, 1, INDIRECT>; break;
+		case 2: kern = k_units_tiled<Stat, 2, INDIRECT>; break;
+		case 4: kern = k_units_tiled<Stat, 4, INDIRECT>; break;
+		case 8: kern = k_units_tiled<Stat, 8, INDIRECT>; break;
+		case 16: kern = k_units_tiled<Stat, 16, INDIRECT>; break;
+		default: kern = k_units_tiled<Stat, 32, INDIRECT>; break;
+	}
+	PGT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+	const uint64_t ntiles = (nunits + m - 1) / m;
+	const unsigned grid = (unsigned)(ntiles < (uint64_t)nsm ? ntiles : (uint64_t)nsm);
+	{
+		ProfScope prof(0, st);
+		kern<<<grid, kTileThreads, smem, st>>>(P, tc, units, bounds);
+	}
+	g_launches++;
+	PGT_CUDA(cudaGetLastError());
+	return PGT_OK;
+}
+
 template <class Stat>
 static int launch_units(const DevPlan& P, const Cols& cols, typename Stat::Acc* units, const uint64_t* bounds, cudaStream_t st) {
 	const uint64_t nunits = P.unit_hi - P.unit_lo;
 	if (nunits == 0) return PGT_OK;
+	// The direct kernel reduces every unit with a full warp: it implements the summation order only
+	// when gw == 32 (long units).  Short units always go through the tiled kernel.
+	bool tiled = P.g.gw != 32 || g_tune_level1 == 2;
+	if (g_tune_level1 == 1 && P.g.gw == 32) tiled = false;
+	if (tiled) return bounds ? launch_units_tiled<Stat, true>(P, cols, units, bounds, st) : launch_units_tiled<Stat, false>(P, cols, units, bounds, st);
 	const int threads = 256;
 	const uint64_t want = (nunits + 7) / 8;  // one warp per unit, 8 warps per block
 	const uint32_t upl = P.g.u / 32u;
@@ -694,10 +1068,22 @@ static int launch_windows(const DevPlan& P, const typename Stat::Acc* units, uin
                           const pgt_windows& out, cudaStream_t st) {
 	const uint64_t nwin = P.win_hi - P.win_lo;
 	if (nwin == 0) return PGT_OK;
-	const uint64_t want = (nwin + 7) / 8;
 	const uint64_t cap = (uint64_t)num_sms() * 8;
-	{
-		ProfScope prof(1, st);
+	ProfScope prof(1, st);
+	if (P.g.wunits <= 32 && g_tune_level2 != 1) {
+		// fine windows: a thread per window
+		void (*kern)(DevPlan, const typename Stat::Acc*, uint64_t, const uint32_t*, pgt_windows);
+		const uint32_t wu = P.g.wunits;
+		if (wu <= 1) kern = k_windows_small<Stat, 1>;
+		else if (wu <= 2) kern = k_windows_small<Stat, 2>;
+		else if (wu <= 4) kern = k_windows_small<Stat, 4>;
+		else if (wu <= 8) kern = k_windows_small<Stat, 8>;
+		else if (wu <= 16) kern = k_windows_small<Stat, 16>;
+		else kern = k_windows_small<Stat, 32>;
+		const uint64_t want = (nwin + 255) / 256;
+		kern<<<(unsigned)(want < cap ? want : cap), 256, 0, st>>>(P, units, units_base, pos, out);
+	} else {
+		const uint64_t want = (nwin + 7) / 8;
 		k_windows<Stat><<<(unsigned)(want < cap ? want : cap), 256, 0, st>>>(P, units, units_base, pos, out);
 	}
 	g_launches++;
@@ -706,20 +1092,22 @@ static int launch_windows(const DevPlan& P, const typename Stat::Acc* units, uin
 }
 
 template <class Stat>
-static int launch_global(const typename Stat::Acc*, uint64_t, double*, cudaStream_t) {
+static int launch_global(const typename Stat::Acc*, uint64_t, double*, double*, cudaStream_t) {
 	return PGT_OK;
 }
 template <>
-int launch_global<DxyStat>(const DxyStat::Acc* units, uint64_t n, double* g3, cudaStream_t st) {
-	k_global<DxyStat><<<1, 1024, 0, st>>>(units, n, g3);
-	g_launches++;
+int launch_global<DxyStat>(const DxyStat::Acc* units, uint64_t n, double* scratch, double* g3, cudaStream_t st) {
+	k_global_partial<DxyStat><<<kGlobalBlocks, 1024, 0, st>>>(units, n, scratch);
+	k_global_final<<<1, kGlobalBlocks, 0, st>>>(scratch, g3);
+	g_launches += 2;
 	PGT_CUDA(cudaGetLastError());
 	return PGT_OK;
 }
 template <>
-int launch_global<FusedStat>(const FusedStat::Acc* units, uint64_t n, double* g3, cudaStream_t st) {
-	k_global<FusedStat><<<1, 1024, 0, st>>>(units, n, g3);
-	g_launches++;
+int launch_global<FusedStat>(const FusedStat::Acc* units, uint64_t n, double* scratch, double* g3, cudaStream_t st) {
+	k_global_partial<FusedStat><<<kGlobalBlocks, 1024, 0, st>>>(units, n, scratch);
+	k_global_final<<<1, kGlobalBlocks, 0, st>>>(scratch, g3);
+	g_launches += 2;
 	PGT_CUDA(cudaGetLastError());
 	return PGT_OK;
 }
@@ -826,7 +1214,7 @@ static int run_scan(const pgt_plan* plan, const pgt_range* range, pgt_stat stat,
 		if (bp && nunits) PGT_TRY(launch_bounds_kernel(P, cols->pos, ndata, bounds, st));
 		PGT_TRY(launch_units<Stat>(P, C, units, bounds, st));
 		PGT_TRY(launch_windows<Stat>(P, units, L.u_lo, cols->pos, *out, st));
-		if (want_global) PGT_TRY(launch_global<Stat>(units, nglobal, out->dxy_global, st));
+		if (want_global) PGT_TRY(launch_global<Stat>(units, nglobal, (double*)(ws + L.gpart_off), out->dxy_global, st));
 		return PGT_OK;
 	}
 
@@ -921,7 +1309,7 @@ static int run_scan(const pgt_plan* plan, const pgt_range* range, pgt_stat stat,
 	dev.nskip = (uint32_t*)dptr(out->nskip);
 	dev.dxy_global = want_global ? (double*)(ob0 + ob * 11) : nullptr;
 	PGT_TRY(launch_windows<Stat>(P, units, L.u_lo, nullptr, dev, st));
-	if (want_global) PGT_TRY(launch_global<Stat>(units, nglobal, dev.dxy_global, st));
+	if (want_global) PGT_TRY(launch_global<Stat>(units, nglobal, (double*)(ws + L.gpart_off), dev.dxy_global, st));
 	auto back = [&](void* h, const void* d, size_t elem) -> cudaError_t {
 		return (h && d && nwin) ? cudaMemcpyAsync(h, d, nwin * elem, cudaMemcpyDeviceToHost, st) : cudaSuccess;
 	};

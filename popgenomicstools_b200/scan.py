@@ -296,3 +296,8 @@ def profile_read():
     un, wn = C.c_uint64(), C.c_uint64()
     check(_cabi.load().pgt_profile_read(C.byref(um), C.byref(un), C.byref(wm), C.byref(wn)))
     return dict(units_ms=um.value, units_launches=un.value, windows_ms=wm.value, windows_launches=wn.value)
+
+
+def tune(key, value):
+    """Kernel-selection knobs for tests/experiments (pgt_tune)."""
+    check(_cabi.load().pgt_tune(key.encode(), int(value)))

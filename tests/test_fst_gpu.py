@@ -137,3 +137,40 @@ def test_shards_bit_identical(pgt):
         for k in full:
             cat = np.concatenate([p[k] for p in parts])
             assert cat.tobytes() == full[k].tobytes(), (nsh, k)
+
+
+@pytest.mark.parametrize("W,S", [(50000, 10000), (4096, 4096), (300, 299), (2560, 256)])
+def test_tiled_and_direct_level1_are_bit_identical(pgt, W, S):
+    """Both level-1 kernels implement the same summation order (lane-strided partials + butterfly
+    per unit): for long units (group width 32) the TMA-staged tiled kernel and the direct
+    warp-per-unit kernel must agree bit for bit, at any tile/CTA placement."""
+    import torch
+    lengths = [W + 3 * S, 123457, 7, 60001]
+    offs = np.concatenate([[0], np.cumsum(lengths)]).astype(np.uint64)
+    n = int(offs[-1])
+    a, b = pgt.synth_fst(8, 0, n)
+    pos = pgt.synth_pos(8, 0, n, offs, 1)
+    plan = pgt.WindowPlan(offs, W, S)
+    res = {}
+    try:
+        for mode in (1, 2):
+            pgt.tune("level1", mode)
+            o = pgt.fst_window(plan, pos, a, b)
+            torch.cuda.synchronize()
+            res[mode] = {k: v.cpu().numpy() for k, v in o.items()}
+    finally:
+        pgt.tune("level1", 0)
+    for k in res[1]:
+        assert res[1][k].tobytes() == res[2][k].tobytes(), k
+    # unaligned column pointers (views starting at odd elements) exercise the head/tail path
+    a2, b2 = torch.empty(n + 3, dtype=torch.float64, device="cuda"), torch.empty(n + 5, dtype=torch.float64, device="cuda")
+    a2[3:].copy_(a)
+    b2[5:].copy_(b)
+    try:
+        pgt.tune("level1", 2)
+        o = pgt.fst_window(plan, pos, a2[3:], b2[5:])
+        torch.cuda.synchronize()
+    finally:
+        pgt.tune("level1", 0)
+    for k in res[1]:
+        assert o[k].cpu().numpy().tobytes() == res[1][k].tobytes(), k

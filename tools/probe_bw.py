@@ -1,32 +1,43 @@
-"""Scratch probe: level-1/level-2 timing of the fst scan at several sizes (not the bench)."""
-import sys, time
+"""Scratch probe: level-1/level-2 timing at several (stat, n, W, S, unit, level1) points (not the bench).
+usage: probe_bw.py stat,n,W,S,unit,level1 ..."""
+import sys
 import numpy as np, torch
 sys.path.insert(0, ".")
 import popgenomicstools_b200 as pgt
+from popgenomicstools_b200 import _cabi
+from popgenomicstools_b200.workloads import human_like_contigs
 
-def contigs(n_total, S):
-    mb = [248,242,198,190,182,171,159,145,138,134,135,133,114,107,102,90,83,80,59,64,47,51,156,57]
-    tot = sum(mb); L = [n_total*m//tot for m in mb]
-    L[0] = max(S, L[0]//S*S)
-    L[-1] += n_total - sum(L)
-    return np.concatenate([[0], np.cumsum(L)]).astype(np.uint64)
-
-for n, W, S, unit in [(int(float(x.split(',')[0])), int(x.split(',')[1]), int(x.split(',')[2]), int(x.split(',')[3])) for x in sys.argv[1:]]:
-    offs = contigs(n, S)
+BPS = {"fst": 16, "het": 1, "dxy": 24, "fused": 41}
+STAT = {"fst": _cabi.PGT_STAT_FST, "het": _cabi.PGT_STAT_HET, "dxy": _cabi.PGT_STAT_DXY, "fused": _cabi.PGT_STAT_FUSED}
+for spec in sys.argv[1:]:
+    stat, n, W, S, unit, l1 = spec.split(",")
+    n, W, S, unit, l1 = int(float(n)), int(W), int(S), int(unit), int(l1)
+    _, offs = human_like_contigs(n, S)
     plan = pgt.WindowPlan(offs, W, S, unit_sites=unit)
-    a, b = pgt.synth_fst(4, 0, n)
-    pos = pgt.synth_pos(4, 0, n, offs, 1)
+    cols = dict(pos=pgt.synth_pos(4, 0, n, offs, 1))
+    if stat in ("fst", "fused"):
+        cols["a"], cols["b"] = pgt.synth_fst(4, 0, n)
+    if stat in ("het", "fused"):
+        cols["geno"] = pgt.synth_het(4, 0, n)
+    if stat in ("dxy", "fused"):
+        cols["f1"], cols["f2"], cols["n1"], cols["n2"] = pgt.synth_dxy(4, 0, n)
+    pgt.tune("level1", l1)
     torch.cuda.synchronize()
-    out = pgt.fst_window(plan, pos, a, b)
-    for _ in range(3): pgt.fst_window(plan, pos, a, b, out=out)
+    out = pgt.scan(plan, STAT[stat], cols, minind=5)
+    for _ in range(3):
+        pgt.scan(plan, STAT[stat], cols, minind=5, out=out)
     torch.cuda.synchronize()
+    pgt.profile(True); pgt.profile_read()
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
     K = 10
     ev[0].record()
-    for _ in range(K): pgt.fst_window(plan, pos, a, b, out=out)
+    for _ in range(K):
+        pgt.scan(plan, STAT[stat], cols, minind=5, out=out)
     ev[1].record(); torch.cuda.synchronize()
+    pr = pgt.profile_read(); pgt.profile(False)
     ms = ev[0].elapsed_time(ev[1]) / K
-    print(f"n={n:.3g} W={W} S={S} u={unit} windows={plan.num_windows} units={plan.num_units} ms={ms:.4f} "
-          f"sites/s={n/ms*1e3:.4g} GB/s(16B)={16*n/ms/1e6:.1f} GB/s(20B)={20*n/ms/1e6:.1f}", flush=True)
-    del a, b, pos, out, plan
+    l1ms = pr["units_ms"] / K; l2ms = pr["windows_ms"] / K
+    print(f"{stat} n={n:.3g} W={W} S={S} u={unit} l1={l1} win={plan.num_windows} units={plan.num_units} step_ms={ms:.4f} "
+          f"L1_ms={l1ms:.4f} L2_ms={l2ms:.4f} sites/s={n/ms*1e3:.4g} L1_GB/s={BPS[stat]*n/l1ms/1e6:.1f}", flush=True)
+    del cols, out, plan
     torch.cuda.empty_cache()
