@@ -431,9 +431,11 @@ __global__ void __launch_bounds__(256) k_units(DevPlan P, Cols cols, typename St
 // copied by the producer's lanes, so nothing outside [column, column + n) is ever read.
 
 static constexpr int kTileThreads = 512;
+static constexpr int kTileMaxStages = 4;
 static constexpr int kTileConsumerWarps = kTileThreads / 32 - 1;
 static constexpr int kMaxTileCols = 7;
-static constexpr uint32_t kTileCtlBytes = 256;
+static constexpr uint32_t kTileCtlBytes = 384;
+
 
 struct TileCfg {
 	const char* gcol[kMaxTileCols];  // global column pointers (element 0 = site_origin), staging order
@@ -443,14 +445,16 @@ struct TileCfg {
 	uint32_t ncol;
 	uint32_t m;            // units per tile
 	uint32_t stage_bytes;
+	uint32_t nstages;      // 2..kTileMaxStages
 	int minind;
+	uint64_t valid_elems;  // elements every column holds from element 0 (bounds the aligned superset copies)
 };
 
 struct TileCtl {
-	uint64_t full[2];
-	uint64_t empty[2];
-	uint64_t s0[2];                       // column element index of the tile's first site
-	const char* cp[2][kMaxTileCols];      // where site s0 of each column lives (shared, or global if unstaged)
+	uint64_t full[kTileMaxStages];
+	uint64_t empty[kTileMaxStages];
+	uint64_t s0[kTileMaxStages];                   // column element index of the tile's first site
+	const char* cp[kTileMaxStages][kMaxTileCols];  // where site s0 of each column lives (shared, or global if unstaged)
 };
 static_assert(sizeof(TileCtl) <= kTileCtlBytes, "control block");
 
@@ -503,7 +507,7 @@ __global__ void __launch_bounds__(kTileThreads, 1)
 	const uint64_t ntiles = (nunits + tc.m - 1) / tc.m;
 
 	if (threadIdx.x == 0) {
-		for (int s = 0; s < 2; ++s) {
+		for (uint32_t s = 0; s < tc.nstages; ++s) {
 			mbar_init(&ctl->full[s], 2);
 			mbar_init(&ctl->empty[s], kTileConsumerWarps);
 		}
@@ -513,12 +517,27 @@ __global__ void __launch_bounds__(kTileThreads, 1)
 
 	if (warp == 0) {
 		// ------------------------------------------------------------------ producer
+		// lane c stages column c: the bulk copy covers the 16-byte-aligned SUPERSET of the slice
+		// whenever that stays inside the column (always, except at the first/last elements of a
+		// column that is not 16-byte aligned/padded); only then are head/tail bytes copied by hand.
 		uint32_t it = 0;
+		uint32_t psi = 0xffffffffu;  // cached segment of the producer
+		pgt_seg psg;
+		psg.unit_base = 0;
+		psg.nunits = 0;
+		auto unit_span = [&](uint64_t j, uint64_t* end) -> uint64_t {  // global [start, end) of unit j
+			if (psi == 0xffffffffu || j - psg.unit_base >= psg.nunits) {
+				psi = find_seg<true>(P, j);
+				psg = P.segs[psi];
+			}
+			uint64_t st;
+			const uint32_t len = pgt_unit_range(P.g, psg.nsites, j - psg.unit_base, &st);
+			*end = psg.site_base + st + len;
+			return psg.site_base + st;
+		};
 		for (uint64_t t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
-			const uint32_t stg = it & 1u;
-			if (it >= 2) mbar_wait(&ctl->empty[stg], ((it >> 1) - 1u) & 1u);
-			// generic-proxy reads of this stage are done; order them before the async-proxy writes
-			asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+			const uint32_t stg = it % tc.nstages;
+			// the tile's element range is computed BEFORE waiting for the stage to drain
 			const uint64_t j0 = P.unit_lo + t * tc.m;
 			const uint64_t j1 = (P.unit_hi - j0 < tc.m) ? P.unit_hi : j0 + tc.m;
 			uint64_t s0, s1;  // element range of the tile in the columns
@@ -527,49 +546,61 @@ __global__ void __launch_bounds__(kTileThreads, 1)
 				s1 = bounds[j1 - P.unit_lo];
 			} else {
 				uint64_t e;
-				s0 = unit_bounds_global(P, j0, &e) - P.site_origin;
-				unit_bounds_global(P, j1 - 1, &e);
+				s0 = unit_span(j0, &e) - P.site_origin;
+				unit_span(j1 - 1, &e);
 				s1 = e - P.site_origin;
 			}
+			if (it >= tc.nstages) mbar_wait(&ctl->empty[stg], ((it / tc.nstages) - 1u) & 1u);
+			// generic-proxy reads of this stage are done; order them before the async-proxy writes
+			asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 			unsigned char* stage = stages + (size_t)stg * tc.stage_bytes;
-			uint32_t tx = 0;
-			for (uint32_t c = 0; c < tc.ncol; ++c) {
-				const char* A = tc.gcol[c] + s0 * tc.elem[c];
-				const uint64_t nbytes = (s1 - s0) * tc.elem[c];
-				const uint32_t pad = (uint32_t)((uintptr_t)A & 15u);
-				const bool staged = pad + nbytes <= tc.col_cap[c];
-				unsigned char* region = stage + tc.col_off[c];
-				if (lane == 0) ctl->cp[stg][c] = staged ? (const char*)(region + pad) : A;
-				if (!staged) continue;  // oversized slice (bp mode, more sites than bp): consumers read global memory
-				const char* A0 = (const char*)(((uintptr_t)A + 15u) & ~(uintptr_t)15u);
-				const char* A1 = (const char*)(((uintptr_t)(A + nbytes)) & ~(uintptr_t)15u);
-				uint32_t nh, ntl;
-				if (A1 > A0) {
-					tx += (uint32_t)(A1 - A0);
-					nh = (uint32_t)(A0 - A);
-					ntl = (uint32_t)((A + nbytes) - A1);
-				} else {
-					nh = (uint32_t)nbytes;  // < 32 bytes in total: no aligned interior
-					ntl = 0;
-				}
-				if (lane < nh) region[pad + lane] = (unsigned char)__ldg((const unsigned char*)A + lane);
-				if (lane < ntl) region[pad + (uint32_t)(A1 - A) + lane] = (unsigned char)__ldg((const unsigned char*)A1 + lane);
+			const uint32_t c = lane < tc.ncol ? lane : 0u;
+			const char* A = tc.gcol[c] + s0 * tc.elem[c];
+			const uint64_t nbytes = (s1 - s0) * tc.elem[c];
+			const uint32_t pad = (uint32_t)((uintptr_t)A & 15u);
+			const bool staged = lane < tc.ncol && pad + nbytes + 16u <= tc.col_cap[c];
+			unsigned char* region = stage + tc.col_off[c];
+			const char* col_lo = tc.gcol[c];
+			const char* col_hi = tc.gcol[c] + tc.valid_elems * tc.elem[c];
+			const char* B0 = A - pad;  // aligned superset [B0, B1)
+			const char* B1 = (const char*)(((uintptr_t)(A + nbytes) + 15u) & ~(uintptr_t)15u);
+			uint32_t nh = 0, ntl = 0;
+			if (B0 < col_lo) {  // cannot read before the column: copy the head by hand
+				B0 += 16;
+				nh = 16u - pad;
+				if (nh > nbytes) nh = (uint32_t)nbytes;
 			}
+			if (B1 > col_hi) {  // cannot read past the column: copy the tail by hand
+				B1 -= 16;
+				ntl = (uint32_t)((A + nbytes) - B1);
+				if (B1 < A + nh) ntl = (uint32_t)(nbytes - nh);
+			}
+			uint32_t tx = (staged && B1 > B0) ? (uint32_t)(B1 - B0) : 0u;
+			if (lane < tc.ncol) ctl->cp[stg][c] = staged ? (const char*)(region + pad) : A;
+			uint32_t txsum = tx;
+#pragma unroll
+			for (int m = 16; m >= 1; m >>= 1) txsum += __shfl_xor_sync(0xffffffffu, txsum, m);
 			if (lane == 0) {
 				ctl->s0[stg] = s0;
-				mbar_arrive_expect_tx(&ctl->full[stg], tx);
-				for (uint32_t c = 0; c < tc.ncol; ++c) {
-					const char* A = tc.gcol[c] + s0 * tc.elem[c];
-					const uint64_t nbytes = (s1 - s0) * tc.elem[c];
-					const uint32_t pad = (uint32_t)((uintptr_t)A & 15u);
-					if (pad + nbytes > tc.col_cap[c]) continue;
-					const char* A0 = (const char*)(((uintptr_t)A + 15u) & ~(uintptr_t)15u);
-					const char* A1 = (const char*)(((uintptr_t)(A + nbytes)) & ~(uintptr_t)15u);
-					if (A1 > A0) bulk_g2s(stage + tc.col_off[c] + pad + (uint32_t)(A0 - A), A0, (uint32_t)(A1 - A0), &ctl->full[stg]);
-				}
+				mbar_arrive_expect_tx(&ctl->full[stg], txsum);
 			}
 			__syncwarp();
-			if (lane == 0) mbar_arrive(&ctl->full[stg]);  // head/tail bytes and the control words are in place
+			if (tx) bulk_g2s(region + pad + (B0 - A), B0, tx, &ctl->full[stg]);
+			// rare: hand-copied head / tail bytes
+			const uint32_t any = __ballot_sync(0xffffffffu, staged && (nh | ntl));
+			for (uint32_t cc = 0; cc < tc.ncol; ++cc) {
+				if (!((any >> cc) & 1u)) continue;
+				const uint32_t nh_c = __shfl_sync(0xffffffffu, nh, cc), nt_c = __shfl_sync(0xffffffffu, ntl, cc);
+				const uint32_t pad_c = __shfl_sync(0xffffffffu, pad, cc);
+				const unsigned long long A_c = __shfl_sync(0xffffffffu, (unsigned long long)(uintptr_t)A, cc);
+				const unsigned long long nb_c = __shfl_sync(0xffffffffu, (unsigned long long)nbytes, cc);
+				unsigned char* reg_c = stage + tc.col_off[cc];
+				const unsigned char* Ac = (const unsigned char*)(uintptr_t)A_c;
+				if (lane < nh_c) reg_c[pad_c + lane] = __ldg(Ac + lane);
+				if (lane < nt_c) reg_c[pad_c + (uint32_t)(nb_c - nt_c) + lane] = __ldg(Ac + (nb_c - nt_c) + lane);
+			}
+			__syncwarp();
+			if (lane == 0) mbar_arrive(&ctl->full[stg]);  // control words (and any head/tail bytes) are in place
 		}
 	} else {
 		// ------------------------------------------------------------------ consumers
@@ -583,16 +614,22 @@ __global__ void __launch_bounds__(kTileThreads, 1)
 		sg.nunits = 0;
 		uint32_t it = 0;
 		for (uint64_t t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
-			const uint32_t stg = it & 1u;
-			mbar_wait(&ctl->full[stg], (it >> 1) & 1u);
+			const uint32_t stg = it % tc.nstages;
+			mbar_wait(&ctl->full[stg], (it / tc.nstages) & 1u);
 			const uint64_t s0 = ctl->s0[stg];
 			const char* cp[kMaxTileCols];
 #pragma unroll
 			for (int c = 0; c < kMaxTileCols; ++c) cp[c] = ctl->cp[stg][c];
 			const uint64_t j0 = P.unit_lo + t * tc.m;
 			const uint32_t cnt = (uint32_t)((P.unit_hi - j0 < tc.m) ? (P.unit_hi - j0) : tc.m);
-			for (uint32_t base = wgroup0; base < cnt; base += NGROUPS) {  // warp-uniform trip count
-				const uint32_t ul = base + lane / G;
+			// Units are dealt to the consumer groups round-robin by GLOBAL unit index, so the group that
+			// gets the extra unit rotates from tile to tile and warps that finish early run ahead
+			// into the next stage: no warp is systematically idle.
+			const uint32_t rot = (uint32_t)((t * tc.m) % NGROUPS);
+			const uint32_t myg = wgroup0 + lane / G;
+			const uint32_t first = myg >= rot ? myg - rot : myg + NGROUPS - rot;
+			for (uint32_t base = 0; base < cnt; base += NGROUPS) {  // warp-uniform trip count
+				const uint32_t ul = base + first;
 				const bool active = ul < cnt;
 				const uint64_t j = j0 + (active ? ul : 0u);
 				uint32_t rel, len;
@@ -948,9 +985,13 @@ extern "C" size_t pgt_scan_workspace_bytes(const pgt_plan* plan, const pgt_range
 // valid when pgt_geom.gw == 32), 2 force the tiled kernel (k_units_tiled)
 static int g_tune_level1 = 0;
 static int g_tune_level2 = 0;  // 0 auto, 1 force warp-per-window
+static int g_tune_stages = 2;   // tiled kernel: shared-memory stages (2..4)
+static int g_tune_stage_kb = 110;  // tiled kernel: bytes per stage (stages * stage_kb <= 224)
 extern "C" int pgt_tune(const char* key, int value) {
 	if (key && strcmp(key, "level1") == 0) g_tune_level1 = value;
 	else if (key && strcmp(key, "level2") == 0) g_tune_level2 = value;
+	else if (key && strcmp(key, "stages") == 0 && value >= 2 && value <= kTileMaxStages) g_tune_stages = value;
+	else if (key && strcmp(key, "stage_kb") == 0 && value >= 8 && value <= 110) g_tune_stage_kb = value;
 	else return pgt_set_error(PGT_ERR_ARGS, "pgt_tune: unknown key");
 	return PGT_OK;
 }
@@ -972,14 +1013,17 @@ template <>
 StatCols tile_columns<FusedStat>(const Cols& c) { return StatCols{{c.a, c.b, c.f1, c.f2, c.n1, c.n2, c.g}, {8, 8, 8, 8, 4, 4, 1}, 7}; }
 
 template <class Stat, bool INDIRECT>
-static int launch_units_tiled(const DevPlan& P, const Cols& cols, typename Stat::Acc* units, const uint64_t* bounds, cudaStream_t st) {
+static int launch_units_tiled(const DevPlan& P, const Cols& cols, typename Stat::Acc* units, const uint64_t* bounds, uint64_t valid_elems,
+                              cudaStream_t st) {
 	const uint64_t nunits = P.unit_hi - P.unit_lo;
 	const StatCols sc = tile_columns<Stat>(cols);
 	uint32_t bps = 0;
 	for (uint32_t c = 0; c < sc.n; ++c) bps += sc.elem[c];
 	const int nsm = num_sms();
-	// two stages of <= 96 KB; tiles of whole units; at least ~4 tiles per SM when the input allows
-	const uint32_t stage_budget = 96u * 1024u;
+	// `nstages` stages of <= `stage_kb` KB; tiles of whole units; at least ~4 tiles per SM when the input allows
+	uint32_t nstages = (uint32_t)g_tune_stages;
+	uint32_t stage_budget = (uint32_t)g_tune_stage_kb * 1024u;
+	if (nstages * stage_budget > 224u * 1024u) stage_budget = 224u * 1024u / nstages;
 	uint32_t tsites = (stage_budget - 48u * sc.n) / bps;
 	if (tsites > 16384u) tsites = 16384u;
 	uint32_t m = tsites / P.g.ueff;
@@ -993,17 +1037,19 @@ static int launch_units_tiled(const DevPlan& P, const Cols& cols, typename Stat:
 	memset(&tc, 0, sizeof(tc));
 	tc.ncol = sc.n;
 	tc.m = m;
+	tc.nstages = nstages;
 	tc.minind = cols.minind;
+	tc.valid_elems = valid_elems;
 	uint32_t o = 0;
 	for (uint32_t c = 0; c < sc.n; ++c) {
 		tc.gcol[c] = (const char*)sc.ptr[c];
 		tc.elem[c] = sc.elem[c];
 		tc.col_off[c] = o;
-		tc.col_cap[c] = (uint32_t)align_up((size_t)m * P.g.ueff * sc.elem[c] + 32, 16);
+		tc.col_cap[c] = (uint32_t)align_up((size_t)m * P.g.ueff * sc.elem[c] + 48, 16);
 		o += tc.col_cap[c];
 	}
 	tc.stage_bytes = (uint32_t)align_up(o, 128);
-	const size_t smem = kTileCtlBytes + 2 * (size_t)tc.stage_bytes;
+	const size_t smem = kTileCtlBytes + nstages * (size_t)tc.stage_bytes;
 	void (*kern)(DevPlan, TileCfg, typename Stat::Acc*, const uint64_t*);
 	switch (P.g.gw) {
 		case 1: kern = k_units_tiled<Stat, 1, INDIRECT>; break;
@@ -1025,15 +1071,30 @@ static int launch_units_tiled(const DevPlan& P, const Cols& cols, typename Stat:
 	return PGT_OK;
 }
 
+// valid_elems: number of elements every column is known to hold from element 0
 template <class Stat>
-static int launch_units(const DevPlan& P, const Cols& cols, typename Stat::Acc* units, const uint64_t* bounds, cudaStream_t st) {
+static int launch_units(const DevPlan& P, const Cols& cols, typename Stat::Acc* units, const uint64_t* bounds, uint64_t valid_elems,
+                        cudaStream_t st) {
 	const uint64_t nunits = P.unit_hi - P.unit_lo;
 	if (nunits == 0) return PGT_OK;
-	// The direct kernel reduces every unit with a full warp: it implements the summation order only
-	// when gw == 32 (long units).  Short units always go through the tiled kernel.
-	bool tiled = P.g.gw != 32 || g_tune_level1 == 2;
+	// Kernel choice.  The direct kernel reduces every unit with a full warp, so it implements the
+	// summation order only when gw == 32 (long units); short units always take the tiled kernel.
+	// For long units both kernels give bit-identical results and the choice is purely a speed
+	// matter (measured on B200, profiles/): the TMA-staged tiled kernel wins on big inputs
+	// (no sector over-fetch, bytes in flight without registers), the direct kernel on small ones
+	// (no pipeline fill) and for the 1-byte genotype column.
+	uint32_t bps = 0;
+	{
+		const StatCols sc = tile_columns<Stat>(cols);
+		for (uint32_t c = 0; c < sc.n; ++c) bps += sc.elem[c];
+	}
+	const uint64_t approx_bytes = nunits * (uint64_t)P.g.ueff * bps;
+	bool tiled = P.g.gw != 32 || (bps > 1 && approx_bytes >= (256ull << 20));
+	if (g_tune_level1 == 2) tiled = true;
 	if (g_tune_level1 == 1 && P.g.gw == 32) tiled = false;
-	if (tiled) return bounds ? launch_units_tiled<Stat, true>(P, cols, units, bounds, st) : launch_units_tiled<Stat, false>(P, cols, units, bounds, st);
+	if (tiled)
+		return bounds ? launch_units_tiled<Stat, true>(P, cols, units, bounds, valid_elems, st)
+		              : launch_units_tiled<Stat, false>(P, cols, units, bounds, valid_elems, st);
 	const int threads = 256;
 	const uint64_t want = (nunits + 7) / 8;  // one warp per unit, 8 warps per block
 	const uint32_t upl = P.g.u / 32u;
@@ -1212,7 +1273,9 @@ static int run_scan(const pgt_plan* plan, const pgt_range* range, pgt_stat stat,
 		C.n2 = cols->n2;
 		C.minind = minind;
 		if (bp && nunits) PGT_TRY(launch_bounds_kernel(P, cols->pos, ndata, bounds, st));
-		PGT_TRY(launch_units<Stat>(P, C, units, bounds, st));
+		// elements the caller's columns are known to hold: up to the end of the last unit read
+		const uint64_t valid = bp ? ndata : pgt_plan_unit_start(plan, L.u_hi) - L.origin;
+		PGT_TRY(launch_units<Stat>(P, C, units, bounds, valid, st));
 		PGT_TRY(launch_windows<Stat>(P, units, L.u_lo, cols->pos, *out, st));
 		if (want_global) PGT_TRY(launch_global<Stat>(units, nglobal, (double*)(ws + L.gpart_off), out->dxy_global, st));
 		return PGT_OK;
@@ -1280,7 +1343,7 @@ static int run_scan(const pgt_plan* plan, const pgt_range* range, pgt_stat stat,
 		// entry ub is rewritten by slab i+1 relative to ITS slice, after slab i's unit kernel
 		// (stream order on `st`).
 		if (bp) PGT_TRY(launch_bounds_kernel(Ps, C.pos, ns, sb, st));
-		PGT_TRY(launch_units<Stat>(Ps, C, units + (ua - L.u_lo), sb, st));
+		PGT_TRY(launch_units<Stat>(Ps, C, units + (ua - L.u_lo), sb, ns, st));
 		PGT_CUDA(cudaEventRecord(hs.freed[slot], st));
 		slot_used[slot] = true;
 		slot ^= 1;

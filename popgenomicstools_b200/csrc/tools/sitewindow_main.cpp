@@ -190,7 +190,12 @@ int main(int argc, char** argv) {
 	std::vector<uint64_t> off(runs.size() + 1, 0);
 	for (size_t i = 0; i < runs.size(); ++i) off[i + 1] = off[i] + runs[i].count;
 	pgt_plan* plan = nullptr;
-	if (pgt_plan_create(&plan, PGT_MODE_SITES, off.data(), (uint32_t)runs.size(), winsize, stepsize, 0) != PGT_OK) {
+#if defined(PGT_TOOL_HET)
+	const uint32_t unit_sites = 4096;  // integer counts: unit size does not change results, larger is faster
+#else
+	const uint32_t unit_sites = 0;
+#endif
+	if (pgt_plan_create(&plan, PGT_MODE_SITES, off.data(), (uint32_t)runs.size(), winsize, stepsize, unit_sites) != PGT_OK) {
 		fprintf(stderr, "%s\n", pgt_last_error());
 		return -1;
 	}

@@ -10,8 +10,11 @@ from popgenomicstools_b200.workloads import human_like_contigs
 BPS = {"fst": 16, "het": 1, "dxy": 24, "fused": 41}
 STAT = {"fst": _cabi.PGT_STAT_FST, "het": _cabi.PGT_STAT_HET, "dxy": _cabi.PGT_STAT_DXY, "fused": _cabi.PGT_STAT_FUSED}
 for spec in sys.argv[1:]:
-    stat, n, W, S, unit, l1 = spec.split(",")
+    f = spec.split(",")
+    stat, n, W, S, unit, l1 = f[:6]
     n, W, S, unit, l1 = int(float(n)), int(W), int(S), int(unit), int(l1)
+    stages, skb = (int(f[6]), int(f[7])) if len(f) > 7 else (2, 110)
+    pgt.tune("stages", stages); pgt.tune("stage_kb", skb)
     _, offs = human_like_contigs(n, S)
     plan = pgt.WindowPlan(offs, W, S, unit_sites=unit)
     cols = dict(pos=pgt.synth_pos(4, 0, n, offs, 1))
@@ -37,7 +40,7 @@ for spec in sys.argv[1:]:
     pr = pgt.profile_read(); pgt.profile(False)
     ms = ev[0].elapsed_time(ev[1]) / K
     l1ms = pr["units_ms"] / K; l2ms = pr["windows_ms"] / K
-    print(f"{stat} n={n:.3g} W={W} S={S} u={unit} l1={l1} win={plan.num_windows} units={plan.num_units} step_ms={ms:.4f} "
+    print(f"{stat} n={n:.3g} W={W} S={S} u={unit} l1={l1} st={stages}x{skb}KB win={plan.num_windows} units={plan.num_units} step_ms={ms:.4f} "
           f"L1_ms={l1ms:.4f} L2_ms={l2ms:.4f} sites/s={n/ms*1e3:.4g} L1_GB/s={BPS[stat]*n/l1ms/1e6:.1f}", flush=True)
     del cols, out, plan
     torch.cuda.empty_cache()
