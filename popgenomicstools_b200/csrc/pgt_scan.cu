@@ -658,6 +658,78 @@ __global__ void __launch_bounds__(kTileThreads, 1)
 	}
 }
 
+// hetWindow's 1-byte genotype column: a warp per unit, lanes take 16-byte aligned chunks
+// (LDG.128) and count with byte-SIMD + popc; the partial chunks at the two ends of the unit are
+// read byte by byte, so nothing outside [unit start, unit end) is touched.  Integer counts: the
+// result is independent of the order, identical to the generic kernels.
+__device__ __forceinline__ void het_count_word(uint32_t w, uint32_t& nonmissing, uint32_t& nhet) {
+	nonmissing += __popc(~w & 0x80808080u);                 // g >= 0  (hetWindow.cpp:78)
+	nhet += __popc(__vcmpeq4(w, 0x01010101u) & 0x01010101u);  // g == 1 (hetWindow.cpp:80)
+}
+template <bool INDIRECT>
+__global__ void __launch_bounds__(256) k_units_het_vec(DevPlan P, const int8_t* __restrict__ geno, HetStat::Acc* __restrict__ units,
+                                                        const uint64_t* __restrict__ bounds) {
+	const uint32_t lane = threadIdx.x & 31u;
+	const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+	const uint64_t nwarp = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+	uint32_t si = 0xffffffffu;
+	pgt_seg sg;
+	sg.unit_base = 0;
+	sg.nunits = 0;
+	for (uint64_t j = P.unit_lo + warp; j < P.unit_hi; j += nwarp) {
+		uint64_t i0;
+		uint32_t len;
+		if (INDIRECT) {
+			const uint64_t b0 = bounds[j - P.unit_lo], b1 = bounds[j - P.unit_lo + 1];
+			i0 = b0;
+			len = (uint32_t)(b1 - b0);
+		} else {
+			if (si == 0xffffffffu || j - sg.unit_base >= sg.nunits) {
+				si = find_seg<true>(P, j);
+				sg = P.segs[si];
+			}
+			uint64_t st;
+			len = pgt_unit_range(P.g, sg.nsites, j - sg.unit_base, &st);
+			i0 = sg.site_base + st - P.site_origin;
+		}
+		const int8_t* A = geno + i0;
+		const int8_t* E = A + len;
+		const int8_t* A0 = (const int8_t*)(((uintptr_t)A + 15u) & ~(uintptr_t)15u);  // first aligned chunk inside
+		const int8_t* A1 = (const int8_t*)((uintptr_t)E & ~(uintptr_t)15u);          // end of the last aligned chunk
+		uint32_t nonmissing = 0, nhet = 0;
+		if (A1 > A0) {
+			const uint32_t nch = (uint32_t)(A1 - A0) >> 4;
+			for (uint32_t c = lane; c < nch; c += 32u) {
+				const uint4 v = __ldg(reinterpret_cast<const uint4*>(A0) + c);
+				het_count_word(v.x, nonmissing, nhet);
+				het_count_word(v.y, nonmissing, nhet);
+				het_count_word(v.z, nonmissing, nhet);
+				het_count_word(v.w, nonmissing, nhet);
+			}
+			const uint32_t nh = (uint32_t)(A0 - A), nt = (uint32_t)(E - A1);  // < 16 each
+			if (lane < nh) {
+				const int g = __ldg(A + lane);
+				nonmissing += (g >= 0);
+				nhet += (g == 1);
+			}
+			if (lane >= 16u && lane - 16u < nt) {
+				const int g = __ldg(A1 + (lane - 16u));
+				nonmissing += (g >= 0);
+				nhet += (g == 1);
+			}
+		} else {
+			for (uint32_t x = lane; x < len; x += 32u) {  // < 32 bytes without an aligned chunk
+				const int g = __ldg(A + x);
+				nonmissing += (g >= 0);
+				nhet += (g == 1);
+			}
+		}
+		HetStat::Acc acc{nonmissing, nhet};
+		acc = warp_butterfly<HetStat>(acc);
+		if (lane == 0) units[j - P.unit_lo] = acc;
+	}
+}
+
 // bp mode: bounds[t] = index (relative to the columns' element 0) of the first site at or after
 // the first bp of unit unit_lo+t, t in [0, unit_hi-unit_lo]; the unit's bp -> (chromosome, pos) is
 // closed form, the site is a lower_bound in that chromosome's slice of `pos`.
@@ -792,6 +864,27 @@ __global__ void __launch_bounds__(256) k_windows_small(DevPlan P, const typename
 		const uint32_t cnt = (uint32_t)pgt_window_units(P.g, sg, k, &fu);
 		const typename Stat::Acc acc = SmallTree<Stat, P2, 1>::eval(units + (sg.unit_base + fu - units_base), 0u, cnt);
 		emit_window<Stat>(P, sg, w, k, acc, pos, out);
+	}
+}
+
+// W = S = 1 (the tools' default arguments): every window is one site, so the window table is an
+// elementwise map of the columns; level 1 is skipped and the per-site statistic is evaluated here.
+template <class Stat>
+__global__ void __launch_bounds__(256) k_windows_persite(DevPlan P, Cols cols, pgt_windows out) {
+	const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+	uint32_t si = 0xffffffffu;
+	pgt_seg sg;
+	sg.win_base = 0;
+	sg.nwin = 0;
+	for (uint64_t w = P.win_lo + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; w < P.win_hi; w += stride) {
+		if (si == 0xffffffffu || w - sg.win_base >= sg.nwin) {
+			si = find_seg<false>(P, w);
+			sg = P.segs[si];
+		}
+		const uint64_t k = w - sg.win_base;
+		typename Stat::Acc acc = Stat::zero();
+		Stat::fold(acc, Stat::load(cols, sg.site_base + k - P.site_origin), cols.minind);
+		emit_window<Stat>(P, sg, w, k, acc, cols.pos, out);
 	}
 }
 
@@ -1071,6 +1164,21 @@ static int launch_units_tiled(const DevPlan& P, const Cols& cols, typename Stat:
 	return PGT_OK;
 }
 
+// hetWindow: the vectorised byte kernel replaces the generic direct kernel
+template <class Stat>
+static bool launch_het_vec(const DevPlan&, const Cols&, typename Stat::Acc*, const uint64_t*, uint64_t, cudaStream_t) {
+	return false;
+}
+template <>
+bool launch_het_vec<HetStat>(const DevPlan& P, const Cols& cols, HetStat::Acc* units, const uint64_t* bounds, uint64_t want, cudaStream_t st) {
+	const uint64_t cap = (uint64_t)num_sms() * 8;
+	const unsigned grid = (unsigned)(want < cap ? want : cap);
+	ProfScope prof(0, st);
+	if (bounds) k_units_het_vec<true><<<grid, 256, 0, st>>>(P, cols.g, units, bounds);
+	else k_units_het_vec<false><<<grid, 256, 0, st>>>(P, cols.g, units, bounds);
+	return true;
+}
+
 // valid_elems: number of elements every column is known to hold from element 0
 template <class Stat>
 static int launch_units(const DevPlan& P, const Cols& cols, typename Stat::Acc* units, const uint64_t* bounds, uint64_t valid_elems,
@@ -1097,6 +1205,11 @@ static int launch_units(const DevPlan& P, const Cols& cols, typename Stat::Acc* 
 		              : launch_units_tiled<Stat, false>(P, cols, units, bounds, valid_elems, st);
 	const int threads = 256;
 	const uint64_t want = (nunits + 7) / 8;  // one warp per unit, 8 warps per block
+	if (launch_het_vec<Stat>(P, cols, units, bounds, want, st)) {
+		g_launches++;
+		PGT_CUDA(cudaGetLastError());
+		return PGT_OK;
+	}
 	const uint32_t upl = P.g.u / 32u;
 	void (*kern)(DevPlan, Cols, typename Stat::Acc*, const uint64_t*);
 	if (bounds) kern = upl == 8 ? k_units<Stat, 8, true> : k_units<Stat, 0, true>;
@@ -1272,6 +1385,17 @@ static int run_scan(const pgt_plan* plan, const pgt_range* range, pgt_stat stat,
 		C.n1 = cols->n1;
 		C.n2 = cols->n2;
 		C.minind = minind;
+		if (!bp && P.g.W == 1 && P.g.S == 1 && !want_global && g_tune_level2 != 1) {
+			// default arguments of fstWindow / hetWindow: one window per site, no reduction at all
+			if (nwin) {
+				const uint64_t want = (nwin + 255) / 256, cap = (uint64_t)num_sms() * 8;
+				ProfScope prof(1, st);
+				k_windows_persite<Stat><<<(unsigned)(want < cap ? want : cap), 256, 0, st>>>(P, C, *out);
+				g_launches++;
+				PGT_CUDA(cudaGetLastError());
+			}
+			return PGT_OK;
+		}
 		if (bp && nunits) PGT_TRY(launch_bounds_kernel(P, cols->pos, ndata, bounds, st));
 		// elements the caller's columns are known to hold: up to the end of the last unit read
 		const uint64_t valid = bp ? ndata : pgt_plan_unit_start(plan, L.u_hi) - L.origin;

@@ -127,3 +127,30 @@ def test_argument_errors():
         WindowPlan([0, 10], 5, 6)   # S > W: the reference segfaults, we refuse
     with pytest.raises(PgtError):
         WindowPlan([0, 10, 5], 2, 1)
+
+
+def test_many_small_contigs_match_oracle():
+    """Draft-assembly shape: tens of thousands of scaffolds, many shorter than the window."""
+    rng = np.random.default_rng(11)
+    lengths = rng.integers(1, 60, size=20000).tolist()
+    W, S = 25, 5
+    offs = np.concatenate([[0], np.cumsum(lengths)]).astype(np.uint64)
+    plan = WindowPlan(offs, W, S)
+    f, l, lab = plan.windows()
+    of, ol, olab, on = oracle_windows_sites(lengths, W, S)
+    assert np.array_equal(f, of) and np.array_equal(l, ol) and np.array_equal(lab, olab)
+    assert plan.num_segments <= len(lengths)
+
+
+def test_empty_and_degenerate_inputs():
+    assert WindowPlan([0], 5, 1).num_windows == 0              # no contigs
+    assert WindowPlan([0, 0, 0], 5, 1).num_windows == 0         # only empty contigs
+    p = WindowPlan([0, 0, 7, 7, 9], 3, 3)                       # empty contigs between real ones
+    f, l, lab = p.windows()
+    of, ol, olab, on = oracle_windows_sites([7, 2], 3, 3)
+    assert np.array_equal(f, of) and np.array_equal(l, ol)
+    assert lab.tolist() == [1, 1, 1, 3]                         # labels index the ORIGINAL contig list
+    assert WindowPlan([0, 3], 10, 1).num_windows == 0           # 3 sites <= W-S at EOF: dropped
+    assert WindowPlan([0, 3], 10, 8).num_windows == 1           # 3 sites >  W-S at EOF: printed
+    big = WindowPlan([0, 2**40], 2**31, 2**20)                  # 64-bit site axis
+    assert big.num_windows == (2**40 - 2**31) // 2**20 + 1

@@ -41,6 +41,6 @@ for spec in sys.argv[1:]:
     ms = ev[0].elapsed_time(ev[1]) / K
     l1ms = pr["units_ms"] / K; l2ms = pr["windows_ms"] / K
     print(f"{stat} n={n:.3g} W={W} S={S} u={unit} l1={l1} st={stages}x{skb}KB win={plan.num_windows} units={plan.num_units} step_ms={ms:.4f} "
-          f"L1_ms={l1ms:.4f} L2_ms={l2ms:.4f} sites/s={n/ms*1e3:.4g} L1_GB/s={BPS[stat]*n/l1ms/1e6:.1f}", flush=True)
+          f"L1_ms={l1ms:.4f} L2_ms={l2ms:.4f} sites/s={n/ms*1e3:.4g} L1_GB/s={BPS[stat]*n/max(l1ms,1e-9)/1e6:.1f}", flush=True)
     del cols, out, plan
     torch.cuda.empty_cache()
