@@ -43,6 +43,7 @@ struct pgt_seg {
 	uint64_t win_base;   // global index of its first emitted window
 	uint64_t nwin;       // emitted windows (full + emitted trailing partial)
 	uint64_t nfull;      // K = full windows
+	uint64_t blk_base;   // global index of its first scan block (blocks of g.wunits units, see k_block_scan)
 	uint32_t first_contig;
 	uint32_t ncontig;
 };

@@ -16,6 +16,7 @@ struct pgt_plan {
 	uint64_t nwin;
 	uint64_t nunits;
 	uint64_t nsites;
+	uint64_t nblocks;  // scan blocks of g.wunits units over all segments
 };
 
 int pgt_set_error(int code, const std::string& msg);

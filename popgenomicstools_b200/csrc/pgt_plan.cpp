@@ -54,6 +54,7 @@ extern "C" int pgt_plan_create(pgt_plan** out, pgt_mode mode, const uint64_t* co
 	p->nsites = p->off[ncontig] - origin;
 	p->nwin = 0;
 	p->nunits = 0;
+	p->nblocks = 0;
 
 	uint32_t last_nonempty = ncontig;  // index of the last non-empty contig
 	for (uint32_t c = ncontig; c-- > 0;)
@@ -90,8 +91,10 @@ extern "C" int pgt_plan_create(pgt_plan** out, pgt_mode mode, const uint64_t* co
 		sg.nunits = pgt_seg_nunits(p->g, N);
 		sg.win_base = p->nwin;
 		sg.unit_base = p->nunits;
+		sg.blk_base = p->nblocks;
 		p->nwin += sg.nwin;
 		p->nunits += sg.nunits;
+		p->nblocks += (sg.nunits + p->g.wunits - 1) / p->g.wunits;
 		p->segs.push_back(sg);
 		base += N;
 		N = 0;

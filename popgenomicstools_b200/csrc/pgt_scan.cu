@@ -144,6 +144,14 @@ extern "C" int pgt_profile_read(double* units_ms, uint64_t* units_launches, doub
 	return PGT_OK;
 }
 
+// tuning knobs (tests / experiments, pgt_tune):
+//   level1: 0 auto, 1 force the direct kernel (k_units; only valid when pgt_geom.gw == 32), 2 force the tiled kernel
+//   level2: 0 auto, 1 force warp-per-window, 2 force scan mode (k_block_scan + k_windows_hgw)
+static int g_tune_level1 = 0;
+static int g_tune_level2 = 0;
+static int g_tune_stages = 2;      // tiled kernel: shared-memory stages (2..4)
+static int g_tune_stage_kb = 110;  // tiled kernel: bytes per stage (stages * stage_kb <= 224)
+
 static int num_sms() {
 	int dev = 0, n = 0;
 	if (cudaGetDevice(&dev) != cudaSuccess) return 0;
@@ -189,6 +197,16 @@ __device__ __forceinline__ uint32_t find_seg(const DevPlan& P, uint64_t x) {
 		uint32_t mid = lo + ((hi - lo) >> 1);
 		uint64_t key = BY_UNIT ? P.segs[mid].unit_base : P.segs[mid].win_base;
 		if (key <= x) lo = mid;
+		else hi = mid;
+	}
+	return lo;
+}
+// last segment with blk_base <= x AND at least one scan block
+__device__ __forceinline__ uint32_t find_seg_by_block(const DevPlan& P, uint64_t x) {
+	uint32_t lo = 0, hi = P.nseg;
+	while (hi - lo > 1) {
+		uint32_t mid = lo + ((hi - lo) >> 1);
+		if (P.segs[mid].blk_base <= x) lo = mid;
 		else hi = mid;
 	}
 	return lo;
@@ -888,6 +906,118 @@ __global__ void __launch_bounds__(256) k_windows_persite(DevPlan P, Cols cols, p
 	}
 }
 
+// ----------------------------------------------------------------------------- level 2, scan mode
+//
+// Fine steps with long windows (e.g. W = 1000, S = 1): summing W/S unit partials per window
+// would cost O(n * W / S^2).  Instead the unit array is cut into blocks of B = wunits units
+// (aligned to the segment's first unit), and an inclusive prefix scan PRE and suffix scan SUF are
+// taken inside every block.  A window covers at most two adjacent blocks, so
+//     window = SUF[first unit] + PRE[last unit]          (van Herk / Gil-Werman)
+// -- two reads per window, only additions of true partial sums (no subtraction, no cancellation).
+// Order inside a block: chunks of 256 units; warp shuffle scan, warp totals, running carry.
+
+template <class Acc>
+__device__ __forceinline__ Acc shfl_up_acc(const Acc& v, unsigned delta) {
+	static_assert(sizeof(Acc) % 4 == 0, "Acc is made of 32-bit words");
+	uint32_t w[sizeof(Acc) / 4];
+	memcpy(w, &v, sizeof(Acc));
+#pragma unroll
+	for (unsigned i = 0; i < sizeof(Acc) / 4; ++i) w[i] = __shfl_up_sync(0xffffffffu, w[i], delta);
+	Acc r;
+	memcpy(&r, w, sizeof(Acc));
+	return r;
+}
+
+// one direction of the block scan: items x0 + i (forward) or x1 - 1 - i (backward), i = 0..n-1
+template <class Stat, bool BACKWARD>
+__device__ __forceinline__ void cta_scan_dir(const typename Stat::Acc* __restrict__ in, typename Stat::Acc* __restrict__ outp, uint64_t x0, uint64_t x1,
+                                             typename Stat::Acc* s_wtot, typename Stat::Acc* s_carry) {
+	typedef typename Stat::Acc Acc;
+	const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+	const uint64_t n = x1 - x0;
+	if (threadIdx.x == 0) *s_carry = Stat::zero();
+	__syncthreads();
+	for (uint64_t base = 0; base < n; base += blockDim.x) {
+		const uint64_t i = base + threadIdx.x;
+		const bool ok = i < n;
+		const uint64_t idx = BACKWARD ? (x1 - 1 - i) : (x0 + i);
+		Acc v = Stat::zero();
+		if (ok) Stat::add(v, in[idx]);
+		// inclusive scan inside the warp
+#pragma unroll
+		for (unsigned d = 1; d < 32; d <<= 1) {
+			Acc o = shfl_up_acc(v, d);
+			if (lane >= d) {
+				Acc t = o;          // earlier items first: t = earlier + v
+				Stat::add(t, v);
+				v = t;
+			}
+		}
+		if (lane == 31) s_wtot[warp] = v;
+		__syncthreads();
+		Acc pre = *s_carry;  // everything before this chunk
+		for (uint32_t w = 0; w < warp; ++w) Stat::add(pre, s_wtot[w]);
+		Stat::add(pre, v);
+		if (ok) outp[idx] = pre;
+		__syncthreads();
+		if (threadIdx.x == blockDim.x - 1) *s_carry = pre;  // inclusive total through this chunk
+		__syncthreads();
+	}
+}
+
+template <class Stat>
+__global__ void __launch_bounds__(256) k_block_scan(DevPlan P, typename Stat::Acc* __restrict__ units, typename Stat::Acc* __restrict__ pre,
+                                                     uint64_t units_base, uint64_t blk_lo, uint64_t blk_hi) {
+	__shared__ typename Stat::Acc s_wtot[8];
+	__shared__ typename Stat::Acc s_carry;
+	const uint64_t B = P.g.wunits;
+	for (uint64_t gb = blk_lo + blockIdx.x; gb < blk_hi; gb += gridDim.x) {
+		const pgt_seg sg = P.segs[find_seg_by_block(P, gb)];
+		const uint64_t lb = gb - sg.blk_base;
+		uint64_t u0 = sg.unit_base + lb * B;
+		uint64_t u1 = sg.unit_base + ((lb + 1) * B < sg.nunits ? (lb + 1) * B : sg.nunits);
+		// clip to the units this scan computed (shards): see DESIGN.md, the clipped values are never used
+		if (u0 < P.unit_lo) u0 = P.unit_lo;
+		if (u1 > P.unit_hi) u1 = P.unit_hi;
+		if (u1 <= u0) continue;
+		cta_scan_dir<Stat, false>(units, pre, u0 - units_base, u1 - units_base, s_wtot, &s_carry);  // PRE (reads raw units)
+		cta_scan_dir<Stat, true>(units, units, u0 - units_base, u1 - units_base, s_wtot, &s_carry);  // SUF in place
+	}
+}
+
+template <class Stat>
+__global__ void __launch_bounds__(256) k_windows_hgw(DevPlan P, const typename Stat::Acc* __restrict__ suf, const typename Stat::Acc* __restrict__ pre,
+                                                      uint64_t units_base, const uint32_t* __restrict__ pos, pgt_windows out) {
+	const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+	const uint64_t B = P.g.wunits;
+	uint32_t si = 0xffffffffu;
+	pgt_seg sg;
+	sg.win_base = 0;
+	sg.nwin = 0;
+	for (uint64_t w = P.win_lo + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; w < P.win_hi; w += stride) {
+		if (si == 0xffffffffu || w - sg.win_base >= sg.nwin) {
+			si = find_seg<false>(P, w);
+			sg = P.segs[si];
+		}
+		const uint64_t k = w - sg.win_base;
+		uint64_t fu;
+		const uint64_t cnt = pgt_window_units(P.g, sg, k, &fu);
+		const uint64_t lu = fu + cnt - 1;  // segment-local first / last unit
+		const uint64_t gf = sg.unit_base + fu - units_base, gl = sg.unit_base + lu - units_base;
+		typename Stat::Acc acc = Stat::zero();
+		if (fu / B == lu / B) {
+			// inside one block: block-aligned start (PRE up to the last unit), or it runs to the block /
+			// segment end (SUF from the first unit)
+			if (fu % B == 0) Stat::add(acc, pre[gl]);
+			else Stat::add(acc, suf[gf]);
+		} else {
+			Stat::add(acc, suf[gf]);
+			Stat::add(acc, pre[gl]);
+		}
+		emit_window<Stat>(P, sg, w, k, acc, pos, out);
+	}
+}
+
 // dxyWindow's global line (dxyWindow.cpp:382-385,429-433) over the unit partials [0, n): one
 // block; thread t adds partials t, t+1024, ...; warp butterflies; counts in 64 bit.
 template <class Stat>
@@ -997,7 +1127,9 @@ static size_t acc_bytes(pgt_stat stat) {
 
 struct Layout {
 	uint64_t w_lo, w_hi, u_lo, u_hi, g_hi, origin;
-	size_t segs_off, off_off, siteoff_off, gpart_off, units_off, bounds_off, stage_off, outs_off, total;
+	size_t segs_off, off_off, siteoff_off, gpart_off, units_off, pre_off, bounds_off, stage_off, outs_off, total;
+	bool hgw;               // level 2 in scan mode
+	uint64_t blk_lo, blk_hi;  // scan blocks covering [u_lo, u_hi)
 	size_t stage_col_bytes[8];
 	uint64_t slab_sites;
 };
@@ -1050,6 +1182,23 @@ static int make_layout(const pgt_plan* plan, const pgt_range* range, pgt_stat st
 	o += align_up((size_t)kGlobalBlocks * 3 * sizeof(double), 256);
 	L->units_off = o;
 	o += align_up((size_t)nunits * acc_bytes(stat) + 8, 256);
+	// level 2 in scan mode when summing wunits partials per window would dominate (fine steps, long windows)
+	{
+		const double direct = (double)(hi - lo) * plan->g.wunits;
+		const double scan = 4.0 * (3.0 * (double)nunits + 2.0 * (double)(hi - lo));
+		L->hgw = plan->g.wunits > 32 && direct > scan;
+		if (g_tune_level2 == 1) L->hgw = false;
+		if (g_tune_level2 == 2 && plan->g.wunits >= 2) L->hgw = true;
+	}
+	L->pre_off = o;
+	L->blk_lo = L->blk_hi = 0;
+	if (L->hgw && nunits) {
+		o += align_up((size_t)nunits * acc_bytes(stat) + 8, 256);
+		const pgt_seg& s0 = plan->segs[pgt_plan_seg_of_unit(plan, L->u_lo)];
+		const pgt_seg& s1 = plan->segs[pgt_plan_seg_of_unit(plan, L->u_hi - 1)];
+		L->blk_lo = s0.blk_base + (L->u_lo - s0.unit_base) / plan->g.wunits;
+		L->blk_hi = s1.blk_base + (L->u_hi - 1 - s1.unit_base) / plan->g.wunits + 1;
+	}
 	L->bounds_off = o;
 	if (plan->mode == PGT_MODE_BP) o += align_up((size_t)(nunits + 1) * sizeof(uint64_t), 256);
 	L->stage_off = o;
@@ -1074,15 +1223,9 @@ extern "C" size_t pgt_scan_workspace_bytes(const pgt_plan* plan, const pgt_range
 	return L.total;
 }
 
-// tuning knobs (tests / experiments): level1 = 0 auto, 1 force the direct kernel (k_units, only
-// valid when pgt_geom.gw == 32), 2 force the tiled kernel (k_units_tiled)
-static int g_tune_level1 = 0;
-static int g_tune_level2 = 0;  // 0 auto, 1 force warp-per-window
-static int g_tune_stages = 2;   // tiled kernel: shared-memory stages (2..4)
-static int g_tune_stage_kb = 110;  // tiled kernel: bytes per stage (stages * stage_kb <= 224)
 extern "C" int pgt_tune(const char* key, int value) {
 	if (key && strcmp(key, "level1") == 0) g_tune_level1 = value;
-	else if (key && strcmp(key, "level2") == 0) g_tune_level2 = value;
+	else if (key && strcmp(key, "level2") == 0 && value >= 0 && value <= 2) g_tune_level2 = value;
 	else if (key && strcmp(key, "stages") == 0 && value >= 2 && value <= kTileMaxStages) g_tune_stages = value;
 	else if (key && strcmp(key, "stage_kb") == 0 && value >= 8 && value <= 110) g_tune_stage_kb = value;
 	else return pgt_set_error(PGT_ERR_ARGS, "pgt_tune: unknown key");
@@ -1237,14 +1380,22 @@ static int launch_bounds_kernel(const DevPlan& P, const uint32_t* pos, uint64_t 
 	return PGT_OK;
 }
 
+// scan mode (L.hgw): `units` is scanned in place into SUF, `pre` receives PRE; see k_block_scan
 template <class Stat>
-static int launch_windows(const DevPlan& P, const typename Stat::Acc* units, uint64_t units_base, const uint32_t* pos,
-                          const pgt_windows& out, cudaStream_t st) {
+static int launch_windows(const DevPlan& P, typename Stat::Acc* units, uint64_t units_base, const uint32_t* pos, const pgt_windows& out,
+                          bool hgw, typename Stat::Acc* pre, uint64_t blk_lo, uint64_t blk_hi, cudaStream_t st) {
 	const uint64_t nwin = P.win_hi - P.win_lo;
 	if (nwin == 0) return PGT_OK;
 	const uint64_t cap = (uint64_t)num_sms() * 8;
 	ProfScope prof(1, st);
-	if (P.g.wunits <= 32 && g_tune_level2 != 1) {
+	if (hgw) {
+		const uint64_t nblk = blk_hi - blk_lo;
+		const uint64_t bcap = (uint64_t)num_sms() * 8;
+		k_block_scan<Stat><<<(unsigned)(nblk < bcap ? nblk : bcap), 256, 0, st>>>(P, units, pre, units_base, blk_lo, blk_hi);
+		g_launches++;
+		const uint64_t want = (nwin + 255) / 256;
+		k_windows_hgw<Stat><<<(unsigned)(want < cap ? want : cap), 256, 0, st>>>(P, units, pre, units_base, pos, out);
+	} else if (P.g.wunits <= 32 && g_tune_level2 != 1) {
 		// fine windows: a thread per window
 		void (*kern)(DevPlan, const typename Stat::Acc*, uint64_t, const uint32_t*, pgt_windows);
 		const uint32_t wu = P.g.wunits;
@@ -1331,13 +1482,13 @@ static int run_scan(const pgt_plan* plan, const pgt_range* range, pgt_stat stat,
 	const bool bp = plan->mode == PGT_MODE_BP;
 	if (bp && stat != PGT_STAT_DXY) return pgt_set_error(PGT_ERR_ARGS, "PGT_MODE_BP plans are for PGT_STAT_DXY only");
 	if (bp && (!site_offsets || !cols->pos)) return pgt_set_error(PGT_ERR_ARGS, "bp mode needs site_offsets and pos");
+	const uint64_t nunits = L.u_hi - L.u_lo;
+	const uint64_t nwin = L.w_hi - L.w_lo;
+	if (nunits == 0 && nwin == 0) return PGT_OK;  // empty input / empty shard: nothing to read or write
 	ColDesc cd[8];
 	const int ncol = stat_columns(stat, plan->mode, cols, cd);
 	for (int i = 0; i < ncol; ++i)
 		if (!cd[i].ptr) return pgt_set_error(PGT_ERR_ARGS, "a column required by this statistic is NULL");
-	const uint64_t nunits = L.u_hi - L.u_lo;
-	const uint64_t nwin = L.w_hi - L.w_lo;
-	if (nunits == 0 && nwin == 0) return PGT_OK;
 	if (!bp && nunits > 0 && pgt_plan_unit_start(plan, L.u_lo) < L.origin)
 		return pgt_set_error(PGT_ERR_ARGS, "site_origin lies after the first site this scan must read");
 
@@ -1400,8 +1551,9 @@ static int run_scan(const pgt_plan* plan, const pgt_range* range, pgt_stat stat,
 		// elements the caller's columns are known to hold: up to the end of the last unit read
 		const uint64_t valid = bp ? ndata : pgt_plan_unit_start(plan, L.u_hi) - L.origin;
 		PGT_TRY(launch_units<Stat>(P, C, units, bounds, valid, st));
-		PGT_TRY(launch_windows<Stat>(P, units, L.u_lo, cols->pos, *out, st));
+		// the global line reads the raw unit partials: before level 2, which may scan them in place
 		if (want_global) PGT_TRY(launch_global<Stat>(units, nglobal, (double*)(ws + L.gpart_off), out->dxy_global, st));
+		PGT_TRY(launch_windows<Stat>(P, units, L.u_lo, cols->pos, *out, L.hgw, (typename Stat::Acc*)(ws + L.pre_off), L.blk_lo, L.blk_hi, st));
 		return PGT_OK;
 	}
 
@@ -1495,8 +1647,8 @@ static int run_scan(const pgt_plan* plan, const pgt_range* range, pgt_stat stat,
 	dev.neffective = (uint32_t*)dptr(out->neffective);
 	dev.nskip = (uint32_t*)dptr(out->nskip);
 	dev.dxy_global = want_global ? (double*)(ob0 + ob * 11) : nullptr;
-	PGT_TRY(launch_windows<Stat>(P, units, L.u_lo, nullptr, dev, st));
 	if (want_global) PGT_TRY(launch_global<Stat>(units, nglobal, (double*)(ws + L.gpart_off), dev.dxy_global, st));
+	PGT_TRY(launch_windows<Stat>(P, units, L.u_lo, nullptr, dev, L.hgw, (typename Stat::Acc*)(ws + L.pre_off), L.blk_lo, L.blk_hi, st));
 	auto back = [&](void* h, const void* d, size_t elem) -> cudaError_t {
 		return (h && d && nwin) ? cudaMemcpyAsync(h, d, nwin * elem, cudaMemcpyDeviceToHost, st) : cudaSuccess;
 	};

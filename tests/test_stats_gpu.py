@@ -232,3 +232,52 @@ def test_fst_host_mode_matches_device_mode(pgt):
     host = pgt.fst_window(plan, pos, a, b)
     for k in dev:
         assert host[k].tobytes() == dev[k].tobytes(), k
+
+
+@pytest.mark.parametrize("W,S", [(1000, 1), (777, 13), (64, 1), (5000, 3), (40, 40)])
+def test_level2_scan_mode_matches_oracle_and_direct_mode(pgt, W, S):
+    """Fine steps with long windows run level 2 in scan mode (block prefix/suffix scans,
+    window = SUF[first] + PRE[last]); forced on and off it must agree with the oracle, exactly
+    for the integer statistics and within the stated tolerance for the sums."""
+    lengths = [W + 5 * S, 20011, 3, W // 2 + 1, 9000]
+    offs = offsets(lengths)
+    n = int(offs[-1])
+    chr_id = T.expand_chr(lengths)
+    a, b = pgt.synth_fst(6, 0, n)
+    g = pgt.synth_het(6, 0, n)
+    f1, f2, n1, n2 = pgt.synth_dxy(6, 0, n)
+    pos = pgt.synth_pos(6, 0, n, offs, 1)
+    hpos, ha, hb = pos.cpu().numpy(), a.cpu().numpy(), b.cpu().numpy()
+    ref = O.fst(chr_id, hpos, ha, hb, W, S)
+    absr = O.fst(chr_id, hpos, np.abs(ha), np.abs(hb), W, S)
+    href = O.het(chr_id, hpos, g.cpu().numpy(), W, S)
+    dref = O.dxy(chr_id, hpos, f1.cpu().numpy(), f2.cpu().numpy(), n1.cpu().numpy(), n2.cpu().numpy(), 5, W, S, 1)
+    plan = pgt.WindowPlan(offs, W, S)
+    try:
+        for mode in (2, 1, 0):
+            pgt.tune("level2", mode)
+            res = npy(pgt.fused_window(plan, pos, a, b, g, f1, f2, n1, n2, minind=5))
+            P.assert_exact(res["label"], ref["label"], "label")
+            P.assert_exact(res["start_pos"], ref["start"], "start")
+            P.assert_exact(res["end_pos"], ref["end"], "end")
+            P.assert_exact(res["nsites"], ref["n"], "nsites")
+            P.assert_sum_close(res["sum_a"], ref["asum"], absr["asum"], f"sum_a mode {mode}")
+            P.assert_sum_close(res["sum_b"], ref["bsum"], absr["bsum"], f"sum_b mode {mode}")
+            P.assert_exact(res["nhet"], href["nhet"], "nhet")
+            P.assert_exact(res["nonmissing"], href["nonmissing"], "nonmissing")
+            P.assert_exact(res["het"], href["h"], "het")
+            P.assert_exact(res["neffective"], dref["neff"], "neff")
+            P.assert_exact(res["nskip"], dref["nskip"], "nskip")
+            P.assert_sum_close(res["dxy"], dref["dxy"], dref["dxy"], f"dxy mode {mode}")
+            assert res["dxy_global"][1] == dref["global"][1] and res["dxy_global"][2] == dref["global"][2]
+            # shards in scan mode reproduce the unsharded scan-mode table bit for bit
+            if mode == 2:
+                parts = []
+                for r in range(3):
+                    wl, wh, sl, sh = plan.shard(r, 3)
+                    if wh > wl:
+                        parts.append(npy(pgt.fst_window(plan, pos[sl:sh], a[sl:sh], b[sl:sh], window_range=(wl, wh), site_origin=sl)))
+                for k in ("sum_a", "sum_b", "fst", "start_pos", "nsites"):
+                    assert np.concatenate([p[k] for p in parts]).tobytes() == res[k].tobytes(), k
+    finally:
+        pgt.tune("level2", 0)
