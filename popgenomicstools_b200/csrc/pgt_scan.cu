@@ -1192,8 +1192,10 @@ static int make_layout(const pgt_plan* plan, const pgt_range* range, pgt_stat st
 	}
 	L->pre_off = o;
 	L->blk_lo = L->blk_hi = 0;
+	// PRE array: reserved whenever scan mode is possible, so the workspace size does not depend on the
+	// (tunable) kernel choice
+	if (plan->g.wunits >= 2 && nunits) o += align_up((size_t)nunits * acc_bytes(stat) + 8, 256);
 	if (L->hgw && nunits) {
-		o += align_up((size_t)nunits * acc_bytes(stat) + 8, 256);
 		const pgt_seg& s0 = plan->segs[pgt_plan_seg_of_unit(plan, L->u_lo)];
 		const pgt_seg& s1 = plan->segs[pgt_plan_seg_of_unit(plan, L->u_hi - 1)];
 		L->blk_lo = s0.blk_base + (L->u_lo - s0.unit_base) / plan->g.wunits;
@@ -1343,6 +1345,13 @@ static int launch_units(const DevPlan& P, const Cols& cols, typename Stat::Acc* 
 	bool tiled = P.g.gw != 32 || (bps > 1 && approx_bytes >= (256ull << 20));
 	if (g_tune_level1 == 2) tiled = true;
 	if (g_tune_level1 == 1 && P.g.gw == 32) tiled = false;
+	{
+		// a tile holds whole units: very long units (unit_sites up to 4096) may not fit a stage;
+		// they always have gw == 32, so the direct kernel applies
+		uint32_t nst = (uint32_t)g_tune_stages, budget = (uint32_t)g_tune_stage_kb * 1024u;
+		if (nst * budget > 224u * 1024u) budget = 224u * 1024u / nst;
+		if ((uint64_t)P.g.ueff * bps + 64ull * kMaxTileCols > budget) tiled = false;
+	}
 	if (tiled)
 		return bounds ? launch_units_tiled<Stat, true>(P, cols, units, bounds, valid_elems, st)
 		              : launch_units_tiled<Stat, false>(P, cols, units, bounds, valid_elems, st);

@@ -1,0 +1,138 @@
+"""Every kernel path x statistic x memory mode on one small genome, each compared with the oracle:
+level 1 direct / tiled (TMA-staged) / vectorised het, level 2 warp / thread-per-window / scan mode /
+per-site, unaligned column views, shards, host staging, bp mode.  (compute-sanitizer is closed on
+this pool, so memory-safety evidence is this matrix: any out-of-range read of a tile, head/tail
+byte or halo would change a compared value.)"""
+import numpy as np
+import pytest
+
+import oracle_lib as O
+import parity as P
+import textfmt as T
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def pgt():
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import popgenomicstools_b200 as m
+    yield m
+    m.tune("level1", 0)
+    m.tune("level2", 0)
+
+
+def offsets(l):
+    return np.concatenate([[0], np.cumsum(l)]).astype(np.uint64)
+
+
+def npy(out):
+    import torch
+    torch.cuda.synchronize()
+    return {k: (v.cpu().numpy() if hasattr(v, "cpu") else v) for k, v in out.items()}
+
+
+@pytest.mark.parametrize("W,S,u", [(5000, 100, 0), (1000, 100, 0), (300, 299, 0), (1, 1, 0), (64, 1, 0), (777, 13, 32),
+                                   (2560, 256, 0), (4096, 4096, 4096)])
+def test_site_mode_all_paths(pgt, W, S, u):
+    import torch
+    lengths = [W + 3 * S, 12345, 7, 4001]
+    offs = offsets(lengths)
+    n = int(offs[-1])
+    chr_id = T.expand_chr(lengths)
+    a, b = pgt.synth_fst(1, 0, n)
+    g = pgt.synth_het(1, 0, n)
+    f1, f2, n1, n2 = pgt.synth_dxy(1, 0, n)
+    pos = pgt.synth_pos(1, 0, n, offs, 1)
+    # column views that start at odd element offsets (head/tail handling of the bulk copies / vector loads)
+    A = torch.empty(n + 3, dtype=torch.float64, device="cuda")
+    A[3:].copy_(a)
+    G = torch.empty(n + 5, dtype=torch.int8, device="cuda")
+    G[5:].copy_(g)
+    h = {k: v.cpu().numpy() for k, v in dict(pos=pos, a=a, b=b, g=g, f1=f1, f2=f2, n1=n1, n2=n2).items()}
+    rf = O.fst(chr_id, h["pos"], h["a"], h["b"], W, S)
+    ra = O.fst(chr_id, h["pos"], np.abs(h["a"]), np.abs(h["b"]), W, S)
+    rh = O.het(chr_id, h["pos"], h["g"], W, S)
+    rd = O.dxy(chr_id, h["pos"], h["f1"], h["f2"], h["n1"], h["n2"], 5, W, S, 1)
+
+    def check(res, what):
+        P.assert_exact(res["label"], rf["label"], what + " label")
+        P.assert_exact(res["start_pos"], rf["start"], what + " start")
+        P.assert_exact(res["end_pos"], rf["end"], what + " end")
+        P.assert_exact(res["nsites"], rf["n"], what + " nsites")
+        if "sum_a" in res:
+            P.assert_sum_close(res["sum_a"], rf["asum"], ra["asum"], what + " sum_a")
+            P.assert_sum_close(res["sum_b"], rf["bsum"], ra["bsum"], what + " sum_b")
+        if "nhet" in res:
+            P.assert_exact(res["nhet"], rh["nhet"], what + " nhet")
+            P.assert_exact(res["nonmissing"], rh["nonmissing"], what + " nonmissing")
+            P.assert_exact(res["het"], rh["h"], what + " het")
+        if "dxy" in res:
+            P.assert_exact(res["neffective"], rd["neff"], what + " neff")
+            P.assert_exact(res["nskip"], rd["nskip"], what + " nskip")
+            P.assert_sum_close(res["dxy"], rd["dxy"], rd["dxy"], what + " dxy")
+            assert res["dxy_global"][1] == rd["global"][1] and res["dxy_global"][2] == rd["global"][2], what
+
+    plan = pgt.WindowPlan(offs, W, S, unit_sites=u)
+    for l1 in (0, 1, 2):
+        for l2 in (0, 1, 2):
+            pgt.tune("level1", l1)
+            pgt.tune("level2", l2)
+            tag = f"l1={l1} l2={l2}"
+            check(npy(pgt.fst_window(plan, pos, A[3:], b)), "fst " + tag)
+            check(npy(pgt.het_window(plan, pos, G[5:])), "het " + tag)
+            check(npy(pgt.dxy_window(plan, pos, f1, f2, n1, n2, minind=5)), "dxy " + tag)
+            check(npy(pgt.fused_window(plan, pos, A[3:], b, G[5:], f1, f2, n1, n2, minind=5)), "fused " + tag)
+    pgt.tune("level1", 0)
+    pgt.tune("level2", 0)
+    full = npy(pgt.fused_window(plan, pos, a, b, g, f1, f2, n1, n2, minind=5))
+    parts = []
+    for r in range(3):
+        wl, wh, sl, sh = plan.shard(r, 3)
+        if wh > wl:
+            parts.append(npy(pgt.fused_window(plan, pos[sl:sh], a[sl:sh], b[sl:sh], g[sl:sh], f1[sl:sh], f2[sl:sh], n1[sl:sh],
+                                              n2[sl:sh], minind=5, window_range=(wl, wh), site_origin=sl)))
+    for k in full:
+        if k == "dxy_global":
+            tot = sum(p[k] for p in parts)
+            assert tot[1] == full[k][1] and tot[2] == full[k][2] and abs(tot[0] - full[k][0]) <= 1e-9 * abs(full[k][0])
+        else:
+            assert np.concatenate([p[k] for p in parts]).tobytes() == full[k].tobytes(), k
+    hres = pgt.fused_window(plan, h["pos"], h["a"], h["b"], h["g"], h["f1"], h["f2"], h["n1"], h["n2"], minind=5)
+    check(hres, "host mode")
+    for k in full:
+        if k != "dxy_global":
+            assert hres[k].tobytes() == full[k].tobytes(), "host vs device " + k
+
+
+@pytest.mark.parametrize("density", [10, 1])
+@pytest.mark.parametrize("W,S", [(2000, 500), (100, 100), (1, 1), (777, 10)])
+def test_bp_mode_all_paths(pgt, density, W, S):
+    nsites = [3000, 1500, 40]
+    soff = offsets(nsites)
+    ns = int(soff[-1])
+    chr_len = [x * density + 17 for x in nsites]
+    f1, f2, n1, n2 = pgt.synth_dxy(2, 0, ns)
+    p = pgt.synth_pos(2, 0, ns, soff, density)
+    h = [x.cpu().numpy() for x in (p, f1, f2, n1, n2)]
+    ref = O.dxy(T.expand_chr(nsites), h[0], h[1], h[2], h[3], h[4], 5, W, S, 0, 0, chr_len)
+    plan = pgt.WindowPlan(offsets(chr_len), W, S, mode="bp")
+
+    def check(res, what):
+        P.assert_exact(res["label"], ref["label"], what)
+        P.assert_exact(res["start_pos"].astype(np.int64), ref["start"], what)
+        P.assert_exact(res["end_pos"].astype(np.int64), ref["end"], what)
+        P.assert_exact(res["neffective"], ref["neff"], what)
+        P.assert_exact(res["nskip"], ref["nskip"], what)
+        P.assert_sum_close(res["dxy"], ref["dxy"], ref["dxy"], what)
+
+    for l1 in (0, 2):
+        for l2 in (0, 1, 2):
+            pgt.tune("level1", l1)
+            pgt.tune("level2", l2)
+            check(npy(pgt.dxy_window(plan, p, f1, f2, n1, n2, minind=5, site_offsets=soff)), f"bp l1={l1} l2={l2}")
+    pgt.tune("level1", 0)
+    pgt.tune("level2", 0)
+    check(pgt.dxy_window(plan, *h, minind=5, site_offsets=soff), "bp host")
