@@ -256,6 +256,8 @@ int main(int argc, char** argv) {
 		}
 	}
 
+	DeviceWarmup warm;
+	warm.start();
 	if (parse_maf(in1, &m1, argv[argc - 2]) != 0) return -1;
 	if (parse_maf(in2, &m2, argv[argc - 1]) != 0) return -1;
 	const uint64_t n1 = m1.pos.size(), n2 = m2.pos.size();
@@ -367,7 +369,8 @@ int main(int argc, char** argv) {
 	std::vector<double> dxy(nwin);
 	double global[3] = {0, 0, 0};
 	{
-		if (select_device() != 0) return -1;
+		if (warm.finish() != 0) return -1;
+		tm.cuda_init_ms = warm.ms;
 		pgt_columns cols;
 		memset(&cols, 0, sizeof(cols));
 		cols.pos = pos.data();

@@ -84,6 +84,8 @@ int main(int argc, char** argv) {
 
 	// ---- parse (timed separately from compute) --------------------------------------------
 	Timing tm;
+	DeviceWarmup warm;
+	warm.start();
 	const size_t n_eff = effective_size(in.data, in.size);
 	const unsigned nt = n_eff < (1u << 20) ? 1 : parse_threads();
 	tm.threads = nt;
@@ -203,7 +205,8 @@ int main(int argc, char** argv) {
 	std::vector<uint32_t> label(nwin), startp(nwin), endp(nwin), midp(nwin), cnt(nwin);
 	std::vector<double> stat(nwin);
 	if (nwin) {
-		if (select_device() != 0) return -1;
+		if (warm.finish() != 0) return -1;
+		tm.cuda_init_ms = warm.ms;
 		pgt_columns cols;
 		memset(&cols, 0, sizeof(cols));
 		cols.pos = pos;
