@@ -81,10 +81,12 @@ def cli_arm(tmp, jobs, W, S):
             with open(j[0], "rb") as r:
                 shutil.copyfileobj(r, w, 1 << 24)
     best = None
+    ours_out = os.path.join(tmp, "ours.tsv")
     for _ in range(2):  # second run = warm page cache + warm driver
         t0 = time.perf_counter()
-        p = subprocess.run([exe, allp, str(W), str(S)], stdout=subprocess.DEVNULL, stderr=subprocess.PIPE, text=True,
-                           env=dict(os.environ, PGT_TIMING="1"))
+        with open(ours_out, "wb") as fo:
+            p = subprocess.run([exe, allp, str(W), str(S)], stdout=fo, stderr=subprocess.PIPE, text=True,
+                               env=dict(os.environ, PGT_TIMING="1"))
         wall = time.perf_counter() - t0
         if p.returncode != 0:
             return {"error": p.stderr[-200:]}
@@ -92,6 +94,21 @@ def cli_arm(tmp, jobs, W, S):
         t["wall_s_incl_process_and_cuda_startup"] = round(wall, 3)
         best = t
     best["sites_per_s_parse_scan_format"] = round(best["sites"] / (best["total_ms"] * 1e-3), 1)
+    # the same file through the unmodified reference binary, one process (how a user runs it), and a
+    # row-by-row comparison of the two outputs (text after %g formatting)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_lib as O
+    ref = O.ref_binary("fstWindow")
+    if ref:
+        ref_out = os.path.join(tmp, "ref.tsv")
+        t0 = time.perf_counter()
+        with open(ref_out, "wb") as fo:
+            subprocess.run([ref, allp, str(W), str(S)], stdout=fo, check=True)
+        rsec = time.perf_counter() - t0
+        a, b = open(ours_out).read().splitlines(), open(ref_out).read().splitlines()
+        diff = sum(1 for x, y in zip(a, b) if x != y) + abs(len(a) - len(b))
+        best["reference_same_file_one_process"] = {"wall_s": round(rsec, 2), "sites_per_s": round(best["sites"] / rsec, 1),
+                                                   "rows": len(b), "rows_differing_from_ours": diff}
     os.remove(allp)
     return best
 
