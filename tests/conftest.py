@@ -17,3 +17,11 @@ def golden_cases():
     path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_transcripts.json")
     with open(path) as f:
         return json.load(f)["cases"]
+
+
+@pytest.fixture(scope="session")
+def golden_extreme_cases():
+    import json
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_transcripts_extreme.json")
+    with open(path) as f:
+        return json.load(f)["cases"]

@@ -30,6 +30,7 @@ def lib():
         _LIB.pgt_oracle_fst.restype = C.c_int64
         _LIB.pgt_oracle_het.restype = C.c_int64
         _LIB.pgt_oracle_dxy.restype = C.c_int64
+        _LIB.pgt_oracle_extreme.restype = C.c_int64
     return _LIB
 
 
@@ -113,6 +114,39 @@ def dxy(chr_id, pos, f1, f2, n1, n2, minind, W, S, fixedsite, skip_missing=0, ch
     res["global"] = glob
     res["rc"] = r if r < 0 else 0
     return res
+
+
+def extreme(mode, chr_id, pos, val, W, cutoff, chrlen=None):
+    """mode 'ihs' | 'xpehh' (oracle/pgt_oracle_extreme.c).  chrlen: per name id, 0 = unknown."""
+    chr_id, pos, val = _c(chr_id, np.uint32), _c(pos, np.uint32), _c(val, np.float64)
+    n = len(pos)
+    chrlen = _c(chrlen if chrlen is not None else [], np.uint32)
+    m = 0 if mode == "ihs" else 1
+    args = [C.c_int(m), _p(chr_id), _p(pos), _p(val), C.c_uint64(n), _p(chrlen), C.c_uint32(len(chrlen)),
+            C.c_uint32(W), C.c_double(cutoff)]
+    cap = lib().pgt_oracle_extreme(*args, C.c_uint64(0), *([None] * 9))
+    if cap < 0:
+        raise ValueError(f"pgt_oracle_extreme error {cap}")
+    o = dict(label=np.zeros(cap, np.uint32), start=np.zeros(cap, np.uint32), end=np.zeros(cap, np.uint32),
+             ext=np.zeros(cap), extpos=np.zeros(cap, np.uint32), nbig=np.zeros(cap, np.uint32), prop=np.zeros(cap),
+             n=np.zeros(cap, np.uint32), first=np.zeros(cap, np.uint64))
+    r = lib().pgt_oracle_extreme(*args, C.c_uint64(cap), _p(o["label"]), _p(o["start"]), _p(o["end"]), _p(o["ext"]),
+                                 _p(o["extpos"]), _p(o["nbig"]), _p(o["prop"]), _p(o["n"]), _p(o["first"]))
+    assert r == cap
+    return o
+
+
+def extreme_rows(res, names):
+    """printWindow of ihsWindow.cpp:75-84 / xpehhWindow.cpp:65-74."""
+    rows = []
+    for i in range(len(res["n"])):
+        lab = res["label"][i]
+        head = [names[lab] if lab != 0xFFFFFFFF else "", str(res["start"][i]), str(res["end"][i])]
+        if res["n"][i] > 0:
+            rows.append("\t".join(head + [g6(res["ext"][i]), str(res["extpos"][i]), g6(res["prop"][i]), str(res["n"][i])]))
+        else:
+            rows.append("\t".join(head + ["NA", "NA", "NA", "0"]))
+    return rows
 
 
 # ---- synthetic generator (CPU twin) ----------------------------------------------------

@@ -42,3 +42,19 @@ def maf_text(names, lengths, pos, f_micro, nind):
 
 def sizes_text(names, chr_len):
     return "".join(f"{nm}\t{ln}\n" for nm, ln in zip(names, chr_len))
+
+
+def ihs_text(names, lengths, pos, v_micro):
+    """selscan `norm --ihs` output: id pos freq ihh1 ihh0 unstd norm crit (no header; ihsWindow.cpp:101,163)."""
+    chr_id = expand_chr(lengths)
+    return "".join(f"{names[c]}_{p}\t{p}\t0.25\t0.1\t0.2\t{micro_str(-v)}\t{micro_str(v)}\t{int(abs(v) > 2000000)}\n"
+                   for c, p, v in zip(chr_id, pos, v_micro))
+
+
+def xpehh_text(names, lengths, pos, v_micro):
+    """selscan `norm --xpehh` output: id pos gpos p1 ihh1 p2 ihh2 xpehh normxpehh crit, one header line
+    (xpehhWindow.cpp:94,110-115,165)."""
+    chr_id = expand_chr(lengths)
+    head = "id\tpos\tgpos\tp1\tihh1\tp2\tihh2\txpehh\tnormxpehh\tcrit\n"
+    return head + "".join(f"{names[c]}_{p}\t{p}\t{p / 1e6:.6f}\t0.5\t0.1\t0.25\t0.2\t{micro_str(v // 2)}\t{micro_str(v)}\t0\n"
+                          for c, p, v in zip(chr_id, pos, v_micro))
