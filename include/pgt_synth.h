@@ -13,6 +13,7 @@
  *   fst : chr pos a b                      (/root/reference/fstWindow.cpp:17-21,141)
  *   het : chr pos genotype                 (/root/reference/hetWindow.cpp:18,139)
  *   dxy : chromo position .. freq nInd x2  (/root/reference/dxyWindow.cpp:24-32,146-152)
+ *   score : normalised iHS / XP-EHH column   (/root/reference/ihsWindow.cpp:160, xpehhWindow.cpp:165)
  */
 #ifndef PGT_SYNTH_H
 #define PGT_SYNTH_H
@@ -31,7 +32,8 @@ enum {
 	PGT_COL_HET_G = 3,
 	PGT_COL_DXY_F = 4,
 	PGT_COL_DXY_N = 5,
-	PGT_COL_POS = 6
+	PGT_COL_POS = 6,
+	PGT_COL_SCORE = 7
 };
 
 PGT_HD uint64_t pgt_splitmix64(uint64_t x) {
@@ -91,6 +93,14 @@ PGT_HD double pgt_synth_dxy_f2(uint64_t seed, uint64_t site) { return pgt_micro_
 /* nInd ~ U{0..20} per population */
 PGT_HD int pgt_synth_dxy_n1(uint64_t seed, uint64_t site) { return (int)(pgt_site_hash(seed, PGT_COL_DXY_N, site) % 21u); }
 PGT_HD int pgt_synth_dxy_n2(uint64_t seed, uint64_t site) { return (int)((pgt_site_hash(seed, PGT_COL_DXY_N, site) >> 32) % 21u); }
+
+/* normalised selection score ~ N(0,1) at 1e-6 resolution (ties across a window stay possible: the
+ * reference keeps the first extreme, ihsWindow.cpp:166) */
+PGT_HD int64_t pgt_synth_score_micro(uint64_t seed, uint64_t site) {
+	uint64_t h = pgt_site_hash(seed, PGT_COL_SCORE, site);
+	return pgt_ih4(h) * 26 + (int64_t)(pgt_splitmix64(h) % 27u) - 13;
+}
+PGT_HD double pgt_synth_score(uint64_t seed, uint64_t site) { return pgt_micro_to_double(pgt_synth_score_micro(seed, site)); }
 
 /* position of the i-th (0-based) site of a contig.
  * density 1 : every bp is a site (pos = i+1);

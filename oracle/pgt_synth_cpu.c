@@ -38,6 +38,10 @@ void pgt_oracle_synth_dxy(uint64_t seed, uint64_t site0, uint64_t n, double* f1,
 }
 
 /* positions of sites [site0, site0+n) of one contig whose first site has global index contig_site0 */
+void pgt_oracle_synth_score(uint64_t seed, uint64_t site0, uint64_t n, double* score) {
+	for (uint64_t i = 0; i < n; ++i) score[i] = pgt_synth_score(seed, site0 + i);
+}
+
 void pgt_oracle_synth_pos(uint64_t seed, uint64_t site0, uint64_t n, uint64_t contig_site0, uint32_t density, uint32_t* pos) {
 	for (uint64_t i = 0; i < n; ++i) pos[i] = pgt_synth_pos(seed, site0 + i, site0 + i - contig_site0, density);
 }

@@ -1,4 +1,5 @@
-"""popgenomicstools_b200 -- B200-native windowed site-statistic scan (fstWindow / hetWindow / dxyWindow hot path).
+"""popgenomicstools_b200 -- B200-native windowed site-statistic scan (fstWindow / hetWindow / dxyWindow hot path,
+plus the bp-window extreme-score scans of ihsWindow / xpehhWindow).
 
 Thin host layer over libpgtscan.so (hand-written sm_100a kernels behind the C ABI of
 include/pgt_scan.h).  Importing the package loads the shared library and fails loudly if it is
@@ -12,5 +13,7 @@ _cabi.load()
 from .scan import (WindowPlan, dxy_window, fst_window, fused_window, het_window, kernel_launch_count, scan,  # noqa: E402
                    synth_dxy, synth_fst, synth_het, synth_pos, profile, profile_read, tune)
 
-__all__ = ["WindowPlan", "scan", "fst_window", "het_window", "dxy_window", "fused_window", "synth_fst", "synth_het",
+from .extreme import (ExtremePlan, ihs_window, profile_read_extreme, scan_extreme, synth_score, xpehh_window)  # noqa: E402
+
+__all__ = ["ExtremePlan", "scan_extreme", "ihs_window", "xpehh_window", "synth_score", "WindowPlan", "scan", "fst_window", "het_window", "dxy_window", "fused_window", "synth_fst", "synth_het",
            "synth_dxy", "synth_pos", "kernel_launch_count", "PgtError"]

@@ -1,4 +1,4 @@
-"""ctypes binding of libpgtscan.so (include/pgt_scan.h).
+"""ctypes binding of libpgtscan.so (include/pgt_scan.h, include/pgt_extreme.h).
 
 The shared library is built in-tree (popgenomicstools_b200/csrc/Makefile, or
 ``__graft_entry__.build()``).  There is no Python/CPU fallback: a missing library raises
@@ -33,6 +33,14 @@ WINDOW_FIELDS = ("label", "start_pos", "end_pos", "mid_pos", "nsites", "sum_a", 
                  "het", "dxy", "neffective", "nskip", "dxy_global")
 
 
+XWINDOW_FIELDS = ("ext_value", "ext_pos", "ext_site", "nbig", "nsites", "prop")
+PGT_XSTAT_IHS, PGT_XSTAT_XPEHH = 0, 1
+
+
+class PgtXWindows(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in XWINDOW_FIELDS]
+
+
 class PgtColumns(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in COLUMN_FIELDS]
 
@@ -44,7 +52,7 @@ class PgtWindows(C.Structure):
 _u64p = C.POINTER(C.c_uint64)
 _u32p = C.POINTER(C.c_uint32)
 
-# name -> (restype, argtypes); every symbol include/pgt_scan.h declares
+# name -> (restype, argtypes); every symbol include/pgt_scan.h and include/pgt_extreme.h declare
 PROTOTYPES = {
     "pgt_last_error": (C.c_char_p, []),
     "pgt_abi_version": (C.c_int, []),
@@ -89,6 +97,20 @@ PROTOTYPES = {
     "pgt_profile_read": (C.c_int, [C.POINTER(C.c_double), _u64p, C.POINTER(C.c_double), _u64p]),
     "pgt_tune": (C.c_int, [C.c_char_p, C.c_int]),
     "pgt_kernel_launch_count": (C.c_uint64, []),
+    # include/pgt_extreme.h
+    "pgt_xplan_create": (C.c_int, [C.POINTER(C.c_void_p), C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32,
+                                   C.c_uint32]),
+    "pgt_xplan_destroy": (None, [C.c_void_p]),
+    "pgt_xplan_num_windows": (C.c_uint64, [C.c_void_p]),
+    "pgt_xplan_num_units": (C.c_uint64, [C.c_void_p]),
+    "pgt_xplan_num_sites": (C.c_uint64, [C.c_void_p]),
+    "pgt_xplan_windows": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "pgt_xplan_shard": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, _u64p, _u64p, _u64p, _u64p]),
+    "pgt_scan_extreme_workspace_bytes": (C.c_size_t, [C.c_void_p, C.POINTER(PgtRange), C.c_int]),
+    "pgt_scan_extreme": (C.c_int, [C.c_void_p, C.POINTER(PgtRange), C.c_int, C.c_double, C.c_void_p, C.c_void_p,
+                                   C.POINTER(PgtXWindows), C.c_void_p, C.c_size_t, C.c_int, C.c_void_p]),
+    "pgt_synth_score": (C.c_int, [C.c_uint64, C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p]),
+    "pgt_profile_read_extreme": (C.c_int, [C.POINTER(C.c_double), _u64p, C.POINTER(C.c_double), _u64p]),
 }
 
 _lib = None

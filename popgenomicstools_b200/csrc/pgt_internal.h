@@ -21,6 +21,11 @@ struct pgt_plan {
 
 int pgt_set_error(int code, const std::string& msg);
 
+// shared by the .cu files: launch counter and the optional per-kernel event timing (pgt_scan.cu)
+void pgt_count_launch();
+bool pgt_profile_enabled();
+void pgt_profile_push(int kind, void* ev_a, void* ev_b);  // cudaEvent_t pair, recorded by the caller
+
 // segment index containing global window w / global unit j / global site x
 uint32_t pgt_plan_seg_of_window(const pgt_plan* p, uint64_t w);
 uint32_t pgt_plan_seg_of_unit(const pgt_plan* p, uint64_t j);

@@ -28,6 +28,7 @@
 #include <string>
 #include <vector>
 
+#include "../../include/pgt_extreme.h"
 #include "pgt_internal.h"
 
 // ----------------------------------------------------------------------------- utilities
@@ -88,12 +89,18 @@ extern "C" int pgt_host_unregister(void* p) {
 }
 
 // ---- optional per-kernel timing (bench.py roofline): CUDA events on the launching stream
+// kinds: 0 = level 1 (k_units*), 1 = level 2 (k_windows*), 2 / 3 = level 1 / 2 of the extreme scan
 struct ProfEvent {
 	cudaEvent_t a, b;
-	int kind;  // 0 = level 1 (k_units), 1 = level 2 (k_windows)
+	int kind;
 };
 static bool g_profile = false;
 static std::vector<ProfEvent> g_prof_events;
+static double g_prof_ms[4] = {0, 0, 0, 0};
+static uint64_t g_prof_n[4] = {0, 0, 0, 0};
+
+bool pgt_profile_enabled() { return g_profile; }
+void pgt_profile_push(int kind, void* ev_a, void* ev_b) { g_prof_events.push_back(ProfEvent{(cudaEvent_t)ev_a, (cudaEvent_t)ev_b, kind}); }
 
 struct ProfScope {
 	cudaStream_t st;
@@ -120,9 +127,8 @@ extern "C" int pgt_profile(int enable) {
 	return PGT_OK;
 }
 
-extern "C" int pgt_profile_read(double* units_ms, uint64_t* units_launches, double* windows_ms, uint64_t* windows_launches) {
-	double ms[2] = {0, 0};
-	uint64_t n[2] = {0, 0};
+// synchronise all recorded events and fold them into the per-kind totals
+static int prof_drain() {
 	for (ProfEvent& e : g_prof_events) {
 		float t = 0;
 		cudaError_t err = cudaEventSynchronize(e.b);
@@ -133,15 +139,27 @@ extern "C" int pgt_profile_read(double* units_ms, uint64_t* units_launches, doub
 			g_prof_events.clear();
 			return cuda_fail(err, "pgt_profile_read");
 		}
-		ms[e.kind] += t;
-		n[e.kind]++;
+		g_prof_ms[e.kind & 3] += t;
+		g_prof_n[e.kind & 3]++;
 	}
 	g_prof_events.clear();
-	if (units_ms) *units_ms = ms[0];
-	if (units_launches) *units_launches = n[0];
-	if (windows_ms) *windows_ms = ms[1];
-	if (windows_launches) *windows_launches = n[1];
 	return PGT_OK;
+}
+static int prof_read(int k0, double* units_ms, uint64_t* units_launches, double* windows_ms, uint64_t* windows_launches) {
+	PGT_TRY(prof_drain());
+	if (units_ms) *units_ms = g_prof_ms[k0];
+	if (units_launches) *units_launches = g_prof_n[k0];
+	if (windows_ms) *windows_ms = g_prof_ms[k0 + 1];
+	if (windows_launches) *windows_launches = g_prof_n[k0 + 1];
+	g_prof_ms[k0] = g_prof_ms[k0 + 1] = 0;
+	g_prof_n[k0] = g_prof_n[k0 + 1] = 0;
+	return PGT_OK;
+}
+extern "C" int pgt_profile_read(double* units_ms, uint64_t* units_launches, double* windows_ms, uint64_t* windows_launches) {
+	return prof_read(0, units_ms, units_launches, windows_ms, windows_launches);
+}
+extern "C" int pgt_profile_read_extreme(double* units_ms, uint64_t* units_launches, double* windows_ms, uint64_t* windows_launches) {
+	return prof_read(2, units_ms, units_launches, windows_ms, windows_launches);
 }
 
 // tuning knobs (tests / experiments, pgt_tune):

@@ -9,7 +9,6 @@
 #include "../../include/pgt_synth.h"
 #include "pgt_internal.h"
 
-extern void pgt_count_launch();
 
 #define PGT_CUDA(call)                                                                                   \
 	do {                                                                                                 \

@@ -170,6 +170,12 @@ def synth_dxy(seed, site0, n):
     return f1, f2, n1, n2
 
 
+def synth_score(seed, site0, n):
+    s = np.empty(n)
+    lib().pgt_oracle_synth_score(C.c_uint64(seed), C.c_uint64(site0), C.c_uint64(n), _p(s))
+    return s
+
+
 def synth_pos(seed, contig_offsets, density):
     """Positions for all sites of contigs given by offsets[ncontig+1]."""
     n = int(contig_offsets[-1])

@@ -1,4 +1,4 @@
-"""The C-ABI library loads without a GPU and exports exactly what include/pgt_scan.h declares;
+"""The C-ABI library loads without a GPU and exports exactly what include/pgt_scan.h and include/pgt_extreme.h declare;
 compute entry points fail loudly (PGT_ERR_CUDA) when no device is usable -- no CPU fallback."""
 import ctypes as C
 import os
@@ -11,9 +11,11 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def declared_functions():
-    src = open(os.path.join(ROOT, "include", "pgt_scan.h")).read()
-    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
-    names = re.findall(r"\b(pgt_[a-z0-9_]+)\s*\(", src)
+    names = []
+    for hdr in ("pgt_scan.h", "pgt_extreme.h"):
+        src = open(os.path.join(ROOT, "include", hdr)).read()
+        src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+        names += re.findall(r"\b(pgt_[a-z0-9_]+)\s*\(", src)
     return sorted(set(names))
 
 
@@ -23,10 +25,10 @@ def test_every_declared_symbol_is_exported_and_bound():
     decl = declared_functions()
     assert len(decl) >= 30
     for name in decl:
-        assert hasattr(lib, name), f"{name} declared in pgt_scan.h but not exported by libpgtscan.so"
+        assert hasattr(lib, name), f"{name} declared in include/*.h but not exported by libpgtscan.so"
         assert name in _cabi.PROTOTYPES, f"{name} has no ctypes prototype in _cabi.py"
     for name in _cabi.PROTOTYPES:
-        assert name in decl, f"{name} bound in _cabi.py but not declared in pgt_scan.h"
+        assert name in decl, f"{name} bound in _cabi.py but not declared in include/*.h"
     assert lib.pgt_abi_version() == 1
 
 
@@ -42,6 +44,11 @@ def test_struct_layouts_match_header():
     wins = re.search(r"typedef struct \{((?:(?!typedef struct).)*?)\} pgt_windows;", hdr, re.S).group(1)
     wins = re.sub(r"/\*.*?\*/", "", wins, flags=re.S)
     assert tuple(re.findall(r"\*\s*(\w+);", wins)) == _cabi.WINDOW_FIELDS
+    xhdr = open(os.path.join(ROOT, "include", "pgt_extreme.h")).read()
+    xw = re.search(r"typedef struct \{((?:(?!typedef struct).)*?)\} pgt_xwindows;", xhdr, re.S).group(1)
+    xw = re.sub(r"/\*.*?\*/", "", xw, flags=re.S)
+    assert tuple(re.findall(r"\*\s*(\w+);", xw)) == _cabi.XWINDOW_FIELDS
+    assert C.sizeof(_cabi.PgtXWindows) == 8 * len(_cabi.XWINDOW_FIELDS) == 48
 
 
 def test_scan_fails_loudly_without_device():
@@ -64,3 +71,15 @@ def test_scan_fails_loudly_without_device():
     assert b"CUDA" in lib.pgt_last_error()
     assert lib.pgt_synth_fst(1, 0, 10, a.ctypes.data, a.ctypes.data, None) < 0
     lib.pgt_plan_destroy(h)
+    # extreme scan: the host bookkeeping works without a device, the scan itself does not
+    pos = np.arange(1, 101, dtype=np.uint32)
+    xh = C.c_void_p()
+    assert lib.pgt_xplan_create(C.byref(xh), pos.ctypes.data, off.ctypes.data, None, 1, 10, 0) == 0
+    assert lib.pgt_xplan_num_windows(xh) == 11
+    xo = _cabi.PgtXWindows()
+    val = np.zeros(11)
+    xo.ext_value = val.ctypes.data
+    rc = lib.pgt_scan_extreme(xh, None, 0, 2.0, pos.ctypes.data, a.ctypes.data, C.byref(xo), ws.ctypes.data, ws.nbytes,
+                              _cabi.PGT_MEM_HOST, None)
+    assert rc == _cabi.PGT_ERR_CUDA
+    lib.pgt_xplan_destroy(xh)
