@@ -71,6 +71,13 @@ int pgt_xplan_windows(const pgt_xplan* plan, uint32_t* label, uint32_t* start, u
 int pgt_xplan_shard(const pgt_xplan* plan, uint32_t shard, uint32_t nshards, uint64_t* w_lo, uint64_t* w_hi,
                     uint64_t* site_lo, uint64_t* site_hi);
 
+/* Optional: keep the window tables (16 B per window) resident on the device so that repeated
+ * scans do not re-upload them.  `buffer` is caller-owned device memory of at least
+ * pgt_xplan_device_bytes(); it must outlive the binding.  buffer = NULL unbinds.  A bound plan
+ * may only be scanned on the device that owns the buffer. */
+size_t pgt_xplan_device_bytes(const pgt_xplan* plan);
+int pgt_xplan_bind_device(pgt_xplan* plan, void* buffer, size_t bytes, void* stream);
+
 /* Per-window results, w_hi - w_lo elements each, any pointer may be NULL.  Empty windows (the
  * reference's "NA NA NA 0" rows, ihsWindow.cpp:82) get ext_value = prop = NaN, ext_pos = 0,
  * ext_site = UINT64_MAX, nbig = nsites = 0. */

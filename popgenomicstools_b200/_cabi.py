@@ -106,6 +106,8 @@ PROTOTYPES = {
     "pgt_xplan_num_sites": (C.c_uint64, [C.c_void_p]),
     "pgt_xplan_windows": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "pgt_xplan_shard": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, _u64p, _u64p, _u64p, _u64p]),
+    "pgt_xplan_device_bytes": (C.c_size_t, [C.c_void_p]),
+    "pgt_xplan_bind_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "pgt_scan_extreme_workspace_bytes": (C.c_size_t, [C.c_void_p, C.POINTER(PgtRange), C.c_int]),
     "pgt_scan_extreme": (C.c_int, [C.c_void_p, C.POINTER(PgtRange), C.c_int, C.c_double, C.c_void_p, C.c_void_p,
                                    C.POINTER(PgtXWindows), C.c_void_p, C.c_size_t, C.c_int, C.c_void_p]),

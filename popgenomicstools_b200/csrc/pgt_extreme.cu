@@ -60,6 +60,7 @@ struct pgt_xplan {
 	std::vector<uint32_t> label, start, end;  // per window
 	std::vector<uint64_t> xoff;               // nwin+1: window w holds sites [xoff[w], xoff[w+1])
 	std::vector<uint64_t> unit0;              // nwin+1: first unit of window w
+	unsigned char* d_tables = nullptr;        // caller-owned device copy of xoff | unit0 (pgt_xplan_bind_device)
 };
 
 namespace {
@@ -235,15 +236,18 @@ extern "C" int pgt_xplan_shard(const pgt_xplan* plan, uint32_t shard, uint32_t n
 
 enum { XMODE_ABS = 0, XMODE_MAX = 1, XMODE_MIN = 2 };
 
-struct XPartial {
-	uint64_t best;  // global site index of the unit's first extreme
-	uint32_t nbig;
-	uint32_t pad;
+// unit partials, SoA (20 B per unit): signed score and global site index of the unit's first
+// extreme, sites beyond the cutoff
+struct XPartials {
+	double* val;
+	uint64_t* idx;
+	uint32_t* nbig;
 };
 
 struct XDev {
-	const uint64_t* xoff;   // nw+1, global site indices
-	const uint64_t* unit0;  // nw+1, relative to the first unit of the range
+	const uint64_t* xoff;   // nw+1 entries for windows w_lo..w_hi: global site indices
+	const uint64_t* unit0;  // nw+1 entries: global unit indices
+	uint64_t unit_base;     // unit0[w_lo]: partials are indexed by unit - unit_base
 	uint64_t nw;
 	uint64_t site_lo, site_hi;  // sites of the range
 	uint64_t origin;            // global index of element 0 of score / pos
@@ -253,7 +257,7 @@ struct XDev {
 
 // key: larger = more extreme.  NaN never beats anything (x > NaN and NaN > x are false in the
 // reference's comparisons); the one case where the reference keeps a NaN -- it is the first site
-// of the window (updateMax on nsites == 0, ihsWindow.cpp:161-164) -- is restored in x_emit.
+// of the window (updateMax on nsites == 0, ihsWindow.cpp:161-164) -- is handled explicitly.
 template <int MODE>
 __device__ __forceinline__ double x_key(double v) {
 	double k = MODE == XMODE_ABS ? fabs(v) : (MODE == XMODE_MAX ? v : -v);
@@ -266,27 +270,18 @@ __device__ __forceinline__ bool x_big(double v, double cutoff) {
 
 struct XAcc {
 	double key;
+	double val;
 	uint64_t idx;
 	uint32_t nbig;
 };
-__device__ __forceinline__ void x_take(XAcc& a, double k, uint64_t i) {
+// (key, idx) lexicographic: larger key wins, equal keys keep the smaller site index = the first
+// extreme in file order, whatever the evaluation order
+__device__ __forceinline__ void x_take(XAcc& a, double k, double v, uint64_t i) {
 	if (k > a.key || (k == a.key && i < a.idx)) {
 		a.key = k;
+		a.val = v;
 		a.idx = i;
 	}
-}
-
-__device__ __forceinline__ void x_emit(const XDev& P, uint64_t w, uint64_t best, uint32_t nbig, uint64_t n, const double* __restrict__ score,
-                                       const uint32_t* __restrict__ pos, const pgt_xwindows& out) {
-	const uint64_t first = P.xoff[w];
-	const double v0 = score[first - P.origin];
-	if (v0 != v0) best = first;
-	if (out.ext_value) out.ext_value[w] = score[best - P.origin];
-	if (out.ext_pos) out.ext_pos[w] = pos ? pos[best - P.origin] : 0u;
-	if (out.ext_site) out.ext_site[w] = best;
-	if (out.nbig) out.nbig[w] = nbig;
-	if (out.nsites) out.nsites[w] = (uint32_t)n;
-	if (out.prop) out.prop[w] = (double)nbig / (double)(uint32_t)n;  // ihsWindow.cpp:79: double / unsigned
 }
 
 // last window w in [0, nw) with xoff[w] <= s
@@ -300,9 +295,11 @@ __device__ __forceinline__ uint64_t x_window_of(const XDev& P, uint64_t s) {
 	return lo;
 }
 
+// Level 1: pure streaming.  Window bounds and unit indices are fetched one window ahead, the only
+// store per unit takes its data from registers, so a group's next unit never waits on anything
+// but its own score loads.
 template <int MODE, int G>
-__global__ void __launch_bounds__(256) k_xunits(XDev P, uint64_t chunk, const double* __restrict__ score, const uint32_t* __restrict__ pos,
-                                                XPartial* __restrict__ partial, pgt_xwindows out) {
+__global__ void __launch_bounds__(256) k_xunits(XDev P, uint64_t chunk, const double* __restrict__ score, XPartials part) {
 	const uint32_t lane = threadIdx.x & 31u;
 	const uint32_t gl = lane & (G - 1);  // lane inside the group
 	const uint32_t gmask = G == 32 ? 0xffffffffu : (((1u << G) - 1u) << (lane & ~(uint32_t)(G - 1)));
@@ -310,73 +307,93 @@ __global__ void __launch_bounds__(256) k_xunits(XDev P, uint64_t chunk, const do
 	const uint64_t c_lo = P.site_lo + group * chunk;
 	if (c_lo >= P.site_hi) return;
 	const uint64_t c_hi = c_lo + chunk < P.site_hi ? c_lo + chunk : P.site_hi;
-	// first unit starting at or after c_lo
 	uint64_t w = x_window_of(P, c_lo);
+	uint64_t w_st = P.xoff[w];
 	uint64_t w_end = P.xoff[w + 1];
-	uint64_t st;
-	{
-		const uint64_t w_st = P.xoff[w];
-		const uint64_t k = (c_lo - w_st + P.U - 1) / P.U;
-		st = w_st + k * P.U;
-	}
-	const double* __restrict__ sc = score - P.origin;  // indexed by global site
+	uint64_t w_end2 = P.xoff[w + 2 <= P.nw ? w + 2 : P.nw];  // one window ahead
+	uint64_t u0 = P.unit0[w], u0n = P.unit0[w + 1];
+	uint64_t st = w_st + (c_lo - w_st + P.U - 1) / P.U * P.U;  // first unit starting at or after c_lo
+	const double* __restrict__ sc = score - P.origin;         // indexed by global site
 	for (;;) {
 		while (st >= w_end) {  // next non-empty window
 			++w;
 			if (w >= P.nw) return;
-			st = P.xoff[w];
-			w_end = P.xoff[w + 1];
+			w_st = w_end;
+			w_end = w_end2;
+			u0 = u0n;
+			w_end2 = P.xoff[w + 2 <= P.nw ? w + 2 : P.nw];
+			u0n = P.unit0[w + 1];
+			st = w_st;
 		}
 		if (st >= c_hi) return;
-		const uint64_t w_st = P.xoff[w];
 		const uint32_t len = (uint32_t)(w_end - st < P.U ? w_end - st : P.U);
-		XAcc a{-CUDART_INF, ~0ull, 0u};
+		XAcc a{-CUDART_INF, 0.0, ~0ull, 0u};
 		const double* __restrict__ p = sc + st;
+		bool first_nan = false;  // lane gl == 0 sees the window's first site when st == w_st
 		uint32_t x = gl;
 		for (; x + 7u * G < len; x += 8u * G) {
 			double v[8];
 #pragma unroll
 			for (int q = 0; q < 8; ++q) v[q] = __ldcs(p + x + q * G);
+			if (x == 0) first_nan = v[0] != v[0];
 #pragma unroll
 			for (int q = 0; q < 8; ++q) {
-				x_take(a, x_key<MODE>(v[q]), st + x + q * G);
+				x_take(a, x_key<MODE>(v[q]), v[q], st + x + q * G);
 				a.nbig += x_big<MODE>(v[q], P.cutoff) ? 1u : 0u;
 			}
 		}
 		for (; x < len; x += G) {
 			const double v = __ldcs(p + x);
-			x_take(a, x_key<MODE>(v), st + x);
+			if (x == 0) first_nan = v != v;
+			x_take(a, x_key<MODE>(v), v, st + x);
 			a.nbig += x_big<MODE>(v, P.cutoff) ? 1u : 0u;
 		}
 #pragma unroll
 		for (int m = G >> 1; m > 0; m >>= 1) {
 			const double ko = __shfl_xor_sync(gmask, a.key, m);
+			const double vo = __shfl_xor_sync(gmask, a.val, m);
 			const uint64_t io = __shfl_xor_sync(gmask, a.idx, m);
 			a.nbig += __shfl_xor_sync(gmask, a.nbig, m);
-			x_take(a, ko, io);
+			x_take(a, ko, vo, io);
 		}
 		if (gl == 0) {
-			const uint64_t n = w_end - w_st;
-			if (n <= P.U) x_emit(P, w, a.idx, a.nbig, n, score, pos, out);
-			else partial[P.unit0[w] + (st - w_st) / P.U] = XPartial{a.idx, a.nbig, 0u};
+			if (st == w_st && first_nan) {  // a NaN on the window's first site stays the extreme
+				a.val = p[0];
+				a.idx = st;
+			}
+			const uint64_t j = u0 + (st - w_st) / P.U - P.unit_base;
+			part.val[j] = a.val;
+			part.idx[j] = a.idx;
+			part.nbig[j] = a.nbig;
 		}
 		st += len;
 	}
 }
 
+__device__ __forceinline__ void x_emit(uint64_t w, double val, uint64_t best, uint32_t nbig, uint64_t n, uint64_t origin,
+                                       const uint32_t* __restrict__ pos, const pgt_xwindows& out) {
+	if (out.ext_value) out.ext_value[w] = val;
+	if (out.ext_pos) out.ext_pos[w] = pos ? pos[best - origin] : 0u;
+	if (out.ext_site) out.ext_site[w] = best;
+	if (out.nbig) out.nbig[w] = nbig;
+	if (out.nsites) out.nsites[w] = (uint32_t)n;
+	if (out.prop) out.prop[w] = (double)nbig / (double)(uint32_t)n;  // ihsWindow.cpp:79: double / unsigned
+}
+
+// Level 2: thread per window.  Empty windows get the "NA" defaults, single-unit windows copy their
+// partial, windows of 2..32 units are combined by their thread, longer ones by the whole warp.
 template <int MODE>
-__global__ void __launch_bounds__(256) k_xwindows(XDev P, const double* __restrict__ score, const uint32_t* __restrict__ pos,
-                                                  const XPartial* __restrict__ partial, pgt_xwindows out) {
+__global__ void __launch_bounds__(256) k_xwindows(XDev P, const uint32_t* __restrict__ pos, XPartials part, pgt_xwindows out) {
 	const uint64_t w = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
 	const uint32_t lane = threadIdx.x & 31u;
 	const bool valid = w < P.nw;
-	uint64_t n = 0, u0 = 0, nu = 0;
+	uint64_t n = 0, u0 = 0, nu = 0, first = 0;
 	if (valid) {
-		n = P.xoff[w + 1] - P.xoff[w];
-		u0 = P.unit0[w];
-		nu = P.unit0[w + 1] - u0;
+		first = P.xoff[w];
+		n = P.xoff[w + 1] - first;
+		u0 = P.unit0[w] - P.unit_base;
+		nu = P.unit0[w + 1] - P.unit_base - u0;
 	}
-	const double* __restrict__ sc = score - P.origin;
 	if (valid && n == 0) {  // the reference's "NA NA NA 0" row (ihsWindow.cpp:82)
 		if (out.ext_value) out.ext_value[w] = CUDART_NAN;
 		if (out.ext_pos) out.ext_pos[w] = 0u;
@@ -384,16 +401,18 @@ __global__ void __launch_bounds__(256) k_xwindows(XDev P, const double* __restri
 		if (out.nbig) out.nbig[w] = 0u;
 		if (out.nsites) out.nsites[w] = 0u;
 		if (out.prop) out.prop[w] = CUDART_NAN;
-	} else if (valid && nu >= 2 && nu <= 32) {
-		XAcc a{-CUDART_INF, ~0ull, 0u};
-		for (uint64_t j = 0; j < nu; ++j) {
-			const XPartial q = partial[u0 + j];
-			x_take(a, x_key<MODE>(sc[q.best]), q.best);
-			a.nbig += q.nbig;
+	} else if (valid && nu <= 32) {
+		const double v0 = part.val[u0];
+		XAcc a{x_key<MODE>(v0), v0, part.idx[u0], part.nbig[u0]};
+		if (!(v0 != v0 && a.idx == first)) {  // unless the first site is a NaN (it then stays)
+			for (uint64_t j = 1; j < nu; ++j) {
+				const double v = part.val[u0 + j];
+				x_take(a, x_key<MODE>(v), v, part.idx[u0 + j]);
+			}
 		}
-		x_emit(P, w, a.idx, a.nbig, n, score, pos, out);
+		for (uint64_t j = 1; j < nu; ++j) a.nbig += part.nbig[u0 + j];
+		x_emit(w, a.val, a.idx, a.nbig, n, P.origin, pos, out);
 	}
-	// windows of more than 32 units: the warp combines them one after the other
 	uint32_t todo = __ballot_sync(0xffffffffu, valid && nu > 32);
 	while (todo) {
 		const int src = __ffs(todo) - 1;
@@ -402,20 +421,29 @@ __global__ void __launch_bounds__(256) k_xwindows(XDev P, const double* __restri
 		const uint64_t ub = __shfl_sync(0xffffffffu, u0, src);
 		const uint64_t nub = __shfl_sync(0xffffffffu, nu, src);
 		const uint64_t nb = __shfl_sync(0xffffffffu, n, src);
-		XAcc a{-CUDART_INF, ~0ull, 0u};
+		const uint64_t fb = __shfl_sync(0xffffffffu, first, src);
+		XAcc a{-CUDART_INF, 0.0, ~0ull, 0u};
 		for (uint64_t j = lane; j < nub; j += 32) {
-			const XPartial q = partial[ub + j];
-			x_take(a, x_key<MODE>(sc[q.best]), q.best);
-			a.nbig += q.nbig;
+			const double v = part.val[ub + j];
+			x_take(a, x_key<MODE>(v), v, part.idx[ub + j]);
+			a.nbig += part.nbig[ub + j];
 		}
 #pragma unroll
 		for (int m = 16; m > 0; m >>= 1) {
 			const double ko = __shfl_xor_sync(0xffffffffu, a.key, m);
+			const double vo = __shfl_xor_sync(0xffffffffu, a.val, m);
 			const uint64_t io = __shfl_xor_sync(0xffffffffu, a.idx, m);
 			a.nbig += __shfl_xor_sync(0xffffffffu, a.nbig, m);
-			x_take(a, ko, io);
+			x_take(a, ko, vo, io);
 		}
-		if (lane == 0) x_emit(P, wb, a.idx, a.nbig, nb, score, pos, out);
+		if (lane == 0) {
+			const double v0 = part.val[ub];
+			if (v0 != v0 && part.idx[ub] == fb) {
+				a.val = v0;
+				a.idx = fb;
+			}
+			x_emit(wb, a.val, a.idx, a.nbig, nb, P.origin, pos, out);
+		}
 	}
 }
 
@@ -461,8 +489,9 @@ struct XProf {
 size_t xalign(size_t x) { return (x + 255) / 256 * 256; }
 
 struct XLayout {
-	uint64_t w_lo, w_hi, nw, site_lo, site_hi, nsite, unit_lo, nunit;
-	size_t off_xoff, off_unit0, off_partial, off_score, off_out, total = 0;
+	uint64_t w_lo = 0, w_hi = 0, nw = 0, site_lo = 0, site_hi = 0, nsite = 0, unit_lo = 0, nunit = 0;
+	bool resident = false;  // window tables are bound on the device (pgt_xplan_bind_device)
+	size_t off_xoff = 0, off_unit0 = 0, p_val = 0, p_idx = 0, p_nbig = 0, off_score = 0, total = 0;
 	// host mode staging of the outputs, one block per field
 	size_t o_value = 0, o_site = 0, o_nbig = 0, o_nsites = 0, o_prop = 0;
 };
@@ -483,18 +512,23 @@ int x_layout(const pgt_xplan* plan, const pgt_range* range, pgt_mem mem, XLayout
 	L->nsite = L->site_hi - L->site_lo;
 	L->unit_lo = plan->unit0[lo];
 	L->nunit = plan->unit0[hi] - plan->unit0[lo];
+	L->resident = plan->d_tables != nullptr;
 	size_t o = 0;
-	L->off_xoff = o;
-	o += xalign((L->nw + 1) * sizeof(uint64_t));
-	L->off_unit0 = o;
-	o += xalign((L->nw + 1) * sizeof(uint64_t));
-	L->off_partial = o;
-	o += xalign(L->nunit * sizeof(XPartial));
-	L->off_score = o;
-	L->off_out = o;
+	if (!L->resident) {
+		L->off_xoff = o;
+		o += xalign((L->nw + 1) * sizeof(uint64_t));
+		L->off_unit0 = o;
+		o += xalign((L->nw + 1) * sizeof(uint64_t));
+	}
+	L->p_val = o;
+	o += xalign(L->nunit * sizeof(double));
+	L->p_idx = o;
+	o += xalign(L->nunit * sizeof(uint64_t));
+	L->p_nbig = o;
+	o += xalign(L->nunit * sizeof(uint32_t));
 	if (mem == PGT_MEM_HOST) {
+		L->off_score = o;
 		o += xalign(L->nsite * sizeof(double));
-		L->off_out = o;
 		L->o_value = o;
 		o += xalign(L->nw * sizeof(double));
 		L->o_site = o;
@@ -518,37 +552,38 @@ int x_num_sms() {
 }
 
 template <int MODE, int G>
-void x_launch_units(const XDev& P, uint64_t nsite, const double* score, const uint32_t* pos, XPartial* partial, const pgt_xwindows& out,
-                    cudaStream_t st) {
+void x_launch_units(const XDev& P, uint64_t nsite, const double* score, const XPartials& part, cudaStream_t st) {
 	// site axis dealt in equal chunks to groups of G lanes: at least 64 sites per lane, at most
-	// 8 resident CTAs of 256 threads per SM
-	const uint64_t max_groups = (uint64_t)x_num_sms() * 8ull * 256ull / G;
+	// one wave of resident CTAs (grid = multiple of the SM count)
+	int per_sm = 0;
+	if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_xunits<MODE, G>, 256, 0) != cudaSuccess || per_sm < 1) per_sm = 4;
+	const uint64_t max_groups = (uint64_t)x_num_sms() * (uint64_t)per_sm * 256ull / G;
 	uint64_t chunk = (nsite + max_groups - 1) / max_groups;
 	const uint64_t min_chunk = 64ull * G;
 	if (chunk < min_chunk) chunk = min_chunk;
 	const uint64_t groups = (nsite + chunk - 1) / chunk;
 	const uint64_t threads = groups * G;
 	const unsigned grid = (unsigned)((threads + 255) / 256);
-	k_xunits<MODE, G><<<grid, 256, 0, st>>>(P, chunk, score, pos, partial, out);
+	k_xunits<MODE, G><<<grid, 256, 0, st>>>(P, chunk, score, part);
 	pgt_count_launch();
 }
 
 template <int MODE>
-int x_run(const XDev& P, uint64_t nsite, uint64_t nunit, const double* score, const uint32_t* pos, XPartial* partial, const pgt_xwindows& out,
-          cudaStream_t st) {
+int x_run(const XDev& P, uint64_t nsite, uint64_t nunit, const double* score, const uint32_t* pos, const XPartials& part,
+          const pgt_xwindows& out, cudaStream_t st) {
 	if (nsite) {
 		XProf prof(2, st);
 		// lanes per unit from the mean unit length: short windows get narrow groups
 		const uint64_t mean = nunit ? nsite / nunit : 0;
-		if (mean >= 128) x_launch_units<MODE, 32>(P, nsite, score, pos, partial, out, st);
-		else if (mean >= 32) x_launch_units<MODE, 8>(P, nsite, score, pos, partial, out, st);
-		else if (mean >= 8) x_launch_units<MODE, 2>(P, nsite, score, pos, partial, out, st);
-		else x_launch_units<MODE, 1>(P, nsite, score, pos, partial, out, st);
+		if (mean >= 128) x_launch_units<MODE, 32>(P, nsite, score, part, st);
+		else if (mean >= 32) x_launch_units<MODE, 8>(P, nsite, score, part, st);
+		else if (mean >= 8) x_launch_units<MODE, 2>(P, nsite, score, part, st);
+		else x_launch_units<MODE, 1>(P, nsite, score, part, st);
 		PGT_CUDA(cudaGetLastError());
 	}
 	if (P.nw) {
 		XProf prof(3, st);
-		k_xwindows<MODE><<<(unsigned)((P.nw + 255) / 256), 256, 0, st>>>(P, score, pos, partial, out);
+		k_xwindows<MODE><<<(unsigned)((P.nw + 255) / 256), 256, 0, st>>>(P, pos, part, out);
 		pgt_count_launch();
 		PGT_CUDA(cudaGetLastError());
 	}
@@ -556,6 +591,27 @@ int x_run(const XDev& P, uint64_t nsite, uint64_t nunit, const double* score, co
 }
 
 }  // namespace
+
+extern "C" size_t pgt_xplan_device_bytes(const pgt_xplan* plan) {
+	return plan ? 2 * xalign((plan->nwin + 1) * sizeof(uint64_t)) + 256 : 0;
+}
+
+extern "C" int pgt_xplan_bind_device(pgt_xplan* plan, void* buffer, size_t bytes, void* stream) {
+	if (!plan) return pgt_set_error(PGT_ERR_ARGS, "pgt_xplan_bind_device: plan is NULL");
+	if (!buffer) {
+		plan->d_tables = nullptr;
+		return PGT_OK;
+	}
+	if (bytes < pgt_xplan_device_bytes(plan)) return pgt_set_error(PGT_ERR_NOMEM, "pgt_xplan_bind_device: buffer too small");
+	cudaStream_t st = (cudaStream_t)stream;
+	unsigned char* b = (unsigned char*)(((uintptr_t)buffer + 255) / 256 * 256);
+	const size_t tb = (plan->nwin + 1) * sizeof(uint64_t);
+	PGT_CUDA(cudaMemcpyAsync(b, plan->xoff.data(), tb, cudaMemcpyHostToDevice, st));
+	PGT_CUDA(cudaMemcpyAsync(b + xalign(tb), plan->unit0.data(), tb, cudaMemcpyHostToDevice, st));
+	PGT_CUDA(cudaStreamSynchronize(st));
+	plan->d_tables = b;
+	return PGT_OK;
+}
 
 extern "C" size_t pgt_scan_extreme_workspace_bytes(const pgt_xplan* plan, const pgt_range* range, pgt_mem mem) {
 	XLayout L;
@@ -585,29 +641,27 @@ extern "C" int pgt_scan_extreme(const pgt_xplan* plan, const pgt_range* range, p
 	}
 	cudaStream_t st = (cudaStream_t)stream;
 	unsigned char* ws = (unsigned char*)(((uintptr_t)workspace + 255) / 256 * 256);
-	uint64_t* d_xoff = (uint64_t*)(ws + L.off_xoff);
-	uint64_t* d_unit0 = (uint64_t*)(ws + L.off_unit0);
-	XPartial* d_partial = (XPartial*)(ws + L.off_partial);
-	// window tables of the range; unit indices relative to the range's first unit
-	PGT_CUDA(cudaMemcpyAsync(d_xoff, plan->xoff.data() + L.w_lo, (L.nw + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
-	std::vector<uint64_t> rel;
-	const uint64_t* unit0_src = plan->unit0.data() + L.w_lo;
-	if (L.unit_lo != 0) {
-		rel.resize(L.nw + 1);
-		for (uint64_t i = 0; i <= L.nw; ++i) rel[i] = unit0_src[i] - L.unit_lo;
-		unit0_src = rel.data();
-	}
-	PGT_CUDA(cudaMemcpyAsync(d_unit0, unit0_src, (L.nw + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
-	if (!rel.empty()) PGT_CUDA(cudaStreamSynchronize(st));  // `rel` is pageable and dies with this scope
 
 	XDev P;
-	P.xoff = d_xoff;
-	P.unit0 = d_unit0;
+	if (L.resident) {  // tables bound once with pgt_xplan_bind_device: nothing to upload
+		const uint64_t* t = (const uint64_t*)plan->d_tables;
+		P.xoff = t + L.w_lo;
+		P.unit0 = (const uint64_t*)(plan->d_tables + xalign((plan->nwin + 1) * sizeof(uint64_t))) + L.w_lo;
+	} else {
+		uint64_t* d_xoff = (uint64_t*)(ws + L.off_xoff);
+		uint64_t* d_unit0 = (uint64_t*)(ws + L.off_unit0);
+		PGT_CUDA(cudaMemcpyAsync(d_xoff, plan->xoff.data() + L.w_lo, (L.nw + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
+		PGT_CUDA(cudaMemcpyAsync(d_unit0, plan->unit0.data() + L.w_lo, (L.nw + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
+		P.xoff = d_xoff;
+		P.unit0 = d_unit0;
+	}
+	P.unit_base = L.unit_lo;
 	P.nw = L.nw;
 	P.site_lo = L.site_lo;
 	P.site_hi = L.site_hi;
 	P.U = plan->U;
 	P.cutoff = cutoff;
+	XPartials part{(double*)(ws + L.p_val), (uint64_t*)(ws + L.p_idx), (uint32_t*)(ws + L.p_nbig)};
 	const int mode = stat == PGT_XSTAT_IHS ? XMODE_ABS : (cutoff < 0 ? XMODE_MIN : XMODE_MAX);  // xpehhWindow.cpp:171
 
 	pgt_xwindows dout;
@@ -634,9 +688,9 @@ extern "C" int pgt_scan_extreme(const pgt_xplan* plan, const pgt_range* range, p
 		if (out->nsites) dout.nsites = (uint32_t*)(ws + L.o_nsites);
 	}
 	switch (mode) {
-		case XMODE_ABS: rc = x_run<XMODE_ABS>(P, L.nsite, L.nunit, d_score, d_pos, d_partial, dout, st); break;
-		case XMODE_MAX: rc = x_run<XMODE_MAX>(P, L.nsite, L.nunit, d_score, d_pos, d_partial, dout, st); break;
-		default: rc = x_run<XMODE_MIN>(P, L.nsite, L.nunit, d_score, d_pos, d_partial, dout, st); break;
+		case XMODE_ABS: rc = x_run<XMODE_ABS>(P, L.nsite, L.nunit, d_score, d_pos, part, dout, st); break;
+		case XMODE_MAX: rc = x_run<XMODE_MAX>(P, L.nsite, L.nunit, d_score, d_pos, part, dout, st); break;
+		default: rc = x_run<XMODE_MIN>(P, L.nsite, L.nunit, d_score, d_pos, part, dout, st); break;
 	}
 	if (rc != PGT_OK) return rc;
 	if (mem == PGT_MEM_HOST) {

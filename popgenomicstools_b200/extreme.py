@@ -54,6 +54,7 @@ class ExtremePlan:
                                    int(unit_sites)))
         self._h = h
         self._workspaces = {}
+        self._bound = None
 
     def __del__(self):
         h, self._h = getattr(self, "_h", None), None
@@ -89,6 +90,20 @@ class ExtremePlan:
         v = [C.c_uint64() for _ in range(4)]
         check(self._lib.pgt_xplan_shard(self._h, rank, nranks, *[C.byref(x) for x in v]))
         return tuple(x.value for x in v)
+
+    def bind(self, device):
+        """Keep the window tables resident on `device` (pgt_xplan_bind_device); later scans on that
+        device skip the per-call table upload."""
+        torch = _torch()
+        device = torch.device(device)
+        if self._bound is not None and self._bound[0] == device:
+            return
+        buf = torch.empty(int(self._lib.pgt_xplan_device_bytes(self._h)), dtype=torch.uint8, device=device)
+        with torch.cuda.device(device):
+            check(self._lib.pgt_xplan_bind_device(self._h, buf.data_ptr(), buf.numel(),
+                                                  C.c_void_p(torch.cuda.current_stream(device).cuda_stream)))
+        self._bound = (device, buf)
+        self._workspaces = {}
 
     def workspace(self, device, mem, window_range=None, site_origin=0):
         torch = _torch()
@@ -153,6 +168,10 @@ def scan_extreme(plan, stat, cutoff, pos, score, window_range=None, site_origin=
         if v is not None:
             setattr(w, k, v.data_ptr() if on_device else v.ctypes.data)
     mem = _cabi.PGT_MEM_DEVICE if on_device else _cabi.PGT_MEM_HOST
+    if on_device:
+        plan.bind(dev)
+    elif plan._bound is not None and plan._bound[0] != dev:
+        raise ValueError(f"plan is bound to {plan._bound[0]}, scan requested on {dev}")
     ws = plan.workspace(dev, mem, window_range, site_origin)
     with torch.cuda.device(dev):
         stream = torch.cuda.current_stream(dev).cuda_stream
