@@ -52,6 +52,9 @@ static int xcuda_fail(cudaError_t e, const char* what) {
 
 static const uint32_t kDefaultUnit = 2048;
 
+// pgt_tune("xgroup", G): force the lanes-per-unit of the extreme scan's level 1 (0 = auto; 4, 8, 16, 32)
+int g_tune_xgroup = 0;
+
 // ----------------------------------------------------------------------------- host plan
 
 struct pgt_xplan {
@@ -331,7 +334,7 @@ __global__ void __launch_bounds__(256) k_xunits(XDev P, uint64_t chunk, const do
 		const double* __restrict__ p = sc + st;
 		bool first_nan = false;  // lane gl == 0 sees the window's first site when st == w_st
 		uint32_t x = gl;
-		for (; x + 7u * G < len; x += 8u * G) {
+		for (; x + 7u * G < len; x += 8u * G) {  // full rounds: 8 loads in flight per lane
 			double v[8];
 #pragma unroll
 			for (int q = 0; q < 8; ++q) v[q] = __ldcs(p + x + q * G);
@@ -342,11 +345,18 @@ __global__ void __launch_bounds__(256) k_xunits(XDev P, uint64_t chunk, const do
 				a.nbig += x_big<MODE>(v[q], P.cutoff) ? 1u : 0u;
 			}
 		}
-		for (; x < len; x += G) {
-			const double v = __ldcs(p + x);
-			if (x == 0) first_nan = v != v;
-			x_take(a, x_key<MODE>(v), v, st + x);
-			a.nbig += x_big<MODE>(v, P.cutoff) ? 1u : 0u;
+		if (x < len) {  // ragged last round, predicated: still all of its loads in flight at once
+			double v[7];
+#pragma unroll
+			for (int q = 0; q < 7; ++q) v[q] = x + q * G < len ? __ldcs(p + x + q * G) : CUDART_NAN;
+			if (x == 0) first_nan = v[0] != v[0];
+#pragma unroll
+			for (int q = 0; q < 7; ++q) {
+				if (x + q * G < len) {
+					x_take(a, x_key<MODE>(v[q]), v[q], st + x + q * G);
+					a.nbig += x_big<MODE>(v[q], P.cutoff) ? 1u : 0u;
+				}
+			}
 		}
 #pragma unroll
 		for (int m = G >> 1; m > 0; m >>= 1) {
@@ -573,12 +583,18 @@ int x_run(const XDev& P, uint64_t nsite, uint64_t nunit, const double* score, co
           const pgt_xwindows& out, cudaStream_t st) {
 	if (nsite) {
 		XProf prof(2, st);
-		// lanes per unit from the mean unit length: short windows get narrow groups
+		// lanes per unit from the mean unit length: short windows get narrow groups, so that every
+		// lane still streams several rounds of 8 loads per unit
 		const uint64_t mean = nunit ? nsite / nunit : 0;
-		if (mean >= 128) x_launch_units<MODE, 32>(P, nsite, score, part, st);
-		else if (mean >= 32) x_launch_units<MODE, 8>(P, nsite, score, part, st);
-		else if (mean >= 8) x_launch_units<MODE, 2>(P, nsite, score, part, st);
-		else x_launch_units<MODE, 1>(P, nsite, score, part, st);
+		// measured on B200 (profiles/r01c_extreme_xgroup_sweep.txt): best at ~32-64 sites per lane
+		int g = mean >= 1024 ? 32 : (mean >= 512 ? 16 : (mean >= 160 ? 8 : 4));
+		if (g_tune_xgroup >= 4) g = g_tune_xgroup;
+		switch (g) {
+			case 32: x_launch_units<MODE, 32>(P, nsite, score, part, st); break;
+			case 16: x_launch_units<MODE, 16>(P, nsite, score, part, st); break;
+			case 8: x_launch_units<MODE, 8>(P, nsite, score, part, st); break;
+			default: x_launch_units<MODE, 4>(P, nsite, score, part, st); break;
+		}
 		PGT_CUDA(cudaGetLastError());
 	}
 	if (P.nw) {

@@ -168,7 +168,8 @@ extern "C" int pgt_profile_read_extreme(double* units_ms, uint64_t* units_launch
 static int g_tune_level1 = 0;
 static int g_tune_level2 = 0;
 static int g_tune_stages = 2;      // tiled kernel: shared-memory stages (2..4)
-static int g_tune_stage_kb = 110;  // tiled kernel: bytes per stage (stages * stage_kb <= 224)
+static int g_tune_stage_kb = 110;
+extern int g_tune_xgroup;         // extreme scan (pgt_extreme.cu): lanes per unit, 0 = auto  // tiled kernel: bytes per stage (stages * stage_kb <= 224)
 
 static int num_sms() {
 	int dev = 0, n = 0;
@@ -1248,6 +1249,7 @@ extern "C" int pgt_tune(const char* key, int value) {
 	else if (key && strcmp(key, "level2") == 0 && value >= 0 && value <= 2) g_tune_level2 = value;
 	else if (key && strcmp(key, "stages") == 0 && value >= 2 && value <= kTileMaxStages) g_tune_stages = value;
 	else if (key && strcmp(key, "stage_kb") == 0 && value >= 8 && value <= 110) g_tune_stage_kb = value;
+	else if (key && strcmp(key, "xgroup") == 0 && (value == 0 || value == 4 || value == 8 || value == 16 || value == 32)) g_tune_xgroup = value;
 	else return pgt_set_error(PGT_ERR_ARGS, "pgt_tune: unknown key");
 	return PGT_OK;
 }

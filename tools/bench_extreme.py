@@ -30,6 +30,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--cpu-sites", type=float, default=2e6)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--xgroup", default="0", help="comma list of forced lanes-per-unit values (0 = auto)")
     a = ap.parse_args()
     import numpy as np
     import torch
@@ -44,7 +46,8 @@ def main():
     torch.cuda.synchronize()
     pos_h = pos_d.cpu().numpy()
     peak, peak_src = bench.hbm_peak()
-    for W in [int(x) for x in a.winsize.split(",")]:
+    for W, xg in [(int(x), int(g)) for x in a.winsize.split(",") for g in a.xgroup.split(",")]:
+        pgt.tune("xgroup", xg)
         t0 = time.perf_counter()
         plan = pgt.ExtremePlan(pos_h, offs, W)
         plan_s = time.perf_counter() - t0
@@ -71,7 +74,7 @@ def main():
                 "unit": "sites/s", "n_gpus": 1, "steps": a.steps, "warmup": a.warmup, "ms_per_step": round(ms, 4),
                 "dtype": "f64", "data": "synthetic",
                 "config": {"workload": f"ihsWindow, {n} synthetic sites over 24 chromosomes (1 SNP per {a.density} bp), {W}-bp windows, cutoff 2",
-                           "windows": plan.num_windows, "units": plan.num_units, "unit_sites": 2048,
+                           "windows": plan.num_windows, "units": plan.num_units, "unit_sites": 2048, "xgroup": xg,
                            "l2": "8 GB score column >> 126 MB L2; no flush needed"},
                 "gpu_launches": pgt.kernel_launch_count() - l0,
                 "host_bookkeeping_s": round(plan_s, 3),
@@ -81,6 +84,8 @@ def main():
                              "kernel_ms_per_launch": round(l1_ms, 4), "level2_ms_per_launch": round(l2_ms, 4)}}
         # e2e: host columns through the C ABI (H2D of the score column + D2H of the rows inside the timed region)
         try:
+            if a.no_e2e:
+                raise RuntimeError('skipped (--no-e2e)')
             hs = torch.empty(n, dtype=torch.float64, pin_memory=True)
             hs.copy_(score_d)
             torch.cuda.synchronize()
