@@ -94,6 +94,28 @@ def cli_arm(tmp, jobs, W, S):
         t["wall_s_incl_process_and_cuda_startup"] = round(wall, 3)
         best = t
     best["sites_per_s_parse_scan_format"] = round(best["sites"] / (best["total_ms"] * 1e-3), 1)
+    # the same input as a binary columnar cache (PGT_PACK, csrc/tools/pgt_colfile.h): no text parsing at all
+    try:
+        cache = os.path.join(tmp, "all.pgtc")
+        t0 = time.perf_counter()
+        subprocess.run([exe, allp, str(W), str(S)], check=True, env=dict(os.environ, PGT_PACK=cache))
+        pack_s = time.perf_counter() - t0
+        cache_out = os.path.join(tmp, "cache.tsv")
+        ct = None
+        for _ in range(2):
+            t0 = time.perf_counter()
+            with open(cache_out, "wb") as fo:
+                p = subprocess.run([exe, cache, str(W), str(S)], stdout=fo, stderr=subprocess.PIPE, text=True,
+                                   env=dict(os.environ, PGT_TIMING="1"), check=True)
+            cwall = time.perf_counter() - t0
+            ct = json.loads(p.stderr.strip().splitlines()[-1])
+        best["columnar_cache"] = {"pack_s": round(pack_s, 3), "file_bytes": os.path.getsize(cache), "load_ms": ct["parse_ms"],
+                                  "scan_ms": ct["scan_ms"], "format_ms": ct["format_ms"], "total_ms": ct["total_ms"],
+                                  "wall_s_incl_process_and_cuda_startup": round(cwall, 3),
+                                  "identical_stdout": open(cache_out, "rb").read() == open(ours_out, "rb").read()}
+        os.remove(cache)
+    except Exception as ex:
+        best["columnar_cache"] = {"error": repr(ex)[:200]}
     # the same file through the unmodified reference binary, one process (how a user runs it), and a
     # row-by-row comparison of the two outputs (text after %g formatting)
     sys.path.insert(0, os.path.join(ROOT, "tests"))

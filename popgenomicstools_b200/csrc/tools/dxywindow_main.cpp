@@ -17,9 +17,13 @@
 //   * bp mode needs positions strictly increasing within a chromosome and <= its sizefile
 //     length (the reference silently produces misplaced entries otherwise): error, exit 255.
 //   * MAF files without data lines: error instead of reading an empty record.
+// Binary columnar cache (pgt_colfile.h): PGT_PACK=<pop1.pgtc> PGT_PACK2=<pop2.pgtc> parse the two MAFs,
+// write one cache per population and exit without touching the GPU; a `.pgtc` file given in place of
+// a MAF (magic sniff, next to the gzip sniff of dxyWindow.cpp:82-83) skips the parsing of that file.
 #include <map>
 
 #include "pgt_cli.h"
+#include "pgt_colfile.h"
 
 using namespace pgtcli;
 
@@ -96,6 +100,24 @@ static int load_maf(const char* path, Maf* m, const char* which, Input* keep) {
 }
 
 static int parse_maf(const Input& in, Maf* m, const char* path) {
+	if (pgtcol::is_colfile(in.data, in.size)) {  // cached columns of one population
+		pgtcol::View v;
+		std::string err;
+		if (pgtcol::open_view(in.data, in.size, &v, &err) != 0 || v.kind != pgtcol::KIND_MAF) {
+			fprintf(stderr, "dxyWindow: %s: %s\n", path, err.empty() ? "columnar file of another tool" : err.c_str());
+			return -1;
+		}
+		const uint64_t n = v.nsites;
+		m->pos.assign((const uint32_t*)v.col[0], (const uint32_t*)v.col[0] + n);
+		m->freq.assign((const double*)v.col[1], (const double*)v.col[1] + n);
+		m->nind.assign((const int32_t*)v.col[2], (const int32_t*)v.col[2] + n);
+		m->chr.reserve(n);
+		for (const ContigRun& r : v.runs) {
+			m->names.push_back(r.name);
+			m->chr.insert(m->chr.end(), r.count, (uint32_t)m->names.size() - 1);
+		}
+		return 0;
+	}
 	// skip the header line (dxyWindow.cpp:284), stop at the first empty line (:313)
 	const char* nl = (const char*)memchr(in.data, '\n', in.size);
 	size_t begin = nl ? (size_t)(nl + 1 - in.data) : in.size;
@@ -257,9 +279,29 @@ int main(int argc, char** argv) {
 	}
 
 	DeviceWarmup warm;
-	warm.start();
+	const char* pack1 = getenv("PGT_PACK");
+	const char* pack2 = getenv("PGT_PACK2");
+	if (!pack1 && !pack2) warm.start();
 	if (parse_maf(in1, &m1, argv[argc - 2]) != 0) return -1;
 	if (parse_maf(in2, &m2, argv[argc - 1]) != 0) return -1;
+	if (pack1 || pack2) {  // write the binary columnar caches and stop: no GPU involved
+		auto pack = [&](const char* path, const Maf& m) -> int {
+			std::vector<ContigRun> runs;
+			for (uint64_t i = 0; i < m.pos.size(); ++i) {
+				if (runs.empty() || m.chr[i] != m.chr[i - 1]) runs.push_back(ContigRun{m.names[m.chr[i]], 0});
+				runs.back().count++;
+			}
+			const void* cols[3] = {m.pos.data(), m.freq.data(), m.nind.data()};
+			if (pgtcol::write_file(path, pgtcol::KIND_MAF, runs, m.pos.size(), cols) != 0) {
+				fprintf(stderr, "dxyWindow: cannot write %s\n", path);
+				return -1;
+			}
+			return 0;
+		};
+		if (pack1 && pack(pack1, m1) != 0) return -1;
+		if (pack2 && pack(pack2, m2) != 0) return -1;
+		return 0;
+	}
 	const uint64_t n1 = m1.pos.size(), n2 = m2.pos.size();
 	if (n1 == 0 || n2 == 0) {
 		fprintf(stderr, "dxyWindow: MAF file without data lines\n");

@@ -19,11 +19,14 @@
 //   * a flag without a value (`-winsize` as last argument): the reference dereferences argv[argc]; here error;
 //   * more than 6 (iHS) / 8 (XP-EHH) numeric fields after the position overflow the reference's vector;
 //     extra fields are ignored here.
+// Binary columnar cache (pgt_colfile.h): PGT_PACK=<out.pgtc> parses, writes the cache and exits
+// without touching the GPU; a `.pgtc` file given as the input (magic sniff) skips the parsing.
 // PGT_TIMING=1 prints parse / scan / format milliseconds to stderr; PGT_DEVICE, PGT_THREADS as in the other tools.
 #include <map>
 
 #include "../../../include/pgt_extreme.h"
 #include "pgt_cli.h"
+#include "pgt_colfile.h"
 
 using namespace pgtcli;
 
@@ -196,10 +199,20 @@ int main(int argc, char** argv) {
 	// ---- parse (timed separately from compute) --------------------------------------------
 	Timing tm;
 	DeviceWarmup warm;
-	warm.start();
+	const char* pack_path = getenv("PGT_PACK");
+	if (!pack_path) warm.start();
+	pgtcol::View view;
+	const bool columnar = pgtcol::is_colfile(in.data, in.size);
+	if (columnar) {
+		std::string err;
+		if (pgtcol::open_view(in.data, in.size, &view, &err) != 0 || view.kind != pgtcol::KIND_SCORE) {
+			fprintf(stderr, "%s: %s: %s\n", kTool, argv[1], err.empty() ? "columnar file of another tool" : err.c_str());
+			return -1;
+		}
+	}
 	size_t begin = 0;
 #if defined(PGT_TOOL_XPEHH)
-	{  // skip header (xpehhWindow.cpp:110-115)
+	if (!columnar) {  // skip header (xpehhWindow.cpp:110-115)
 		const char* nl = in.size ? (const char*)memchr(in.data, '\n', in.size) : nullptr;
 		if (!nl) {
 			fprintf(stderr, "Input XPEHH file had zero sites\n");
@@ -208,9 +221,10 @@ int main(int argc, char** argv) {
 		begin = (size_t)(nl + 1 - in.data);
 	}
 #endif
-	const unsigned nt = (in.size - begin) < (1u << 20) ? 1 : parse_threads();
+	const size_t text_end = columnar ? begin : in.size;  // columnar input: nothing to parse
+	const unsigned nt = (text_end - begin) < (1u << 20) ? 1 : parse_threads();
 	tm.threads = nt;
-	std::vector<size_t> starts = chunk_starts(in.data, begin, in.size, nt);
+	std::vector<size_t> starts = chunk_starts(in.data, begin, text_end, nt);
 	std::vector<Chunk> chunks(starts.size() - 1);
 	for (size_t i = 0; i + 1 < starts.size(); ++i) {
 		chunks[i].begin = starts[i];
@@ -238,8 +252,9 @@ int main(int argc, char** argv) {
 		c.row0 = n;
 		n += c.nlines;
 	}
-	uint32_t* pos = (uint32_t*)malloc(std::max<uint64_t>(n, 1) * sizeof(uint32_t));
-	double* score = (double*)malloc(std::max<uint64_t>(n, 1) * sizeof(double));
+	if (columnar) n = view.nsites;
+	uint32_t* pos = columnar ? (uint32_t*)view.col[0] : (uint32_t*)malloc(std::max<uint64_t>(n, 1) * sizeof(uint32_t));
+	double* score = columnar ? (double*)view.col[1] : (double*)malloc(std::max<uint64_t>(n, 1) * sizeof(double));
 	if (!pos || !score) {
 		fprintf(stderr, "%s: out of memory for %llu sites\n", kTool, (unsigned long long)n);
 		return -1;
@@ -323,6 +338,7 @@ int main(int argc, char** argv) {
 	}
 	// rows at a chunk head that repeat the previous chunk's last row (sequential, rare)
 	std::vector<ContigRun> runs;
+	if (columnar) runs = view.runs;
 	for (Chunk& c : chunks) {
 		for (auto& fx : c.head_fix) {
 			const uint64_t r = fx.first;
@@ -342,6 +358,16 @@ int main(int argc, char** argv) {
 	}
 	tm.sites = n;
 	tm.parse_ms = now_ms() - t_start;
+	if (pack_path) {  // write the binary columnar cache and stop: no GPU involved
+		const void* cols[2] = {pos, score};
+		if (pgtcol::write_file(pack_path, pgtcol::KIND_SCORE, runs, n, cols) != 0) {
+			fprintf(stderr, "%s: cannot write %s\n", kTool, pack_path);
+			return -1;
+		}
+		tm.total_ms = now_ms() - t_start;
+		tm.report(kTool);
+		return 0;
+	}
 	static char obuf[1 << 20];
 	setvbuf(stdout, obuf, _IOFBF, sizeof(obuf));
 	if (n == 0) {

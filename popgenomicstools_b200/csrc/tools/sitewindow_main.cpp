@@ -12,11 +12,14 @@
 //   * step size > window size: the reference segfaults; we print an error and exit 255.
 //   * a line that does not parse: the reference silently reuses stale values; we report it.
 //   * the input file is opened read-only (the reference needs write permission, fstWindow.cpp:45).
+// Binary columnar cache (pgt_colfile.h): PGT_PACK=<out.pgtc> parses the text, writes the cache and
+// exits without touching the GPU; a `.pgtc` file given as the input (magic sniff) skips the parsing.
 // Set PGT_TIMING=1 for a JSON timing line on stderr (parse / scan / format, opt-in so stderr
 // stays byte-identical by default); PGT_DEVICE selects the GPU, PGT_THREADS the parser threads.
 #include <atomic>
 
 #include "pgt_cli.h"
+#include "pgt_colfile.h"
 
 using namespace pgtcli;
 
@@ -85,8 +88,23 @@ int main(int argc, char** argv) {
 	// ---- parse (timed separately from compute) --------------------------------------------
 	Timing tm;
 	DeviceWarmup warm;
-	warm.start();
-	const size_t n_eff = effective_size(in.data, in.size);
+	const char* pack_path = getenv("PGT_PACK");
+	if (!pack_path) warm.start();
+#if defined(PGT_TOOL_FST)
+	const uint32_t want_kind = pgtcol::KIND_FST;
+#else
+	const uint32_t want_kind = pgtcol::KIND_HET;
+#endif
+	pgtcol::View view;
+	const bool columnar = pgtcol::is_colfile(in.data, in.size);
+	if (columnar) {
+		std::string err;
+		if (pgtcol::open_view(in.data, in.size, &view, &err) != 0 || view.kind != want_kind) {
+			fprintf(stderr, "%s: %s: %s\n", kTool, argv[1], err.empty() ? "columnar file of another tool" : err.c_str());
+			return -1;
+		}
+	}
+	const size_t n_eff = columnar ? 0 : effective_size(in.data, in.size);
 	const unsigned nt = n_eff < (1u << 20) ? 1 : parse_threads();
 	tm.threads = nt;
 	std::vector<size_t> starts = chunk_starts(in.data, 0, n_eff, nt);
@@ -117,13 +135,15 @@ int main(int argc, char** argv) {
 		c.row0 = n;
 		n += c.nlines;
 	}
-	uint32_t* pos = (uint32_t*)malloc(std::max<uint64_t>(n, 1) * sizeof(uint32_t));
+	if (columnar) n = view.nsites;
+	// columnar input: the columns are the file mapping itself (read-only from here on)
+	uint32_t* pos = columnar ? (uint32_t*)view.col[0] : (uint32_t*)malloc(std::max<uint64_t>(n, 1) * sizeof(uint32_t));
 #if defined(PGT_TOOL_FST)
-	double* col_a = (double*)malloc(std::max<uint64_t>(n, 1) * sizeof(double));
-	double* col_b = (double*)malloc(std::max<uint64_t>(n, 1) * sizeof(double));
+	double* col_a = columnar ? (double*)view.col[1] : (double*)malloc(std::max<uint64_t>(n, 1) * sizeof(double));
+	double* col_b = columnar ? (double*)view.col[2] : (double*)malloc(std::max<uint64_t>(n, 1) * sizeof(double));
 	if (!pos || !col_a || !col_b) {
 #else
-	int8_t* geno = (int8_t*)malloc(std::max<uint64_t>(n, 1));
+	int8_t* geno = columnar ? (int8_t*)view.col[1] : (int8_t*)malloc(std::max<uint64_t>(n, 1));
 	if (!pos || !geno) {
 #endif
 		fprintf(stderr, "%s: out of memory for %llu sites\n", kTool, (unsigned long long)n);
@@ -172,6 +192,7 @@ int main(int argc, char** argv) {
 		for (auto& x : th) x.join();
 	}
 	std::vector<ContigRun> runs;
+	if (columnar) runs = view.runs;
 	for (Chunk& c : chunks) {
 		if (c.bad_line >= 0) {
 			fprintf(stderr, "%s: cannot parse line %llu of %s\n", kTool, (unsigned long long)(c.row0 + c.bad_line + 1), argv[1]);
@@ -181,6 +202,20 @@ int main(int argc, char** argv) {
 	}
 	tm.sites = n;
 	tm.parse_ms = now_ms() - t_start;
+	if (pack_path) {  // write the binary columnar cache and stop: no GPU involved
+#if defined(PGT_TOOL_FST)
+		const void* cols[3] = {pos, col_a, col_b};
+#else
+		const void* cols[2] = {pos, geno};
+#endif
+		if (pgtcol::write_file(pack_path, want_kind, runs, n, cols) != 0) {
+			fprintf(stderr, "%s: cannot write %s\n", kTool, pack_path);
+			return -1;
+		}
+		tm.total_ms = now_ms() - t_start;
+		tm.report(kTool);
+		return 0;
+	}
 	if (n == 0) {
 		tm.total_ms = now_ms() - t_start;
 		tm.report(kTool);

@@ -157,3 +157,39 @@ def test_timing_report_is_opt_in(tmp_path):
     t = json.loads(err)
     assert out2 == out and t["sites"] == 5000 and t["windows"] == len(out.splitlines())
     assert {"parse_ms", "scan_ms", "format_ms"} <= set(t)
+
+
+def test_columnar_cache_gives_the_same_rows_as_the_text(tmp_path):
+    """PGT_PACK -> .pgtc -> the tool on the cache prints byte for byte what it prints on the text
+    (fst, het, dxy in both window modes, ihs, xpehh)."""
+    names = ["chr1", "chr2", "chr3"]
+    offs = np.array([0, 120000, 170000, 171000], np.uint64)
+    d = str(tmp_path)
+    for kind, tool, args in (("fst", "fstWindow", [5000, 1000]), ("het", "hetWindow", [4096, 512])):
+        O.write_text(kind, os.path.join(d, f"s.{kind}"), names, offs, seed=2, density=3)
+        assert U.run(U.ours(tool), [f"s.{kind}"] + args, cwd=d, env={"PGT_PACK": os.path.join(d, f"s.{kind}.pgtc")})[0] == 0
+        t = U.run(U.ours(tool), [f"s.{kind}"] + args, cwd=d)
+        c = U.run(U.ours(tool), [f"s.{kind}.pgtc"] + args, cwd=d)
+        assert t[0] == 0 and len(t[1].splitlines()) > 100 and c == t, tool
+    for pop in (1, 2):
+        O.write_text("maf", os.path.join(d, f"p{pop}.mafs"), names, offs, seed=2, density=3, pop=pop)
+    chr_len = [int(offs[i + 1] - offs[i]) * 3 + 5 for i in range(3)]
+    open(os.path.join(d, "sizes.txt"), "w").write(T.sizes_text(names, chr_len))
+    assert U.run(U.ours("dxyWindow"), ["-fixedsite", 1, "p1.mafs", "p2.mafs"], cwd=d,
+                 env={"PGT_PACK": os.path.join(d, "p1.pgtc"), "PGT_PACK2": os.path.join(d, "p2.pgtc")})[0] == 0
+    for opts in (["-winsize", 2000, "-stepsize", 500, "-minind", 5, "-fixedsite", 1],
+                 ["-winsize", 20000, "-stepsize", 5000, "-minind", 5, "-sizefile", "sizes.txt"]):
+        t = U.run(U.ours("dxyWindow"), opts + ["p1.mafs", "p2.mafs"], cwd=d)
+        c = U.run(U.ours("dxyWindow"), opts + ["p1.pgtc", "p2.pgtc"], cwd=d)
+        m = U.run(U.ours("dxyWindow"), opts + ["p1.pgtc", "p2.mafs"], cwd=d)  # cache and text can be mixed
+        assert t[0] == 0 and len(t[1].splitlines()) > 50 and c == t and m == t, opts
+    lengths = np.diff(offs).astype(int).tolist()
+    pos = O.synth_pos(2, offs, 40)
+    v = np.round(O.synth_score(2, 0, int(offs[-1])) * 1e6).astype(np.int64)
+    open(os.path.join(d, "i.norm"), "w").write(T.ihs_text(names, lengths, pos, v))
+    open(os.path.join(d, "x.norm"), "w").write(T.xpehh_text(names, lengths, pos, v))
+    for tool, f, args in (("ihsWindow", "i", ["-winsize", 50000]), ("xpehhWindow", "x", [-1.5, "-winsize", 50000])):
+        assert U.run(U.ours(tool), [f"{f}.norm"] + args, cwd=d, env={"PGT_PACK": os.path.join(d, f"{f}.pgtc")})[0] == 0
+        t = U.run(U.ours(tool), [f"{f}.norm"] + args, cwd=d)
+        c = U.run(U.ours(tool), [f"{f}.pgtc"] + args, cwd=d)
+        assert t[0] == 0 and len(t[1].splitlines()) > 50 and c == t, tool

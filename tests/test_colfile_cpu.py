@@ -1,0 +1,125 @@
+"""Binary columnar cache (.pgtc): the CLIs' text parsers -> PGT_PACK -> file -> numpy reader.  Runs
+without a GPU (packing never touches the device), so this is also the CPU-side test of the
+multi-threaded text parsers: every parsed value is compared with the generator's exact value."""
+import gzip
+import os
+
+import numpy as np
+import pytest
+
+import cli_util as U
+import oracle_lib as O
+import textfmt as T
+from popgenomicstools_b200 import colfile
+
+
+def pack(tool, args, out, cwd, out2=None, threads=None):
+    env = {"PGT_PACK": str(out)}
+    if out2:
+        env["PGT_PACK2"] = str(out2)
+    if threads:
+        env["PGT_THREADS"] = str(threads)
+    rc, so, se = U.run(U.ours(tool), args, cwd=str(cwd), env=env)
+    assert (rc, so, se) == (0, "", ""), (tool, args, se)
+
+
+def test_roundtrip_python_writer_reader(tmp_path):
+    runs = [("chr1", 5), ("scaffold_2", 3), ("chr1", 2)]
+    cols = dict(pos=np.arange(10, dtype=np.uint32), a=np.linspace(-1, 1, 10), b=np.arange(10) / 7.0)
+    p = tmp_path / "x.pgtc"
+    colfile.write(p, "fst", runs, cols)
+    r = colfile.read(p)
+    assert r["kind"] == "fst" and r["runs"] == runs and r["nsites"] == 10
+    assert list(r["offsets"]) == [0, 5, 8, 10]
+    for k in cols:
+        assert np.array_equal(r["columns"][k], cols[k])
+    assert os.path.getsize(p) % 4096 == 0
+    with pytest.raises(ValueError):
+        (tmp_path / "bad").write_bytes(b"chr1 1 0.1 0.2\n" * 10)
+        colfile.read(tmp_path / "bad")
+
+
+@pytest.mark.parametrize("threads", [1, 5])
+def test_fst_and_het_text_parsers(tmp_path, threads):
+    names = ["chr1", "chr2", "chrUn_3"]
+    offs = np.array([0, 70000, 100000, 100003], np.uint64)
+    n = int(offs[-1])
+    for kind, tool in (("fst", "fstWindow"), ("het", "hetWindow")):
+        txt = tmp_path / f"s.{kind}"
+        O.write_text(kind, str(txt), names, offs, seed=3, density=7)
+        pack(tool, [txt.name, 100, 50], tmp_path / f"s.{kind}.pgtc", tmp_path, threads=threads)
+        r = colfile.read(tmp_path / f"s.{kind}.pgtc")
+        assert r["kind"] == kind and r["runs"] == list(zip(names, np.diff(offs).astype(int).tolist()))
+        assert np.array_equal(r["columns"]["pos"], O.synth_pos(3, offs, 7))
+        if kind == "fst":
+            a, b = O.synth_fst(3, 0, n)
+            assert np.array_equal(r["columns"]["a"], a) and np.array_equal(r["columns"]["b"], b)
+        else:
+            assert np.array_equal(r["columns"]["geno"], O.synth_het(3, 0, n))
+
+
+def test_parser_edge_cases(tmp_path):
+    """Whitespace mix, CRLF, signs, exponents, the first empty line ends the input
+    (/root/reference/fstWindow.cpp:125), genotypes outside int8 are clamped."""
+    (tmp_path / "e.fst").write_text("A 1 0.5 1e-3\nA\t2\t-0.25\t+2\r\nB  3   1.5e2  0.000001\n\nC 9 9 9\n")
+    pack("fstWindow", ["e.fst"], tmp_path / "e.pgtc", tmp_path)
+    r = colfile.read(tmp_path / "e.pgtc")
+    assert r["runs"] == [("A", 2), ("B", 1)]
+    assert r["columns"]["pos"].tolist() == [1, 2, 3]
+    assert r["columns"]["a"].tolist() == [0.5, -0.25, 150.0] and r["columns"]["b"].tolist() == [1e-3, 2.0, 1e-6]
+    (tmp_path / "e.het").write_text("A 1 0\nA 2 -5\nA 3 1\nA 4 300\nA 5 2\n")
+    pack("hetWindow", ["e.het"], tmp_path / "eh.pgtc", tmp_path)
+    assert colfile.read(tmp_path / "eh.pgtc")["columns"]["geno"].tolist() == [0, -1, 1, 127, 2]
+    # malformed line: reported, nothing written
+    (tmp_path / "bad.fst").write_text("A 1 0.5 0.1\nA x 0.5 0.1\n")
+    rc, so, se = U.run(U.ours("fstWindow"), ["bad.fst"], cwd=str(tmp_path), env={"PGT_PACK": str(tmp_path / "bad.pgtc")})
+    assert rc == 255 and "cannot parse line 2" in se and not (tmp_path / "bad.pgtc").exists()
+
+
+def test_maf_parser_plain_and_gzip(tmp_path):
+    names, lengths = ["chr1", "chr2"], [4000, 2500]
+    rng = np.random.default_rng(1)
+    pos = np.concatenate([np.cumsum(rng.integers(1, 9, size=L)) for L in lengths])
+    f1, f2 = rng.integers(0, 1000001, size=6500), rng.integers(0, 1000001, size=6500)
+    n1, n2 = rng.integers(0, 30, size=6500), rng.integers(0, 30, size=6500)
+    (tmp_path / "p1.mafs").write_text(T.maf_text(names, lengths, pos, f1, n1))
+    with gzip.open(tmp_path / "p2.mafs.gz", "wt") as f:
+        f.write(T.maf_text(names, lengths, pos, f2, n2))
+    pack("dxyWindow", ["-winsize", 10, "-stepsize", 5, "-fixedsite", 1, "p1.mafs", "p2.mafs.gz"], tmp_path / "p1.pgtc", tmp_path,
+         out2=tmp_path / "p2.pgtc")
+    for path, f, nn in ((tmp_path / "p1.pgtc", f1, n1), (tmp_path / "p2.pgtc", f2, n2)):
+        r = colfile.read(path)
+        assert r["kind"] == "maf" and r["runs"] == list(zip(names, lengths))
+        assert np.array_equal(r["columns"]["pos"], pos)
+        assert np.array_equal(r["columns"]["freq"], T.micro_to_f64(f))
+        assert np.array_equal(r["columns"]["nind"], nn)
+
+
+def test_norm_parsers(tmp_path):
+    names, lengths = ["chr1", "chr22"], [3000, 1200]
+    rng = np.random.default_rng(2)
+    pos = np.concatenate([np.cumsum(rng.integers(1, 500, size=L)) for L in lengths])
+    v = rng.integers(-4000000, 4000001, size=4200)
+    (tmp_path / "i.norm").write_text(T.ihs_text(names, lengths, pos, v) + "\n")  # trailing blank line repeats the last site
+    (tmp_path / "x.norm").write_text(T.xpehh_text(names, lengths, pos, v))
+    pack("ihsWindow", ["i.norm"], tmp_path / "i.pgtc", tmp_path)
+    pack("xpehhWindow", ["x.norm", 2], tmp_path / "x.pgtc", tmp_path)
+    ri, rx = colfile.read(tmp_path / "i.pgtc"), colfile.read(tmp_path / "x.pgtc")
+    assert ri["kind"] == rx["kind"] == "score"
+    assert rx["runs"] == list(zip(names, lengths)) and ri["runs"] == [("chr1", 3000), ("chr22", 1201)]
+    assert np.array_equal(rx["columns"]["pos"], pos) and np.array_equal(rx["columns"]["score"], T.micro_to_f64(v))
+    assert np.array_equal(ri["columns"]["pos"], np.append(pos, pos[-1]))
+    assert np.array_equal(ri["columns"]["score"], np.append(T.micro_to_f64(v), v[-1] / 1e6))
+
+
+def test_wrong_kind_and_corrupt_files_are_refused(tmp_path):
+    colfile.write(tmp_path / "h.pgtc", "het", [("A", 3)], dict(pos=[1, 2, 3], geno=[0, 1, 2]))
+    rc, so, se = U.run(U.ours("fstWindow"), ["h.pgtc", 2, 1], cwd=str(tmp_path), env={"PGT_PACK": str(tmp_path / "o.pgtc")})
+    assert rc == 255 and "columnar file of another tool" in se
+    blob = (tmp_path / "h.pgtc").read_bytes()
+    (tmp_path / "t.pgtc").write_bytes(blob[:4096 + 8])  # truncated column block
+    rc, so, se = U.run(U.ours("hetWindow"), ["t.pgtc", 2, 1], cwd=str(tmp_path), env={"PGT_PACK": str(tmp_path / "o.pgtc")})
+    assert rc == 255 and "truncated" in se
+    # re-packing a columnar file reproduces it byte for byte
+    rc, so, se = U.run(U.ours("hetWindow"), ["h.pgtc"], cwd=str(tmp_path), env={"PGT_PACK": str(tmp_path / "h2.pgtc")})
+    assert rc == 0 and (tmp_path / "h2.pgtc").read_bytes() == blob
