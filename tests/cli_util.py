@@ -7,6 +7,9 @@ BIN = os.path.join(ROOT, "popgenomicstools_b200", "bin")
 
 
 def ours(tool):
+    alt = os.environ.get("PGT_TEST_BIN")  # e.g. an ASan/UBSan build of the CLIs (make -C csrc asan)
+    if alt:
+        return os.path.join(alt, tool)
     p = os.path.join(BIN, tool)
     if not os.access(p, os.X_OK):
         subprocess.run(["make", "-s", "-C", os.path.join(ROOT, "popgenomicstools_b200", "csrc")], check=True)
