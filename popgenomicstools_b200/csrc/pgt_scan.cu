@@ -164,8 +164,7 @@ extern "C" int pgt_profile_read_extreme(double* units_ms, uint64_t* units_launch
 
 // tuning knobs (tests / experiments, pgt_tune):
 //   level1: 0 auto, 1 force the direct kernel (k_units; only valid when pgt_geom.gw == 32), 2 force the tiled kernel
-//   level2: 0 auto, 1 force warp-per-window, 2 force scan mode (k_block_scan + k_windows_hgw),
-//           3 thread-per-window straight from global memory (no shared-memory tile)
+//   level2: 0 auto, 1 force warp-per-window, 2 force scan mode (k_block_scan + k_windows_hgw)
 static int g_tune_level1 = 0;
 static int g_tune_level2 = 0;
 static int g_tune_stages = 2;      // tiled kernel: shared-memory stages (2..4)
@@ -905,69 +904,6 @@ __global__ void __launch_bounds__(256) k_windows_small(DevPlan P, const typename
 	}
 }
 
-// Overlapping fine windows (q = W div S >= 2, <= 32 units each): consecutive windows share most of
-// their unit partials, so a CTA takes a run of consecutive windows, stages the union of their
-// partials in shared memory once (coalesced) and every thread evaluates the same tree as
-// k_windows_small from there.  Cuts the L2 traffic of level 2 by ~q; values are bit-identical.
-static constexpr uint32_t kWinTileThreads = 256;
-template <class Stat>
-struct WinTile {
-	static constexpr uint32_t kCap = 40u * 1024u / sizeof(typename Stat::Acc);  // partials per CTA tile (static shared memory)
-};
-
-template <class Stat, int P2>
-__global__ void __launch_bounds__(kWinTileThreads) k_windows_small_sm(DevPlan P, const typename Stat::Acc* __restrict__ units, uint64_t units_base,
-                                                                       const uint32_t* __restrict__ pos, pgt_windows out, uint32_t wpc) {
-	using Acc = typename Stat::Acc;
-	__shared__ __align__(16) unsigned char sm_raw[WinTile<Stat>::kCap * sizeof(Acc)];
-	__shared__ uint64_t sm_lo, sm_hi;
-	Acc* sm = reinterpret_cast<Acc*>(sm_raw);
-	const uint64_t nwin = P.win_hi - P.win_lo;
-	const uint64_t nchunk = (nwin + wpc - 1) / wpc;
-	uint32_t si = 0xffffffffu;
-	pgt_seg sg;
-	sg.win_base = 0;
-	sg.nwin = 0;
-	for (uint64_t c = blockIdx.x; c < nchunk; c += gridDim.x) {
-		const uint64_t w0 = P.win_lo + c * wpc;
-		const uint64_t w1 = w0 + wpc < P.win_hi ? w0 + wpc : P.win_hi;
-		if (threadIdx.x == 0) {  // global unit range [lo, hi) covered by windows w0 .. w1-1 (units grow with the window index)
-			const pgt_seg a = P.segs[find_seg<false>(P, w0)];
-			uint64_t fu;
-			pgt_window_units(P.g, a, w0 - a.win_base, &fu);
-			sm_lo = a.unit_base + fu;
-			const pgt_seg b = P.segs[find_seg<false>(P, w1 - 1)];
-			const uint64_t cnt = pgt_window_units(P.g, b, w1 - 1 - b.win_base, &fu);
-			sm_hi = b.unit_base + fu + cnt;
-		}
-		__syncthreads();
-		const uint64_t lo = sm_lo, hi = sm_hi;
-		const bool staged = hi - lo <= WinTile<Stat>::kCap;  // always, except across runs of window-less segments
-		if (staged) {
-			// copy as 8-byte words: coalesced whatever sizeof(Acc) is
-			const unsigned long long* src = reinterpret_cast<const unsigned long long*>(units + (lo - units_base));
-			unsigned long long* dst = reinterpret_cast<unsigned long long*>(sm);
-			const uint32_t nw8 = (uint32_t)((hi - lo) * (sizeof(Acc) / 8));
-			for (uint32_t i = threadIdx.x; i < nw8; i += kWinTileThreads) dst[i] = src[i];
-		}
-		__syncthreads();
-		for (uint64_t w = w0 + threadIdx.x; w < w1; w += kWinTileThreads) {
-			if (si == 0xffffffffu || w - sg.win_base >= sg.nwin || w < sg.win_base) {
-				si = find_seg<false>(P, w);
-				sg = P.segs[si];
-			}
-			const uint64_t k = w - sg.win_base;
-			uint64_t fu;
-			const uint32_t cnt = (uint32_t)pgt_window_units(P.g, sg, k, &fu);
-			const uint64_t gu = sg.unit_base + fu;
-			const Acc* up = staged ? sm + (gu - lo) : units + (gu - units_base);
-			const Acc acc = SmallTree<Stat, P2, 1>::eval(up, 0u, cnt);
-			emit_window<Stat>(P, sg, w, k, acc, pos, out);
-		}
-		__syncthreads();
-	}
-}
-
 // W = S = 1 (the tools' default arguments): every window is one site, so the window table is an
 // elementwise map of the columns; level 1 is skipped and the per-site statistic is evaluated here.
 template <class Stat>
@@ -1310,7 +1246,7 @@ extern "C" size_t pgt_scan_workspace_bytes(const pgt_plan* plan, const pgt_range
 
 extern "C" int pgt_tune(const char* key, int value) {
 	if (key && strcmp(key, "level1") == 0) g_tune_level1 = value;
-	else if (key && strcmp(key, "level2") == 0 && value >= 0 && value <= 3) g_tune_level2 = value;
+	else if (key && strcmp(key, "level2") == 0 && value >= 0 && value <= 2) g_tune_level2 = value;
 	else if (key && strcmp(key, "stages") == 0 && value >= 2 && value <= kTileMaxStages) g_tune_stages = value;
 	else if (key && strcmp(key, "stage_kb") == 0 && value >= 8 && value <= 110) g_tune_stage_kb = value;
 	else if (key && strcmp(key, "xgroup") == 0 && (value == 0 || value == 4 || value == 8 || value == 16 || value == 32)) g_tune_xgroup = value;
@@ -1488,22 +1424,6 @@ static int launch_windows(const DevPlan& P, typename Stat::Acc* units, uint64_t 
 		g_launches++;
 		const uint64_t want = (nwin + 255) / 256;
 		k_windows_hgw<Stat><<<(unsigned)(want < cap ? want : cap), 256, 0, st>>>(P, units, pre, units_base, pos, out);
-	} else if (P.g.wunits <= 32 && g_tune_level2 != 1 && g_tune_level2 != 3 && P.g.q >= 2 &&
-	           (uint64_t)P.g.upp * 64u + P.g.wunits <= WinTile<Stat>::kCap) {
-		// overlapping fine windows: a thread per window, the partials of a run of windows staged in shared memory
-		void (*kern)(DevPlan, const typename Stat::Acc*, uint64_t, const uint32_t*, pgt_windows, uint32_t);
-		const uint32_t wu = P.g.wunits;
-		if (wu <= 2) kern = k_windows_small_sm<Stat, 2>;
-		else if (wu <= 4) kern = k_windows_small_sm<Stat, 4>;
-		else if (wu <= 8) kern = k_windows_small_sm<Stat, 8>;
-		else if (wu <= 16) kern = k_windows_small_sm<Stat, 16>;
-		else kern = k_windows_small_sm<Stat, 32>;
-		// windows per CTA tile: as many as fit the shared-memory tile, a multiple of the block size when possible
-		uint64_t wpc = (WinTile<Stat>::kCap - P.g.wunits) / P.g.upp;
-		if (wpc > 4 * kWinTileThreads) wpc = 4 * kWinTileThreads;
-		if (wpc >= kWinTileThreads) wpc = wpc / kWinTileThreads * kWinTileThreads;
-		const uint64_t want = (nwin + wpc - 1) / wpc;
-		kern<<<(unsigned)(want < cap ? want : cap), kWinTileThreads, 0, st>>>(P, units, units_base, pos, out, (uint32_t)wpc);
 	} else if (P.g.wunits <= 32 && g_tune_level2 != 1) {
 		// fine windows: a thread per window
 		void (*kern)(DevPlan, const typename Stat::Acc*, uint64_t, const uint32_t*, pgt_windows);

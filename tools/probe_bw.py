@@ -1,5 +1,5 @@
 """Scratch probe: level-1/level-2 timing at several (stat, n, W, S, unit, level1) points (not the bench).
-usage: probe_bw.py stat,n,W,S,unit,level1 ..."""
+usage: probe_bw.py stat,n,W,S,unit,level1[,stages,stage_kb[,level2]] ..."""
 import sys
 import numpy as np, torch
 sys.path.insert(0, ".")
@@ -14,6 +14,8 @@ for spec in sys.argv[1:]:
     stat, n, W, S, unit, l1 = f[:6]
     n, W, S, unit, l1 = int(float(n)), int(W), int(S), int(unit), int(l1)
     stages, skb = (int(f[6]), int(f[7])) if len(f) > 7 else (2, 110)
+    l2 = int(f[8]) if len(f) > 8 else 0
+    pgt.tune("level2", l2)
     pgt.tune("stages", stages); pgt.tune("stage_kb", skb)
     _, offs = human_like_contigs(n, S)
     plan = pgt.WindowPlan(offs, W, S, unit_sites=unit)
@@ -40,7 +42,7 @@ for spec in sys.argv[1:]:
     pr = pgt.profile_read(); pgt.profile(False)
     ms = ev[0].elapsed_time(ev[1]) / K
     l1ms = pr["units_ms"] / K; l2ms = pr["windows_ms"] / K
-    print(f"{stat} n={n:.3g} W={W} S={S} u={unit} l1={l1} st={stages}x{skb}KB win={plan.num_windows} units={plan.num_units} step_ms={ms:.4f} "
+    print(f"{stat} n={n:.3g} W={W} S={S} u={unit} l1={l1} l2={l2} st={stages}x{skb}KB win={plan.num_windows} units={plan.num_units} step_ms={ms:.4f} "
           f"L1_ms={l1ms:.4f} L2_ms={l2ms:.4f} sites/s={n/ms*1e3:.4g} L1_GB/s={BPS[stat]*n/max(l1ms,1e-9)/1e6:.1f}", flush=True)
     del cols, out, plan
     torch.cuda.empty_cache()
