@@ -736,12 +736,20 @@ __global__ void __launch_bounds__(256) k_units_het_vec(DevPlan P, const int8_t* 
 		uint32_t nonmissing = 0, nhet = 0;
 		if (A1 > A0) {
 			const uint32_t nch = (uint32_t)(A1 - A0) >> 4;
-			for (uint32_t c = lane; c < nch; c += 32u) {
-				const uint4 v = __ldg(reinterpret_cast<const uint4*>(A0) + c);
-				het_count_word(v.x, nonmissing, nhet);
-				het_count_word(v.y, nonmissing, nhet);
-				het_count_word(v.z, nonmissing, nhet);
-				het_count_word(v.w, nonmissing, nhet);
+			// 8 x 16 bytes in flight per lane (one 4096-site unit = one round); chunks past the end read
+			// as 0x80 bytes = missing genotypes, which count for nothing
+			const uint4 kMissing = make_uint4(0x80808080u, 0x80808080u, 0x80808080u, 0x80808080u);
+			for (uint32_t c0 = lane; c0 < nch; c0 += 256u) {
+				uint4 v[8];
+#pragma unroll
+				for (int q = 0; q < 8; ++q) v[q] = c0 + 32u * q < nch ? __ldg(reinterpret_cast<const uint4*>(A0) + c0 + 32u * q) : kMissing;
+#pragma unroll
+				for (int q = 0; q < 8; ++q) {
+					het_count_word(v[q].x, nonmissing, nhet);
+					het_count_word(v[q].y, nonmissing, nhet);
+					het_count_word(v[q].z, nonmissing, nhet);
+					het_count_word(v[q].w, nonmissing, nhet);
+				}
 			}
 			const uint32_t nh = (uint32_t)(A0 - A), nt = (uint32_t)(E - A1);  // < 16 each
 			if (lane < nh) {
@@ -1286,6 +1294,14 @@ static int launch_units_tiled(const DevPlan& P, const Cols& cols, typename Stat:
 	if (tsites > 16384u) tsites = 16384u;
 	uint32_t m = tsites / P.g.ueff;
 	if (m < 1) m = 1;
+	{
+		// A tile's units are dealt to NG consumer groups; a tile of m units takes ceil(m / NG) rounds.
+		// When the last round would be mostly idle (measured: dxy, m = 18 over 15 warps, 6.29 TB/s;
+		// m = 15, 6.80 TB/s) a smaller tile of whole rounds wins; a nearly full last round (fst,
+		// m = 27 of 30) is better left alone: the larger tile keeps more bytes in flight.
+		const uint32_t ng = (uint32_t)kTileConsumerWarps * (32u / P.g.gw);
+		if (m > ng && m % ng != 0 && (double)m / (double)((m + ng - 1) / ng * ng) < 0.8) m = m / ng * ng;
+	}
 	const uint64_t want_tiles = (uint64_t)nsm * 4;
 	if ((nunits + m - 1) / m < want_tiles) {
 		uint64_t mm = (nunits + want_tiles - 1) / want_tiles;
