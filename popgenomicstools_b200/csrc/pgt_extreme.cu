@@ -148,7 +148,11 @@ extern "C" int pgt_xplan_create(pgt_xplan** out, const uint32_t* pos, const uint
 			for (;;) {
 				const uint32_t c = next.fetch_add(1);
 				if (c >= ncontig) break;
-				run_windows(pos, contig_offsets[c], contig_offsets[c + 1], c == 0, contig_len ? contig_len[c] : 0u, winsize, &rows[c]);
+				try {
+					run_windows(pos, contig_offsets[c], contig_offsets[c + 1], c == 0, contig_len ? contig_len[c] : 0u, winsize, &rows[c]);
+				} catch (const std::bad_alloc&) {  // e.g. -winsize 1 over gigabase gaps: rows do not fit
+					rows[c].err = 2;
+				}
 			}
 		};
 		if (nt == 1) work();
@@ -159,6 +163,10 @@ extern "C" int pgt_xplan_create(pgt_xplan** out, const uint32_t* pos, const uint
 		}
 		uint64_t nwin = 0;
 		for (uint32_t c = 0; c < ncontig; ++c) {
+			if (rows[c].err == 2) {
+				delete P;
+				return pgt_set_error(PGT_ERR_NOMEM, "pgt_xplan_create: out of memory for the window table");
+			}
 			if (rows[c].err) {
 				const uint64_t i = rows[c].err_site;
 				delete P;
