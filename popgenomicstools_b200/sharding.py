@@ -8,7 +8,7 @@ to rank 0 is a single torch.distributed call (NCCL over NVLink on GPUs, gloo in 
 """
 import numpy as np
 
-F64_FIELDS = ("sum_a", "sum_b", "fst", "het", "dxy")
+F64_FIELDS = ("sum_a", "sum_b", "fst", "het", "dxy", "ext_value", "prop")  # every other field is uint32
 
 
 class PackedWindows:

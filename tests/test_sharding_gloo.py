@@ -67,3 +67,48 @@ def test_shard_gather_roundtrip_gloo(world, tmp_path):
     res = str(tmp_path / "res.txt")
     mp.spawn(_worker, args=(world, _free_port(), lengths, 500, 100, res), nprocs=world, join=True)
     assert open(res).read() == "ok"
+
+
+def _xworker(rank, world, port, lengths, W, result_path):
+    """Same for the ihsWindow / xpehhWindow extreme scan: shards are window ranges without halo."""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import popgenomicstools_b200 as pgt
+    from popgenomicstools_b200.sharding import PackedWindows, shard_counts
+    offs = np.concatenate([[0], np.cumsum(lengths)]).astype(np.uint64)
+    n = int(offs[-1])
+    pos = O.synth_pos(9, offs, 23)
+    val = O.synth_score(9, 0, n)
+    plan = pgt.ExtremePlan(pos, offs, W)
+    w_lo, w_hi, s_lo, s_hi = plan.shard(rank, world)
+    tab = plan.windows()
+    if w_hi > w_lo:  # the shard's site range is exactly the sites of its windows
+        assert s_lo == tab["first_site"][w_lo] and s_hi == s_lo + int(tab["nsites"][w_lo:w_hi].sum())
+    # "compute" this shard from its own slice of the columns only
+    chr_id = T.expand_chr(lengths)
+    ref = O.extreme("ihs", chr_id, pos, val, W, 2.0)
+    fields = ("ext_value", "ext_pos", "nbig", "nsites", "prop")
+    key = dict(ext_value="ext", ext_pos="extpos", nbig="nbig", nsites="n", prop="prop")
+    counts = shard_counts(dist, w_hi - w_lo, world, "cpu", torch)
+    assert sum(counts) == plan.num_windows == len(ref["n"])
+    pw = PackedWindows(fields, w_hi - w_lo, max(counts), "cpu", torch)
+    for k in fields:
+        src = np.ascontiguousarray(ref[key[k]][w_lo:w_hi])
+        if src.dtype == np.uint32:
+            pw.views[k].view(torch.int32).copy_(torch.from_numpy(src.view(np.int32)))
+        else:
+            pw.views[k].copy_(torch.from_numpy(src))
+    g = pw.gather(dist, rank, world)
+    if rank == 0:
+        table = pw.unpack(g, counts)
+        ok = all(table[k].tobytes() == np.ascontiguousarray(ref[key[k]]).tobytes() for k in fields)
+        open(result_path, "w").write("ok" if ok else "mismatch")
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_extreme_shard_gather_roundtrip_gloo(tmp_path):
+    res = str(tmp_path / "xres.txt")
+    mp.spawn(_xworker, args=(2, _free_port(), [9000, 4000, 2500, 10], 5000, res), nprocs=2, join=True)
+    assert open(res).read() == "ok"
