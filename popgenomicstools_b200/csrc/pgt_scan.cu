@@ -703,8 +703,15 @@ __device__ __forceinline__ void het_count_word(uint32_t w, uint32_t& nonmissing,
 	nonmissing += __popc(~w & 0x80808080u);                 // g >= 0  (hetWindow.cpp:78)
 	nhet += __popc(__vcmpeq4(w, 0x01010101u) & 0x01010101u);  // g == 1 (hetWindow.cpp:80)
 }
+// volatile asm: the eight loads of a round stay back to back (the compiler otherwise interleaves
+// them with the counting and keeps only ~3 in flight)
+__device__ __forceinline__ uint4 ldg_stream_u4(const uint4* p) {
+	uint4 v;
+	asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+	return v;
+}
 template <bool INDIRECT>
-__global__ void __launch_bounds__(256) k_units_het_vec(DevPlan P, const int8_t* __restrict__ geno, HetStat::Acc* __restrict__ units,
+__global__ void __launch_bounds__(256, 4) k_units_het_vec(DevPlan P, const int8_t* __restrict__ geno, HetStat::Acc* __restrict__ units,
                                                         const uint64_t* __restrict__ bounds) {
 	const uint32_t lane = threadIdx.x & 31u;
 	const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -742,9 +749,13 @@ __global__ void __launch_bounds__(256) k_units_het_vec(DevPlan P, const int8_t* 
 			for (uint32_t c0 = lane; c0 < nch; c0 += 256u) {
 				uint4 v[8];
 #pragma unroll
-				for (int q = 0; q < 8; ++q) v[q] = c0 + 32u * q < nch ? __ldg(reinterpret_cast<const uint4*>(A0) + c0 + 32u * q) : kMissing;
+				for (int q = 0; q < 8; ++q) {  // unconditional loads (index clamped) so that all 8 are issued back to back
+					const uint32_t c = c0 + 32u * q;
+					v[q] = ldg_stream_u4(reinterpret_cast<const uint4*>(A0) + (c < nch ? c : nch - 1u));
+				}
 #pragma unroll
 				for (int q = 0; q < 8; ++q) {
+					if (c0 + 32u * q >= nch) v[q] = kMissing;
 					het_count_word(v[q].x, nonmissing, nhet);
 					het_count_word(v[q].y, nonmissing, nhet);
 					het_count_word(v[q].z, nonmissing, nhet);
