@@ -26,6 +26,7 @@
 #include <cstdio>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/pgt_extreme.h"
@@ -1625,6 +1626,57 @@ static int run_scan(const pgt_plan* plan, const pgt_range* range, pgt_stat stat,
 	// the copy stream must not start before the caller's stream reaches this point
 	PGT_CUDA(cudaEventRecord(hs.freed[0], st));
 	PGT_CUDA(cudaStreamWaitEvent(hs.copy, hs.freed[0], 0));
+	// Window bookkeeping on the host -- label, nsites, the two edge positions per window -- runs on
+	// worker threads from here on, next to the copy pipeline.  (It cannot simply follow the slab
+	// loop: enqueueing ~10 operations per slab blocks once the driver's queue is full, so the host
+	// would only get to it when most of the transfer is over; 3e7 windows take ~1 s on one thread.)
+	struct Bookkeeper {
+		std::vector<std::thread> th;
+		void join() {
+			for (auto& t : th)
+				if (t.joinable()) t.join();
+		}
+		~Bookkeeper() { join(); }
+	} book;
+	if (nwin && (out->label || out->nsites || out->start_pos || out->end_pos || out->mid_pos)) {
+		unsigned nt = nwin < (1u << 16) ? 1u : std::min<unsigned>(8u, std::max(1u, std::thread::hardware_concurrency()));
+		const uint64_t per = (nwin + nt - 1) / nt;
+		const uint64_t origin = L.origin;
+		for (unsigned t = 0; t < nt; ++t) {
+			const uint64_t wa = L.w_lo + per * t, wb = std::min<uint64_t>(L.w_hi, wa + per);
+			if (wa >= wb) break;
+			book.th.emplace_back([plan, out, cols, bp, wa, wb, origin, w_lo = L.w_lo]() {
+				uint32_t si = pgt_plan_seg_of_window(plan, wa);
+				for (uint64_t w = wa; w < wb; ++w) {
+					while (w >= plan->segs[si].win_base + plan->segs[si].nwin) ++si;
+					const pgt_seg& sg = plan->segs[si];
+					uint64_t fs;
+					const uint32_t n = pgt_window_sites(plan->g, sg, w - sg.win_base, &fs);
+					const uint64_t first = sg.site_base + fs, last = first + n - 1;
+					const uint32_t label = pgt_plan_contig_of(plan, last);
+					const uint64_t o = w - w_lo;
+					if (out->label) out->label[o] = label;
+					if (out->nsites) out->nsites[o] = n;
+					uint32_t sp = 0, ep = 0;
+					bool have = false;
+					if (bp) {
+						sp = (uint32_t)(first - plan->off[pgt_plan_contig_of(plan, first)]) + 1u;
+						ep = (uint32_t)(last - plan->off[label]) + 1u;
+						have = true;
+					} else if (cols->pos) {
+						sp = cols->pos[first - origin];
+						ep = cols->pos[last - origin];
+						have = true;
+					}
+					if (have) {
+						if (out->start_pos) out->start_pos[o] = sp;
+						if (out->end_pos) out->end_pos[o] = ep;
+						if (out->mid_pos) out->mid_pos[o] = (sp + ep) / 2u;
+					}
+				}
+			});
+		}
+	}
 	char* stage[2][8];
 	{
 		size_t o = L.stage_off;
@@ -1719,37 +1771,7 @@ static int run_scan(const pgt_plan* plan, const pgt_range* range, pgt_stat stat,
 	PGT_CUDA(back(out->nskip, dev.nskip, 4));
 	if (want_global) PGT_CUDA(cudaMemcpyAsync(out->dxy_global, dev.dxy_global, 3 * sizeof(double), cudaMemcpyDeviceToHost, st));
 
-	// window bookkeeping on the host while the device drains: label, nsites, edge positions
-	if (nwin && (out->label || out->nsites || out->start_pos || out->end_pos || out->mid_pos)) {
-		uint32_t si = pgt_plan_seg_of_window(plan, L.w_lo);
-		for (uint64_t w = L.w_lo; w < L.w_hi; ++w) {
-			while (w >= plan->segs[si].win_base + plan->segs[si].nwin) ++si;
-			const pgt_seg& sg = plan->segs[si];
-			uint64_t fs;
-			const uint32_t n = pgt_window_sites(plan->g, sg, w - sg.win_base, &fs);
-			const uint64_t first = sg.site_base + fs, last = first + n - 1;
-			const uint32_t label = pgt_plan_contig_of(plan, last);
-			const uint64_t o = w - L.w_lo;
-			if (out->label) out->label[o] = label;
-			if (out->nsites) out->nsites[o] = n;
-			uint32_t sp = 0, ep = 0;
-			bool have = false;
-			if (bp) {
-				sp = (uint32_t)(first - plan->off[pgt_plan_contig_of(plan, first)]) + 1u;
-				ep = (uint32_t)(last - plan->off[label]) + 1u;
-				have = true;
-			} else if (cols->pos) {
-				sp = cols->pos[first - L.origin];
-				ep = cols->pos[last - L.origin];
-				have = true;
-			}
-			if (have) {
-				if (out->start_pos) out->start_pos[o] = sp;
-				if (out->end_pos) out->end_pos[o] = ep;
-				if (out->mid_pos) out->mid_pos[o] = (sp + ep) / 2u;
-			}
-		}
-	}
+	book.join();
 	PGT_CUDA(cudaStreamSynchronize(st));
 	PGT_CUDA(cudaStreamSynchronize(hs.copy));
 	return PGT_OK;
