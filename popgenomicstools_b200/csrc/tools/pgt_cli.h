@@ -269,14 +269,37 @@ struct DeviceWorkspace {
 	}
 };
 
-inline int select_device() {
+// The tools use ONE GPU (PGT_DEVICE, default 0).  CUDA start-up enumerates and initialises every
+// visible device (~0.3 s each on an 8-GPU box), so unless the user already set CUDA_VISIBLE_DEVICES
+// the process restricts itself to its device before the first CUDA call; the device is then index 0.
+inline int& device_index() {
+	static int idx = -1;
+	return idx;
+}
+inline int chosen_device() {
+	int& idx = device_index();
+	if (idx >= 0) return idx;
 	const char* env = getenv("PGT_DEVICE");
+	const int want = env ? atoi(env) : 0;
+	if (!getenv("CUDA_VISIBLE_DEVICES") && want >= 0) {
+		char buf[16];
+		snprintf(buf, sizeof(buf), "%d", want);
+		setenv("CUDA_VISIBLE_DEVICES", buf, 1);
+		idx = 0;
+	} else {
+		idx = want;
+	}
+	return idx;
+}
+
+inline int select_device() {
+	const int dev = chosen_device();
 	int n = pgt_device_count();
 	if (n <= 0) {
 		fprintf(stderr, "No usable CUDA device: %s\n", n < 0 ? pgt_last_error() : "device count is 0");
 		return -1;
 	}
-	if (pgt_set_device(env ? atoi(env) : 0) != PGT_OK) {
+	if (pgt_set_device(dev) != PGT_OK) {
 		fprintf(stderr, "%s\n", pgt_last_error());
 		return -1;
 	}
@@ -291,14 +314,14 @@ struct DeviceWarmup {
 	double ms = 0;
 	std::string err;
 	void start() {
-		th = std::thread([this]() {
+		const int dev = chosen_device();  // on the calling thread, before any CUDA call
+		th = std::thread([this, dev]() {
 			const double t0 = now_ms();
-			const char* env = getenv("PGT_DEVICE");
 			int n = pgt_device_count();
 			if (n <= 0) {
 				rc = -1;
 				err = n < 0 ? pgt_last_error() : "device count is 0";
-			} else if (pgt_set_device(env ? atoi(env) : 0) != PGT_OK) {
+			} else if (pgt_set_device(dev) != PGT_OK) {
 				rc = -1;
 				err = pgt_last_error();
 			} else {
