@@ -1,0 +1,129 @@
+"""Differential fuzz of the text parsers against the UNMODIFIED reference binaries, on the CPU:
+
+    fuzzed text --(our CLI, PGT_PACK: parser only, no GPU)--> columns --(oracle)--> rows
+    fuzzed text --(reference binary)-------------------------------------------> rows
+
+The GPU path is compared with the oracle on columns elsewhere; this closes the loop for the text
+layer: number syntax ("+5", ".5", "5.", "1e-3", "1E2"), whitespace mixes, CRLF, blank lines, short
+lines, non-numeric tokens, chromosome names with and without '_'."""
+import numpy as np
+import pytest
+
+import cli_util as U
+import oracle_lib as O
+from popgenomicstools_b200 import colfile
+
+needs_ref = pytest.mark.skipif(O.ref_binary("ihsWindow") is None, reason="oracle/_ref not built")
+
+NUMS = ["0", "1", "-1", "+2.5", ".5", "-.25", "5.", "1e-3", "-1E2", "2.000000", "0.000001", "-0.0", "3.14159265358979", "123456.789",
+        "1e0", "-7.5e-1", "00.5", "4e1"]
+BAD = ["nan", "NA", "inf", "-", "abc", "1..2"]
+
+
+def ids_of(runs):
+    """Name id per run: equal names share an id (the oracle compares names through ids)."""
+    seen = {}
+    return [seen.setdefault(nm, len(seen)) for nm, _ in runs]
+
+
+def fuzz_norm_text(rng, tool):
+    nfields = 6 if tool == "ihsWindow" else 8
+    lines, pos = [], 0
+    chrs = ["chr1", "chr2", "scaffold", "chr10"]
+    ci = 0
+    for _ in range(int(rng.integers(5, 120))):
+        if rng.random() < 0.08 and ci + 1 < len(chrs):
+            ci += 1
+            pos = 0
+        pos += int(rng.integers(0, 40))
+        r = rng.random()
+        if r < 0.06 and lines:
+            lines.append("" if rng.random() < 0.5 else "  \t ")  # blank line: the previous site again
+            continue
+        name = chrs[ci] if chrs[ci] == "scaffold" else f"{chrs[ci]}_{pos}"
+        sep = rng.choice(["\t", " ", "  ", " \t"])
+        k = nfields
+        if r < 0.14:
+            k = int(rng.integers(0, nfields))  # short line: later fields keep the previous values
+        fields = [str(rng.choice(NUMS)) for _ in range(k)]
+        if 0.14 <= r < 0.20 and k:
+            fields[int(rng.integers(0, k))] = str(rng.choice(BAD))  # extraction stops here
+        line = sep.join([name, str(max(pos, 1))] + fields)
+        lines.append(line + ("\r" if rng.random() < 0.05 else ""))
+    head = "id\tpos\tgpos\tp1\tihh1\tp2\tihh2\txpehh\tnormxpehh\tcrit\n" if tool == "xpehhWindow" else ""
+    return head + "\n".join(lines) + ("\n" if rng.random() < 0.8 else "")
+
+
+@needs_ref
+@pytest.mark.parametrize("tool", ["ihsWindow", "xpehhWindow"])
+def test_norm_parsers_agree_with_the_reference(tool, tmp_path):
+    rng = np.random.default_rng(2026 if tool == "ihsWindow" else 2027)
+    checked = 0
+    for it in range(150):
+        text = fuzz_norm_text(rng, tool)
+        (tmp_path / "f.norm").write_text(text)
+        W = int(rng.choice([1, 7, 25, 100]))
+        cutoff = float(rng.choice([2.0, 0.5, 0.0])) if tool == "ihsWindow" else float(rng.choice([1.0, -1.0, -0.5]))
+        args = ["f.norm", "-winsize", W, "-cutoff", cutoff] if tool == "ihsWindow" else ["f.norm", cutoff, "-winsize", W]
+        rc, out, err = O.run_ref(tool, args, cwd=tmp_path)
+        assert rc == 0
+        prc, pout, perr = U.run(U.ours(tool), args, cwd=str(tmp_path), env={"PGT_PACK": str(tmp_path / "f.pgtc")})
+        assert (prc, pout) == (0, ""), (it, perr)
+        c = colfile.read(tmp_path / "f.pgtc", mmap=False)
+        if c["nsites"] == 0:
+            continue
+        ids = ids_of(c["runs"])
+        chr_id = np.repeat(np.asarray(ids, np.uint32), [n for _, n in c["runs"]])
+        names = {}
+        for (nm, _), i in zip(c["runs"], ids):
+            names[i] = nm
+        r = O.extreme("ihs" if tool == "ihsWindow" else "xpehh", chr_id, c["columns"]["pos"], c["columns"]["score"], W, cutoff)
+        rows = O.extreme_rows(r, [names[i] for i in range(len(names))])
+        assert rows == out.splitlines(), (it, tool, args, text)
+        checked += 1
+    assert checked > 100
+
+
+@needs_ref
+@pytest.mark.parametrize("tool", ["fstWindow", "hetWindow"])
+def test_site_parsers_agree_with_the_reference(tool, tmp_path):
+    """Well-formed lines in every number syntax the stream extraction accepts; the first empty line
+    ends the input (fstWindow.cpp:125)."""
+    rng = np.random.default_rng(77 if tool == "fstWindow" else 78)
+    for it in range(120):
+        lines, pos = [], 0
+        chrs = ["ctgA", "ctgB", "c_3"]
+        ci = 0
+        for _ in range(int(rng.integers(1, 80))):
+            if rng.random() < 0.1 and ci + 1 < len(chrs):
+                ci += 1
+                pos = 0
+            pos += int(rng.integers(1, 9))
+            sep = rng.choice(["\t", " ", "   ", "\t "])
+            if tool == "fstWindow":
+                vals = [str(rng.choice(NUMS)), str(rng.choice(NUMS))]
+            else:
+                vals = [str(rng.choice(["0", "1", "2", "-1", "+1", "-9", "3"]))]
+            lines.append(sep.join([chrs[ci], str(pos)] + vals) + ("\r" if rng.random() < 0.05 else ""))
+        if rng.random() < 0.2 and len(lines) > 3:
+            lines.insert(int(rng.integers(1, len(lines))), "")  # everything after the empty line is ignored
+        (tmp_path / "f.txt").write_text("\n".join(lines) + "\n")
+        W = int(rng.integers(1, 9))
+        S = int(rng.integers(1, W + 1))
+        rc, out, err = O.run_ref(tool, ["f.txt", W, S], cwd=tmp_path)
+        assert rc == 0
+        prc, pout, perr = U.run(U.ours(tool), ["f.txt", W, S], cwd=str(tmp_path), env={"PGT_PACK": str(tmp_path / "f.pgtc")})
+        assert (prc, pout) == (0, ""), (it, perr, lines)
+        c = colfile.read(tmp_path / "f.pgtc", mmap=False)
+        if c["nsites"] == 0:
+            assert out == ""
+            continue
+        ids = ids_of(c["runs"])
+        chr_id = np.repeat(np.asarray(ids, np.uint32), [n for _, n in c["runs"]])
+        names = {i: nm for (nm, _), i in zip(c["runs"], ids)}
+        nl = [names[i] for i in range(len(names))]
+        if tool == "fstWindow":
+            rows = O.fst_rows(O.fst(chr_id, c["columns"]["pos"], c["columns"]["a"], c["columns"]["b"], W, S), nl)
+        else:
+            rows = O.het_rows(O.het(chr_id, c["columns"]["pos"], c["columns"]["geno"], W, S), nl)
+        assert rows == out.splitlines(), (it, tool, W, S, lines)
