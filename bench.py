@@ -315,7 +315,11 @@ def run_b200(args):
     W, S, seed = wl["winsize"], wl["stepsize"], wl["seed"]
     fused = wl["stat"] == "fused"
     names, offs = human_like_contigs(n_total, S)
-    plan = pgt.WindowPlan(offs, W, S)
+    # reduction unit (part of the summation order, any value gives the same results within 1e-16):
+    # 512 sites fills a 110 KB tile of the 16 B/site fst stream with 13 units = one round of the 15
+    # consumer warps (+2 % over the default 256, measured); the 41 B/site fused tile is best at 256
+    unit_sites = wl.get("unit_sites", 0)
+    plan = pgt.WindowPlan(offs, W, S, unit_sites=unit_sites)
     w_lo, w_hi, s_lo, s_hi = plan.shard(rank, world)
     n_local, nwin_local = s_hi - s_lo, w_hi - w_lo
 
@@ -484,7 +488,7 @@ def run_b200(args):
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": wl["desc"], "name": args.workload, "n_sites": n_total, "contigs": 24,
                        "winsize_sites": W, "stepsize_sites": S, "windows": plan.num_windows, "units": plan.num_units,
-                       "unit_sites": 256, "sharding": f"site ranges cut at window starts, halo = W-S = {W - S} sites, {world} shard(s)",
+                       "unit_sites": unit_sites or 256, "sharding": f"site ranges cut at window starts, halo = W-S = {W - S} sites, {world} shard(s)",
                        "l2": "inputs (>= 6 GB per GPU) exceed the 126 MB L2; no flush needed",
                        "gather": ("NCCL gather of the packed per-window results to rank 0 inside every timed step"
                                   if world > 1 else "single GPU: results stay in HBM")},

@@ -23,7 +23,7 @@ def human_like_contigs(n_total, stepsize):
 
 WORKLOADS = {
     # BASELINE.json configs[3]: the configuration the metric is quoted on
-    "C4": dict(stat="fst", n_sites=3_000_000_000, winsize=50000, stepsize=10000, seed=4,
+    "C4": dict(stat="fst", n_sites=3_000_000_000, winsize=50000, stepsize=10000, seed=4, unit_sites=512,
                desc="fstWindow, 3e9 synthetic sites over 24 contigs, 50000-site windows / 10000-site step"),
     # BASELINE.json configs[4]: fused multi-stat scan, fine windows
     "C5": dict(stat="fused", n_sites=3_000_000_000, winsize=1000, stepsize=100, seed=5,

@@ -35,7 +35,7 @@ def npy(out):
 
 
 @pytest.mark.parametrize("W,S,u", [(5000, 100, 0), (1000, 100, 0), (300, 299, 0), (1, 1, 0), (64, 1, 0), (777, 13, 32),
-                                   (2560, 256, 0), (4096, 4096, 4096), (100, 10, 0), (24, 3, 32), (8, 4, 0), (31, 1, 0)])
+                                   (2560, 256, 0), (4096, 4096, 4096), (100, 10, 0), (24, 3, 32), (8, 4, 0), (31, 1, 0), (5000, 1000, 512)])
 def test_site_mode_all_paths(pgt, W, S, u):
     import torch
     lengths = [W + 3 * S, 12345, 7, 4001]
