@@ -827,7 +827,8 @@ __global__ void __launch_bounds__(256) k_bp_bounds(DevPlan P, const uint32_t* __
 
 template <class Stat>
 __device__ __forceinline__ void emit_window(const DevPlan& P, const pgt_seg& sg, uint64_t w, uint64_t k, const typename Stat::Acc& acc,
-                                            const uint32_t* __restrict__ pos, const pgt_windows& out);
+                                            const uint32_t* __restrict__ pos, const pgt_windows& out, bool have_edges = false,
+                                            uint32_t edge_start = 0, uint32_t edge_end = 0);
 
 // One warp per window: lane l adds unit partials l, l+32, ... (from +0.0, so a window of
 // -0.0 values sums to +0.0 exactly as the reference's `double asum = 0`), then the butterfly.
@@ -838,16 +839,42 @@ __global__ void __launch_bounds__(256) k_windows(DevPlan P, const typename Stat:
 	const uint32_t lane = threadIdx.x & 31u;
 	const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
 	const uint64_t nwarp = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+	// The per-window work is a chain of dependent memory round trips; keep it short: the segment is
+	// cached (w only grows, so it changes a few dozen times per warp instead of costing a binary
+	// search in global memory per window), and lane 0 fetches the two edge positions BEFORE the
+	// partials are summed, so that gather overlaps the partial loads instead of following them.
+	uint32_t si = 0xffffffffu;
+	pgt_seg sg;
+	sg.win_base = 0;
+	sg.nwin = 0;
 	for (uint64_t w = P.win_lo + warp; w < P.win_hi; w += nwarp) {
-		const pgt_seg sg = P.segs[find_seg<false>(P, w)];
+		if (si == 0xffffffffu || w - sg.win_base >= sg.nwin) {
+			si = find_seg<false>(P, w);
+			sg = P.segs[si];
+		}
 		const uint64_t k = w - sg.win_base;
 		uint64_t fu;
 		const uint64_t cnt = pgt_window_units(P.g, sg, k, &fu);
+		uint32_t sp = 0, ep = 0;
+		if (lane == 0 && pos && P.mode != PGT_MODE_BP) {
+			uint64_t fs;
+			const uint32_t nsites = pgt_window_sites(P.g, sg, k, &fs);
+			sp = __ldg(pos + (sg.site_base + fs - P.site_origin));
+			ep = __ldg(pos + (sg.site_base + fs + nsites - 1 - P.site_origin));
+		}
 		const typename Stat::Acc* up = units + (sg.unit_base + fu - units_base);
 		typename Stat::Acc acc = Stat::zero();
-		for (uint64_t x = lane; x < cnt; x += 32u) Stat::add(acc, up[x]);
+		for (uint64_t x = lane; x < cnt; x += 128u) {  // four partials per lane in flight; added in index order
+			typename Stat::Acc v[4];
+#pragma unroll
+			for (int q = 0; q < 4; ++q)
+				if (x + 32u * q < cnt) v[q] = up[x + 32u * q];
+#pragma unroll
+			for (int q = 0; q < 4; ++q)
+				if (x + 32u * q < cnt) Stat::add(acc, v[q]);
+		}
 		acc = warp_butterfly<Stat>(acc);
-		if (lane == 0) emit_window<Stat>(P, sg, w, k, acc, pos, out);
+		if (lane == 0) emit_window<Stat>(P, sg, w, k, acc, pos, out, true, sp, ep);
 	}
 }
 
@@ -874,7 +901,8 @@ struct SmallTree<Stat, P2, P2> {
 
 template <class Stat>
 __device__ __forceinline__ void emit_window(const DevPlan& P, const pgt_seg& sg, uint64_t w, uint64_t k, const typename Stat::Acc& acc,
-                                            const uint32_t* __restrict__ pos, const pgt_windows& out) {
+                                            const uint32_t* __restrict__ pos, const pgt_windows& out, bool have_edges, uint32_t edge_start,
+                                            uint32_t edge_end) {
 	const uint64_t o = w - P.win_lo;
 	uint64_t fs;
 	const uint32_t nsites = pgt_window_sites(P.g, sg, k, &fs);
@@ -891,8 +919,8 @@ __device__ __forceinline__ void emit_window(const DevPlan& P, const pgt_seg& sg,
 		ep = (uint32_t)(last - P.off[label]) + 1u;
 		have = true;
 	} else if (pos) {
-		sp = __ldg(pos + (first - P.site_origin));
-		ep = __ldg(pos + (last - P.site_origin));
+		sp = have_edges ? edge_start : __ldg(pos + (first - P.site_origin));  // the caller may have fetched them early
+		ep = have_edges ? edge_end : __ldg(pos + (last - P.site_origin));
 		have = true;
 	}
 	if (have) {
