@@ -150,3 +150,17 @@ def test_c4_fst_3e9_sites_properties(pgt):
         parts.append(npy(o))
     for k in res:
         assert np.concatenate([p[k] for p in parts]).tobytes() == res[k].tobytes(), k
+    # the bench / CLI configuration (512-site reduction units): same table, sums within 1e-12, and again
+    # bit-identical across the level-1 kernels and 8 shards
+    plan512 = pgt.WindowPlan(offs, W, S, unit_sites=512)
+    r5 = npy(pgt.fst_window(plan512, pos, a, b))
+    for k in ("label", "start_pos", "end_pos", "mid_pos", "nsites"):
+        P.assert_exact(r5[k], res[k], k)
+    for k in ("sum_a", "sum_b", "fst"):
+        assert np.all(np.abs(r5[k] - res[k]) <= 1e-12 * np.abs(res[k]) + 1e-15), k
+    parts = []
+    for r in range(8):
+        wl, wh, sl, sh = plan512.shard(r, 8)
+        parts.append(npy(pgt.fst_window(plan512, pos[sl:sh], a[sl:sh], b[sl:sh], window_range=(wl, wh), site_origin=sl)))
+    for k in r5:
+        assert np.concatenate([p[k] for p in parts]).tobytes() == r5[k].tobytes(), k
