@@ -324,7 +324,6 @@ __global__ void __launch_bounds__(256) k_xunits(XDev P, uint64_t chunk, const do
 	uint64_t w_end2 = P.xoff[w + 2 <= P.nw ? w + 2 : P.nw];  // one window ahead
 	uint64_t u0 = P.unit0[w], u0n = P.unit0[w + 1];
 	uint64_t st = w_st + (c_lo - w_st + P.U - 1) / P.U * P.U;  // first unit starting at or after c_lo
-	const double* __restrict__ sc = score - P.origin;         // indexed by global site
 	for (;;) {
 		while (st >= w_end) {  // next non-empty window
 			++w;
@@ -339,7 +338,7 @@ __global__ void __launch_bounds__(256) k_xunits(XDev P, uint64_t chunk, const do
 		if (st >= c_hi) return;
 		const uint32_t len = (uint32_t)(w_end - st < P.U ? w_end - st : P.U);
 		XAcc a{-CUDART_INF, 0.0, ~0ull, 0u};
-		const double* __restrict__ p = sc + st;
+		const double* __restrict__ p = score + (st - P.origin);  // element 0 of `score` is global site P.origin
 		bool first_nan = false;  // lane gl == 0 sees the window's first site when st == w_st
 		uint32_t x = gl;
 		for (; x + 7u * G < len; x += 8u * G) {  // full rounds: 8 loads in flight per lane
