@@ -39,10 +39,10 @@ FLOAT_COL = {"fstWindow": {4}, "hetWindow": {4}, "dxyWindow": {3}}
 
 def test_golden_transcripts_through_the_clis(golden_cases, tmp_path):
     ties = 0
-    # every 3rd transcript through a fresh CLI process (each pays ~1 s of CUDA start-up); ALL
+    # every 4th transcript through a fresh CLI process (each pays 1-3 s of CUDA start-up); ALL
     # transcripts go through the library in test_fst_gpu.py / test_stats_gpu.py
     for i, c in enumerate(golden_cases):
-        if i % 3:
+        if i % 4:
             continue
         d = tmp_path / f"c{i}"
         d.mkdir()
