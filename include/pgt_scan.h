@@ -122,6 +122,14 @@ int pgt_plan_window_units(const pgt_plan* plan, uint64_t w, uint64_t* first_unit
 int pgt_plan_shard(const pgt_plan* plan, uint32_t shard, uint32_t nshards, uint64_t* w_lo, uint64_t* w_hi,
                    uint64_t* site_lo, uint64_t* site_hi);
 
+/* Optional: keep the plan's device tables (segments and contig offsets, a few KB) resident in
+ * caller-owned device memory of at least pgt_plan_device_bytes(), so that scans upload nothing
+ * (lower per-call latency for small inputs; a device-mode site scan then consists of kernel
+ * launches only and can be captured into a CUDA graph).  The buffer must outlive the binding;
+ * buffer = NULL unbinds.  A bound plan may only be scanned on the device that owns the buffer. */
+size_t pgt_plan_device_bytes(const pgt_plan* plan);
+int pgt_plan_bind_device(pgt_plan* plan, void* buffer, size_t bytes, void* stream);
+
 /* ---- scan: the hot path ----------------------------------------------------------------
  *
  * A scan processes windows [w_lo, w_hi) of the plan.  Column pointers address element

@@ -17,6 +17,8 @@ struct pgt_plan {
 	uint64_t nunits;
 	uint64_t nsites;
 	uint64_t nblocks;  // scan blocks of g.wunits units over all segments
+	// optional caller-owned device copy of segs | off (pgt_plan_bind_device); nullptr = upload per scan
+	unsigned char* d_tables = nullptr;
 };
 
 int pgt_set_error(int code, const std::string& msg);

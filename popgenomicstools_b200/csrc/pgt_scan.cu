@@ -1286,6 +1286,28 @@ static int make_layout(const pgt_plan* plan, const pgt_range* range, pgt_stat st
 	return PGT_OK;
 }
 
+extern "C" size_t pgt_plan_device_bytes(const pgt_plan* plan) {
+	if (!plan) return 0;
+	return align_up(plan->segs.size() * sizeof(pgt_seg), 256) + align_up(plan->off.size() * sizeof(uint64_t), 256) + 256;
+}
+
+extern "C" int pgt_plan_bind_device(pgt_plan* plan, void* buffer, size_t bytes, void* stream) {
+	if (!plan) return pgt_set_error(PGT_ERR_ARGS, "pgt_plan_bind_device: plan is NULL");
+	if (!buffer) {
+		plan->d_tables = nullptr;
+		return PGT_OK;
+	}
+	if (bytes < pgt_plan_device_bytes(plan)) return pgt_set_error(PGT_ERR_NOMEM, "pgt_plan_bind_device: buffer too small");
+	cudaStream_t st = (cudaStream_t)stream;
+	unsigned char* b = (unsigned char*)(((uintptr_t)buffer + 255) / 256 * 256);
+	const size_t seg_bytes = plan->segs.size() * sizeof(pgt_seg);
+	if (seg_bytes) PGT_CUDA(cudaMemcpyAsync(b, plan->segs.data(), seg_bytes, cudaMemcpyHostToDevice, st));
+	PGT_CUDA(cudaMemcpyAsync(b + align_up(seg_bytes, 256), plan->off.data(), plan->off.size() * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
+	PGT_CUDA(cudaStreamSynchronize(st));
+	plan->d_tables = b;
+	return PGT_OK;
+}
+
 extern "C" size_t pgt_scan_workspace_bytes(const pgt_plan* plan, const pgt_range* range, pgt_stat stat, pgt_mem mem) {
 	Layout L;
 	if (make_layout(plan, range, stat, mem, &L) != PGT_OK) return 0;
@@ -1580,14 +1602,17 @@ static int run_scan(const pgt_plan* plan, const pgt_range* range, pgt_stat stat,
 	char* ws = (char*)workspace;
 	const size_t seg_bytes = plan->segs.size() * sizeof(pgt_seg);
 	const size_t off_bytes = plan->off.size() * sizeof(uint64_t);
-	if (seg_bytes) PGT_CUDA(cudaMemcpyAsync(ws + L.segs_off, plan->segs.data(), seg_bytes, cudaMemcpyHostToDevice, st));
-	PGT_CUDA(cudaMemcpyAsync(ws + L.off_off, plan->off.data(), off_bytes, cudaMemcpyHostToDevice, st));
+	const bool resident = plan->d_tables != nullptr;  // pgt_plan_bind_device: nothing to upload (and graph-capturable)
+	if (!resident) {
+		if (seg_bytes) PGT_CUDA(cudaMemcpyAsync(ws + L.segs_off, plan->segs.data(), seg_bytes, cudaMemcpyHostToDevice, st));
+		PGT_CUDA(cudaMemcpyAsync(ws + L.off_off, plan->off.data(), off_bytes, cudaMemcpyHostToDevice, st));
+	}
 	if (bp) PGT_CUDA(cudaMemcpyAsync(ws + L.siteoff_off, site_offsets, off_bytes, cudaMemcpyHostToDevice, st));
 
 	DevPlan P;
 	P.g = plan->g;
-	P.segs = (const pgt_seg*)(ws + L.segs_off);
-	P.off = (const uint64_t*)(ws + L.off_off);
+	P.segs = resident ? (const pgt_seg*)plan->d_tables : (const pgt_seg*)(ws + L.segs_off);
+	P.off = resident ? (const uint64_t*)(plan->d_tables + align_up(seg_bytes, 256)) : (const uint64_t*)(ws + L.off_off);
 	P.site_off = bp ? (const uint64_t*)(ws + L.siteoff_off) : nullptr;
 	P.nseg = (uint32_t)plan->segs.size();
 	P.ncontig = (uint32_t)plan->off.size() - 1;

@@ -42,6 +42,20 @@ class WindowPlan:
                                   self.winsize, self.stepsize, int(unit_sites)))
         self._h = h
         self._workspaces = {}
+        self._bound = None
+
+    def bind(self, device):
+        """Keep the plan's device tables resident on `device` (pgt_plan_bind_device): later scans
+        on that device upload nothing.  Called automatically by device-mode scans."""
+        torch = _torch()
+        device = torch.device(device)
+        if self._bound is not None and self._bound[0] == device:
+            return
+        buf = torch.empty(int(self._lib.pgt_plan_device_bytes(self._h)), dtype=torch.uint8, device=device)
+        with torch.cuda.device(device):
+            check(self._lib.pgt_plan_bind_device(self._h, buf.data_ptr(), buf.numel(),
+                                                 C.c_void_p(torch.cuda.current_stream(device).cuda_stream)))
+        self._bound = (device, buf)
 
     def __del__(self):
         h, self._h = getattr(self, "_h", None), None
@@ -197,6 +211,10 @@ def scan(plan, stat, cols, minind=1, site_offsets=None, window_range=None, site_
         so = np.ascontiguousarray(site_offsets, dtype=np.uint64)
         keep.append(so)
     mem = _cabi.PGT_MEM_DEVICE if on_device else _cabi.PGT_MEM_HOST
+    if on_device:
+        plan.bind(dev)
+    elif plan._bound is not None and plan._bound[0] != dev:
+        raise ValueError(f"plan is bound to {plan._bound[0]}, scan requested on {dev}")
     ws = plan.workspace(dev, stat, mem, window_range, site_origin, site_count)
     with torch.cuda.device(dev):
         stream = torch.cuda.current_stream(dev).cuda_stream
