@@ -68,3 +68,29 @@ def read(path, mmap=True):
         at = _pad(at + n * np.dtype(dt).itemsize)
     return dict(kind=kind, nsites=n, runs=[(nm.decode(), int(c)) for nm, c in zip(names, counts)],
                 offsets=np.concatenate([[0], np.cumsum(counts)]).astype(np.uint64), columns=cols)
+
+
+def _main(argv):
+    """python -m popgenomicstools_b200.colfile info FILE.pgtc | head FILE.pgtc [N]"""
+    if len(argv) < 2 or argv[0] not in ("info", "head"):
+        print(_main.__doc__)
+        return 2
+    r = read(argv[1])
+    if argv[0] == "info":
+        print(f"kind\t{r['kind']}\nsites\t{r['nsites']}\nruns\t{len(r['runs'])}")
+        print("columns\t" + ", ".join(f"{k}:{v.dtype}" for k, v in r["columns"].items()))
+        for nm, c in r["runs"][:50]:
+            print(f"run\t{nm}\t{c}")
+        if len(r["runs"]) > 50:
+            print(f"... {len(r['runs']) - 50} more runs")
+        return 0
+    n = int(argv[2]) if len(argv) > 2 else 10
+    names = np.repeat(np.arange(len(r["runs"])), [c for _, c in r["runs"]])[:n]
+    for i in range(min(n, r["nsites"])):
+        print("\t".join([r["runs"][names[i]][0]] + [repr(v[i].item()) for v in r["columns"].values()]))
+    return 0
+
+
+if __name__ == "__main__":
+    import sys
+    sys.exit(_main(sys.argv[1:]))
