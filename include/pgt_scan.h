@@ -88,8 +88,9 @@ int pgt_device_free(void* p);
  * contig_offsets[ncontig+1]: cumulative sizes, contig c spans [off[c], off[c+1]) in site
  * indices (PGT_MODE_SITES) or in entries = bp (PGT_MODE_BP).  Contigs are in file order;
  * adjacent lines with equal names form one contig, as in the reference (chr != oldchr).
- * unit_sites: cap on the reduction unit in sites (0 = default 256); part of the summation
- * order, see DESIGN.md "Summation order".
+ * unit_sites: cap on the reduction unit in sites (0 = default 256; a multiple of 32, <= 4096); part
+ * of the summation order, see DESIGN.md "Summation order".  In PGT_MODE_BP the unit is a bp range: for
+ * sparse data choose about 341 x (bp per site), capped at 4096 (what the dxyWindow CLI does).
  *
  * The enumeration reproduces, in closed form, the reference's behaviour incl. its quirks
  * (SURVEY.md Appendix A): trailing partial window at every contig change but at EOF only if

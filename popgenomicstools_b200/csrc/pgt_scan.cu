@@ -1364,6 +1364,18 @@ static int launch_units_tiled(const DevPlan& P, const Cols& cols, typename Stat:
 		const uint32_t ng = (uint32_t)kTileConsumerWarps * (32u / P.g.gw);
 		if (m > ng && m % ng != 0 && (double)m / (double)((m + ng - 1) / ng * ng) < 0.8) m = m / ng * ng;
 	}
+	const uint32_t cap_sites = m * P.g.ueff;  // sites a stage can hold (what the shared-memory regions are sized for)
+	if (INDIRECT && nunits) {
+		// bp mode: a unit is a bp range and holds anything from 0 to ueff sites.  Sizing tiles for the
+		// dense worst case makes them nearly empty on sparse data (SNP-only MAFs: ~3 % full, and the
+		// per-tile cost dominated: 5.6 ms for 1e8 sites over 3e9 bp).  Size them for the average
+		// density instead; a tile whose slice does not fit is read straight from global memory by
+		// the consumers (`staged` in the kernel), so dense stretches stay correct.
+		const double avg = (double)valid_elems / (double)nunits;  // sites per unit
+		const double want = 0.75 * (double)cap_sites / (avg > 1e-3 ? avg : 1e-3);
+		const uint32_t m_sparse = want > 65536.0 ? 65536u : (uint32_t)want;
+		if (m_sparse > m) m = m_sparse;
+	}
 	const uint64_t want_tiles = (uint64_t)nsm * 4;
 	if ((nunits + m - 1) / m < want_tiles) {
 		uint64_t mm = (nunits + want_tiles - 1) / want_tiles;
@@ -1381,7 +1393,7 @@ static int launch_units_tiled(const DevPlan& P, const Cols& cols, typename Stat:
 		tc.gcol[c] = (const char*)sc.ptr[c];
 		tc.elem[c] = sc.elem[c];
 		tc.col_off[c] = o;
-		tc.col_cap[c] = (uint32_t)align_up((size_t)m * P.g.ueff * sc.elem[c] + 48, 16);
+		tc.col_cap[c] = (uint32_t)align_up((size_t)cap_sites * sc.elem[c] + 48, 16);
 		o += tc.col_cap[c];
 	}
 	tc.stage_bytes = (uint32_t)align_up(o, 128);
