@@ -152,3 +152,46 @@ def test_bp_mode_all_paths(pgt, density, W, S):
     pgt.tune("level1", 0)
     pgt.tune("level2", 0)
     check(pgt.dxy_window(plan, *h, minind=5, site_offsets=soff), "bp host")
+
+
+@pytest.mark.parametrize("W,S", [(1000, 1000), (5000, 1000), (100, 10), (3000, 3000)])
+def test_many_contigs_tile_segment_table(pgt, W, S):
+    """Scaffold-level genomes: hundreds of contigs put consecutive tiles of a CTA into different
+    segments; above 32 segments the tiled kernel uses a tile -> segment table (k_tile_segs).  Same
+    bits as the direct kernel (which binary-searches per unit), oracle parity, shards, host mode."""
+    import torch
+    rng = np.random.default_rng(W + S)
+    lengths = rng.integers(1, 9000, size=400).tolist() + [1, 2, W, W + S, 3 * W]
+    offs = offsets(lengths)
+    n = int(offs[-1])
+    a, b = pgt.synth_fst(8, 0, n)
+    pos = pgt.synth_pos(8, 0, n, offs, 1)
+    plan = pgt.WindowPlan(offs, W, S)
+    assert plan.num_segments > 32
+    ref = O.fst(T.expand_chr(lengths), pos.cpu().numpy(), a.cpu().numpy(), b.cpu().numpy(), W, S)
+    absr = O.fst(T.expand_chr(lengths), pos.cpu().numpy(), np.abs(a.cpu().numpy()), np.abs(b.cpu().numpy()), W, S)
+    try:
+        pgt.tune("level1", 2)  # tiled (the input is far below the automatic 256 MB threshold)
+        tiled = npy(pgt.fst_window(plan, pos, a, b))
+        parts = []
+        for r in range(3):
+            wl, wh, sl, sh = plan.shard(r, 3)
+            if wh > wl:
+                parts.append(npy(pgt.fst_window(plan, pos[sl:sh], a[sl:sh], b[sl:sh], window_range=(wl, wh), site_origin=sl)))
+        host = pgt.fst_window(plan, pos.cpu().numpy(), a.cpu().numpy(), b.cpu().numpy())
+        pgt.tune("level1", 1)
+        direct = npy(pgt.fst_window(plan, pos, a, b))
+    finally:
+        pgt.tune("level1", 0)
+    P.assert_exact(tiled["label"], ref["label"], "label")
+    P.assert_exact(tiled["start_pos"], ref["start"], "start")
+    P.assert_exact(tiled["end_pos"], ref["end"], "end")
+    P.assert_exact(tiled["nsites"], ref["n"], "nsites")
+    P.assert_sum_close(tiled["sum_a"], ref["asum"], absr["asum"], "sum_a")
+    P.assert_sum_close(tiled["sum_b"], ref["bsum"], absr["bsum"], "sum_b")
+    if plan.num_units and pgt.WindowPlan(offs, W, S).num_units:  # direct kernel implements the same order when gw == 32
+        same = all(direct[k].tobytes() == tiled[k].tobytes() for k in tiled)
+        assert same or min(W, S) < 256, "tiled and direct level 1 differ"
+    for k in tiled:
+        assert np.concatenate([p[k] for p in parts]).tobytes() == tiled[k].tobytes(), "shards " + k
+        assert host[k].tobytes() == tiled[k].tobytes(), "host " + k
