@@ -17,6 +17,8 @@ struct pgt_plan {
 	uint64_t nunits;
 	uint64_t nsites;
 	uint64_t nblocks;  // scan blocks of g.wunits units over all segments
+	uint64_t window_units_total;  // unit partials a direct level 2 reads over all windows (short segments have short windows)
+	uint64_t scan_units_total;    // units the block scans of scan mode touch (whole blocks, at least one per segment)
 	// optional caller-owned device copy of segs | off (pgt_plan_bind_device); nullptr = upload per scan
 	unsigned char* d_tables = nullptr;
 };

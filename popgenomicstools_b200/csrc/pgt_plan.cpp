@@ -55,6 +55,8 @@ extern "C" int pgt_plan_create(pgt_plan** out, pgt_mode mode, const uint64_t* co
 	p->nwin = 0;
 	p->nunits = 0;
 	p->nblocks = 0;
+	p->window_units_total = 0;
+	p->scan_units_total = 0;
 
 	uint32_t last_nonempty = ncontig;  // index of the last non-empty contig
 	for (uint32_t c = ncontig; c-- > 0;)
@@ -94,6 +96,9 @@ extern "C" int pgt_plan_create(pgt_plan** out, pgt_mode mode, const uint64_t* co
 		sg.blk_base = p->nblocks;
 		p->nwin += sg.nwin;
 		p->nunits += sg.nunits;
+		// partials a direct level 2 reads: wunits per full window, the rest of the segment for a trailing partial
+		p->window_units_total += sg.nfull * (uint64_t)p->g.wunits + (sg.nwin > sg.nfull ? sg.nunits - sg.nfull * (uint64_t)p->g.upp : 0);
+		p->scan_units_total += (sg.nunits + p->g.wunits - 1) / p->g.wunits * (uint64_t)p->g.wunits;
 		p->nblocks += (sg.nunits + p->g.wunits - 1) / p->g.wunits;
 		p->segs.push_back(sg);
 		base += N;
