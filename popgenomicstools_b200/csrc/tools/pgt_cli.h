@@ -172,6 +172,107 @@ inline bool parse_f64(const char*& p, const char* e, double* v) {
 	return true;
 }
 
+// ---- single-pass fast path for the common line shape -----------------------------------------
+//
+// `name <blanks> digits <blanks> number [<blanks> number] [\r]\n` with plain decimals: one pass over
+// the bytes, no separate search for the line end.  Exactness: <= 9 position digits fit uint32
+// arithmetic checked against 2^32; a decimal with <= 15 digits in total is m / 10^f with m < 2^53
+// and 10^f exact, and ONE IEEE division of two exact doubles is the correctly rounded value of the
+// string -- the double strtod / std::from_chars return (Clinger's fast path).  Anything else (signs
+// on the position, exponents, more digits, inf/nan, missing fields, other white space) makes the
+// function return false WITHOUT side effects and the caller parses that line the general way.
+inline bool fast_decimal(const char*& p, const char* e, double* v) {
+	static const double kPow10[16] = {1e0, 1e1, 1e2, 1e3, 1e4, 1e5, 1e6, 1e7, 1e8, 1e9, 1e10, 1e11, 1e12, 1e13, 1e14, 1e15};
+	const char* q = p;
+	bool neg = false;
+	if (q < e && *q == '-') {
+		neg = true;
+		++q;
+	}
+	uint64_t m = 0;
+	int nd = 0;
+	while (q < e && (unsigned)(*q - '0') <= 9u) {
+		m = m * 10u + (unsigned)(*q - '0');
+		++q;
+		++nd;
+	}
+	int frac = 0;
+	if (q < e && *q == '.') {
+		++q;
+		const char* f0 = q;
+		while (q < e && (unsigned)(*q - '0') <= 9u) {
+			m = m * 10u + (unsigned)(*q - '0');
+			++q;
+		}
+		frac = (int)(q - f0);
+		nd += frac;
+	}
+	if (nd == 0 || nd > 15) return false;
+	if (q < e && *q != ' ' && *q != '\t' && *q != '\n' && *q != '\r') return false;  // exponent, letters, ...
+	const double r = (double)m / kPow10[frac];
+	*v = neg ? -r : r;
+	p = q;
+	return true;
+}
+inline const char* skip_blanks(const char* p, const char* e) {
+	while (p < e && (*p == ' ' || *p == '\t')) ++p;
+	return p;
+}
+// On success: [*name_b, *name_e) = first token, *pos, vals[0..nvals), *next = first byte of the next line.
+template <int NVALS, bool INTVALS>
+inline bool fast_line(const char* p, const char* e, const char** name_b, const char** name_e, uint32_t* pos, double* vals, int32_t* ivals,
+                      const char** next) {
+	const char* s = p;
+	const char* t = s;
+	while (t < e && *t != ' ' && *t != '\t' && *t != '\n' && *t != '\r' && *t != '\v' && *t != '\f') ++t;
+	if (t == s || t >= e || (*t != ' ' && *t != '\t')) return false;
+	const char* q = skip_blanks(t, e);
+	uint64_t x = 0;
+	int nd = 0;
+	while (q < e && (unsigned)(*q - '0') <= 9u) {
+		x = x * 10u + (unsigned)(*q - '0');
+		++q;
+		++nd;
+	}
+	if (nd == 0 || nd > 9 || q >= e || (*q != ' ' && *q != '\t')) return false;
+	double dv[NVALS > 0 ? NVALS : 1];
+	int32_t iv[NVALS > 0 ? NVALS : 1];
+	for (int k = 0; k < NVALS; ++k) {
+		q = skip_blanks(q, e);
+		if (INTVALS) {
+			bool neg = false;
+			if (q < e && *q == '-') {
+				neg = true;
+				++q;
+			}
+			uint32_t g = 0;
+			int gd = 0;
+			while (q < e && (unsigned)(*q - '0') <= 9u) {
+				g = g * 10u + (unsigned)(*q - '0');
+				++q;
+				++gd;
+			}
+			if (gd == 0 || gd > 9) return false;
+			if (q < e && *q != ' ' && *q != '\t' && *q != '\n' && *q != '\r') return false;
+			iv[k] = neg ? -(int32_t)g : (int32_t)g;
+		} else if (!fast_decimal(q, e, &dv[k])) {
+			return false;
+		}
+	}
+	q = skip_blanks(q, e);
+	if (q < e && *q == '\r') ++q;
+	if (q < e && *q != '\n') return false;  // extra fields: let the general path decide
+	*name_b = s;
+	*name_e = t;
+	*pos = (uint32_t)x;
+	for (int k = 0; k < NVALS; ++k) {
+		if (INTVALS) ivals[k] = iv[k];
+		else vals[k] = dv[k];
+	}
+	*next = q < e ? q + 1 : e;
+	return true;
+}
+
 // ---- line-chunked parallel parsing ------------------------------------------------------
 
 struct ContigRun {

@@ -157,23 +157,45 @@ int main(int argc, char** argv) {
 		size_t prev_len = 0;
 		long li = 0;
 		while (p < e) {
-			const char* q = (const char*)memchr(p, '\n', (size_t)(e - p));
-			const char* le = q ? q : e;
-			const char* s = skip_ws(p, le);
-			const char* t = token_end(s, le);
-			bool ok = t > s;
-			const char* cur = t;
-			if (ok) ok = parse_u32(cur, le, &pos[row]);
+			const char* s;
+			const char* t;
+			const char* q;
+			// common line shape in one pass (pgt_cli.h fast_line); anything unusual takes the general path below
+			const char* next = nullptr;
 #if defined(PGT_TOOL_FST)
-			if (ok) ok = parse_f64(cur, le, &col_a[row]);
-			if (ok) ok = parse_f64(cur, le, &col_b[row]);
+			double ab[2];
+			const bool fast = fast_line<2, false>(p, e, &s, &t, &pos[row], ab, nullptr, &next);
+			if (fast) {
+				col_a[row] = ab[0];
+				col_b[row] = ab[1];
+			}
 #else
 			int32_t g = 0;
-			if (ok) ok = parse_i32(cur, le, &g);
+			const bool fast = fast_line<1, true>(p, e, &s, &t, &pos[row], nullptr, &g, &next);
+#endif
+			if (fast) {
+				q = next < e || (next == e && e[-1] == '\n') ? next - 1 : nullptr;  // position of this line's '\n', if any
+			} else {
+				q = (const char*)memchr(p, '\n', (size_t)(e - p));
+				const char* le = q ? q : e;
+				s = skip_ws(p, le);
+				t = token_end(s, le);
+				bool ok = t > s;
+				const char* cur = t;
+				if (ok) ok = parse_u32(cur, le, &pos[row]);
+#if defined(PGT_TOOL_FST)
+				if (ok) ok = parse_f64(cur, le, &col_a[row]);
+				if (ok) ok = parse_f64(cur, le, &col_b[row]);
+#else
+				g = 0;
+				if (ok) ok = parse_i32(cur, le, &g);
+#endif
+				if (!ok && c.bad_line < 0) c.bad_line = li;
+			}
+#if defined(PGT_TOOL_HET)
 			// hetWindow.cpp:78-80 only distinguishes g < 0, g == 1, other
 			geno[row] = (int8_t)(g < 0 ? -1 : (g > 127 ? 127 : g));
 #endif
-			if (!ok && c.bad_line < 0) c.bad_line = li;
 			if (!prev_name || (size_t)(t - s) != prev_len || memcmp(prev_name, s, prev_len) != 0) {
 				c.runs.push_back(ContigRun{std::string(s, t), 0});
 				prev_name = s;

@@ -127,3 +127,46 @@ def test_site_parsers_agree_with_the_reference(tool, tmp_path):
         else:
             rows = O.het_rows(O.het(chr_id, c["columns"]["pos"], c["columns"]["geno"], W, S), nl)
         assert rows == out.splitlines(), (it, tool, W, S, lines)
+
+
+@needs_ref
+def test_maf_parser_agrees_with_the_reference(tmp_path):
+    """dxyWindow: both populations share the site list (the two-file sync is then the identity), fuzzed
+    number syntax and white space in the 7-column MAF lines; -fixedsite 1 windows and the global line."""
+    rng = np.random.default_rng(4242)
+    freqs = ["0.000000", "1.000000", "0.5", ".25", "1e-05", "2.5E-1", "+0.125", "0.333333", "0.999999", "1", "0"]
+    for it in range(80):
+        names = ["chr1", "chr2", "scaf_7"]
+        lines1, lines2 = [], []
+        ci, pos = 0, 0
+        for _ in range(int(rng.integers(2, 60))):
+            if rng.random() < 0.1 and ci + 1 < len(names):
+                ci += 1
+                pos = 0
+            pos += int(rng.integers(1, 30))
+            for lines in (lines1, lines2):
+                sep = rng.choice(["\t", " ", "  ", "\t "])
+                al = rng.choice(["A", "C", "G", "T", "N"], size=3)
+                lines.append(sep.join([names[ci], str(pos), al[0], al[1], al[2], str(rng.choice(freqs)), str(int(rng.integers(0, 12)))])
+                             + ("\r" if rng.random() < 0.03 else ""))
+        head = "chromo\tposition\tmajor\tminor\tref\tknownEM\tnInd\n"
+        (tmp_path / "p1.mafs").write_text(head + "\n".join(lines1) + "\n")
+        (tmp_path / "p2.mafs").write_text(head + "\n".join(lines2) + "\n")
+        W = int(rng.integers(1, 7))
+        S = int(rng.integers(1, W + 1))
+        minind = int(rng.integers(1, 6))
+        args = ["-winsize", W, "-stepsize", S, "-minind", minind, "-fixedsite", 1, "p1.mafs", "p2.mafs"]
+        rc, out, err = O.run_ref("dxyWindow", args, cwd=tmp_path)
+        assert rc == 0
+        prc, pout, perr = U.run(U.ours("dxyWindow"), args, cwd=str(tmp_path),
+                                env={"PGT_PACK": str(tmp_path / "p1.pgtc"), "PGT_PACK2": str(tmp_path / "p2.pgtc")})
+        assert (prc, pout) == (0, ""), (it, perr)
+        c1, c2 = colfile.read(tmp_path / "p1.pgtc", mmap=False), colfile.read(tmp_path / "p2.pgtc", mmap=False)
+        assert c1["runs"] == c2["runs"] and np.array_equal(c1["columns"]["pos"], c2["columns"]["pos"])
+        ids = ids_of(c1["runs"])
+        chr_id = np.repeat(np.asarray(ids, np.uint32), [n for _, n in c1["runs"]])
+        nm = {i: n for (n, _), i in zip(c1["runs"], ids)}
+        r = O.dxy(chr_id, c1["columns"]["pos"], c1["columns"]["freq"], c2["columns"]["freq"], c1["columns"]["nind"],
+                  c2["columns"]["nind"], minind, W, S, 1)
+        assert O.dxy_rows(r, [nm[i] for i in range(len(nm))]) == out.splitlines(), (it, args, lines1[:3])
+        assert O.dxy_global_row(r) == err.strip(), (it, err)
