@@ -24,5 +24,5 @@ cd "$OUT/pkg"
 export ASAN_OPTIONS=detect_leaks=0 UBSAN_OPTIONS=print_stacktrace=1:halt_on_error=1
 LD_PRELOAD="$(gcc -print-file-name=libasan.so)" python -m pytest tests/test_plan_cpu.py tests/test_extreme_plan_cpu.py tests/test_abi_cpu.py -x -q
 cd "$ROOT"  # the CLI tests import the normal package; only the CLI binaries are the sanitizer builds
-PGT_TEST_BIN="$OUT/bin" python -m pytest tests/test_colfile_cpu.py tests/test_extreme_cli_cpu.py tests/test_cli_cpu.py -x -q
+PGT_TEST_BIN="$OUT/bin" python -m pytest tests/test_colfile_cpu.py tests/test_extreme_cli_cpu.py tests/test_cli_cpu.py tests/test_parser_fuzz_cpu.py -x -q
 echo "asan/ubsan host run: clean"
