@@ -265,6 +265,10 @@ int main(int argc, char** argv) {
 		uint64_t row = c.row0;
 		const char* prev_name = nullptr;
 		size_t prev_len = 0;
+		// Values a row inherits from the row before it (stream semantics above) are copied on the spot,
+		// unless that row is itself still waiting for the previous CHUNK's last row: the dependency is
+		// then recorded in head_fix and resolved in row order after all chunks are parsed.
+		bool pend_pos = true, pend_score = true;  // "row - 1 is unresolved": true at the chunk head
 		while (p < e) {
 			const char* q = (const char*)memchr(p, '\n', (size_t)(e - p));
 			const char* le = q ? q : e;
@@ -272,12 +276,16 @@ int main(int argc, char** argv) {
 			const char* t = token_end(s, le);
 			const bool have_prev = row > c.row0;
 			if (t == s) {  // blank line: every extraction fails, the previous site is counted again
-				if (have_prev) {
+				if (!pend_pos && !pend_score) {
 					pos[row] = pos[row - 1];
 					score[row] = score[row - 1];
-					c.runs.back().count++;
 				} else {
 					c.head_fix.emplace_back(row, ROW_BLANK);
+					pend_pos = pend_score = true;
+				}
+				if (have_prev) {
+					c.runs.back().count++;
+				} else {
 					c.runs.push_back(ContigRun{kSame, 1});
 					prev_name = kSame;
 					prev_len = 1;
@@ -288,18 +296,24 @@ int main(int argc, char** argv) {
 				const char* cur = t;
 				uint32_t pv = 0;
 				bool ok = true;
+				bool deferred = false;
 				if (skip_ws(cur, le) >= le) {  // no position field: pos and scores stay
 					ok = false;
-					if (have_prev) pos[row] = pos[row - 1];
-					else {
+					if (!pend_pos && !pend_score) {
+						pos[row] = pos[row - 1];
+					} else {
 						pos[row] = 0;
 						c.head_fix.emplace_back(row, ROW_BLANK);  // takes pos and score of the previous row
+						deferred = true;
+						pend_pos = pend_score = true;
 					}
 				} else if (!parse_u32(cur, le, &pv)) {
 					pos[row] = 0;  // failed numeric extraction stores 0 and fails the stream
 					ok = false;
+					pend_pos = false;
 				} else {
 					pos[row] = pv;
+					pend_pos = false;
 				}
 				uint8_t st = ROW_STALE_SCORE;
 				double v = 0;
@@ -316,9 +330,17 @@ int main(int argc, char** argv) {
 						if (k == kScoreField) st = ROW_OK;
 					}
 				}
-				if (st == ROW_OK) score[row] = v;
-				else if (have_prev) score[row] = score[row - 1];
-				else if (c.head_fix.empty() || c.head_fix.back().first != row) c.head_fix.emplace_back(row, ROW_STALE_SCORE);
+				if (st == ROW_OK) {
+					score[row] = v;
+					pend_score = false;
+				} else if (!deferred) {
+					if (!pend_score) {
+						score[row] = score[row - 1];
+					} else {
+						c.head_fix.emplace_back(row, ROW_STALE_SCORE);
+						pend_score = true;
+					}
+				}
 				if (!prev_name || (size_t)(ne - s) != prev_len || memcmp(prev_name, s, prev_len) != 0) {
 					c.runs.push_back(ContigRun{std::string(s, ne), 0});
 					prev_name = s;
