@@ -172,7 +172,7 @@ static int parse_maf(const Input& in, Maf* m, const char* path) {
 	const char* nl = (const char*)memchr(in.data, '\n', in.size);
 	size_t begin = nl ? (size_t)(nl + 1 - in.data) : in.size;
 	size_t n_eff = begin + effective_size(in.data + begin, in.size - begin);
-	const unsigned nt = (n_eff - begin) < (1u << 20) ? 1 : parse_threads();
+	const unsigned nt = (n_eff - begin) < parallel_min_bytes() ? 1 : parse_threads();
 	std::vector<size_t> starts = chunk_starts(in.data, begin, n_eff, nt);
 	std::vector<MafChunk> chunks(starts.size() - 1);
 	for (size_t i = 0; i + 1 < starts.size(); ++i) {

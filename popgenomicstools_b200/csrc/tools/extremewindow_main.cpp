@@ -222,7 +222,7 @@ int main(int argc, char** argv) {
 	}
 #endif
 	const size_t text_end = columnar ? begin : in.size;  // columnar input: nothing to parse
-	const unsigned nt = (text_end - begin) < (1u << 20) ? 1 : parse_threads();
+	const unsigned nt = (text_end - begin) < parallel_min_bytes() ? 1 : parse_threads();
 	tm.threads = nt;
 	std::vector<size_t> starts = chunk_starts(in.data, begin, text_end, nt);
 	std::vector<Chunk> chunks(starts.size() - 1);

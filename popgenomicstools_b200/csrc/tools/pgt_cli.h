@@ -318,6 +318,13 @@ inline unsigned parse_threads() {
 	return n;
 }
 
+// inputs smaller than this are parsed on one thread (PGT_PARALLEL_MIN_BYTES overrides: the tests
+// use 1 to push tiny fuzzed files through the multi-chunk path)
+inline size_t parallel_min_bytes() {
+	const char* env = getenv("PGT_PARALLEL_MIN_BYTES");
+	return env ? (size_t)strtoull(env, nullptr, 10) : (size_t)(1u << 20);
+}
+
 inline void append_runs(std::vector<ContigRun>& dst, const std::vector<ContigRun>& src) {
 	for (const ContigRun& r : src) {
 		if (!dst.empty() && dst.back().name == r.name) dst.back().count += r.count;

@@ -105,7 +105,7 @@ int main(int argc, char** argv) {
 		}
 	}
 	const size_t n_eff = columnar ? 0 : effective_size(in.data, in.size);
-	const unsigned nt = n_eff < (1u << 20) ? 1 : parse_threads();
+	const unsigned nt = n_eff < parallel_min_bytes() ? 1 : parse_threads();
 	tm.threads = nt;
 	std::vector<size_t> starts = chunk_starts(in.data, 0, n_eff, nt);
 	std::vector<Chunk> chunks(starts.size() - 1);

@@ -13,6 +13,11 @@ import cli_util as U
 import oracle_lib as O
 from popgenomicstools_b200 import colfile
 
+import os
+
+SCALE = int(os.environ.get("PGT_FUZZ_SCALE", "1"))  # more iterations / other seeds for one-off soak runs
+SEED = int(os.environ.get("PGT_FUZZ_SEED", "0"))
+
 needs_ref = pytest.mark.skipif(O.ref_binary("ihsWindow") is None, reason="oracle/_ref not built")
 
 NUMS = ["0", "1", "-1", "+2.5", ".5", "-.25", "5.", "1e-3", "-1E2", "2.000000", "0.000001", "-0.0", "3.14159265358979", "123456.789",
@@ -54,12 +59,25 @@ def fuzz_norm_text(rng, tool):
     return head + "\n".join(lines) + ("\n" if rng.random() < 0.8 else "")
 
 
+# every test runs single-threaded and with three parser threads on tiny chunks (PGT_PARALLEL_MIN_BYTES=1), so
+# that chunk boundaries fall everywhere: rows that inherit values across a chunk boundary, runs of equal
+# names split between chunks, blank lines at chunk heads
+THREADS = [1, 3]
+
+
+def penv(threads, **kw):
+    e = {"PGT_THREADS": str(threads), "PGT_PARALLEL_MIN_BYTES": "1" if threads > 1 else "1048576"}
+    e.update({k: str(v) for k, v in kw.items()})
+    return e
+
+
 @needs_ref
+@pytest.mark.parametrize("threads", THREADS)
 @pytest.mark.parametrize("tool", ["ihsWindow", "xpehhWindow"])
-def test_norm_parsers_agree_with_the_reference(tool, tmp_path):
-    rng = np.random.default_rng(2026 if tool == "ihsWindow" else 2027)
+def test_norm_parsers_agree_with_the_reference(tool, threads, tmp_path):
+    rng = np.random.default_rng((2026 if tool == "ihsWindow" else 2027) + SEED)
     checked = 0
-    for it in range(150):
+    for it in range(150 * SCALE):
         text = fuzz_norm_text(rng, tool)
         (tmp_path / "f.norm").write_text(text)
         W = int(rng.choice([1, 7, 25, 100]))
@@ -67,7 +85,7 @@ def test_norm_parsers_agree_with_the_reference(tool, tmp_path):
         args = ["f.norm", "-winsize", W, "-cutoff", cutoff] if tool == "ihsWindow" else ["f.norm", cutoff, "-winsize", W]
         rc, out, err = O.run_ref(tool, args, cwd=tmp_path)
         assert rc == 0
-        prc, pout, perr = U.run(U.ours(tool), args, cwd=str(tmp_path), env={"PGT_PACK": str(tmp_path / "f.pgtc")})
+        prc, pout, perr = U.run(U.ours(tool), args, cwd=str(tmp_path), env=penv(threads, PGT_PACK=tmp_path / "f.pgtc"))
         assert (prc, pout) == (0, ""), (it, perr)
         c = colfile.read(tmp_path / "f.pgtc", mmap=False)
         if c["nsites"] == 0:
@@ -81,16 +99,17 @@ def test_norm_parsers_agree_with_the_reference(tool, tmp_path):
         rows = O.extreme_rows(r, [names[i] for i in range(len(names))])
         assert rows == out.splitlines(), (it, tool, args, text)
         checked += 1
-    assert checked > 100
+    assert checked > 100 * SCALE
 
 
 @needs_ref
+@pytest.mark.parametrize("threads", THREADS)
 @pytest.mark.parametrize("tool", ["fstWindow", "hetWindow"])
-def test_site_parsers_agree_with_the_reference(tool, tmp_path):
+def test_site_parsers_agree_with_the_reference(tool, threads, tmp_path):
     """Well-formed lines in every number syntax the stream extraction accepts; the first empty line
     ends the input (fstWindow.cpp:125)."""
-    rng = np.random.default_rng(77 if tool == "fstWindow" else 78)
-    for it in range(120):
+    rng = np.random.default_rng((77 if tool == "fstWindow" else 78) + SEED)
+    for it in range(120 * SCALE):
         lines, pos = [], 0
         chrs = ["ctgA", "ctgB", "c_3"]
         ci = 0
@@ -112,7 +131,7 @@ def test_site_parsers_agree_with_the_reference(tool, tmp_path):
         S = int(rng.integers(1, W + 1))
         rc, out, err = O.run_ref(tool, ["f.txt", W, S], cwd=tmp_path)
         assert rc == 0
-        prc, pout, perr = U.run(U.ours(tool), ["f.txt", W, S], cwd=str(tmp_path), env={"PGT_PACK": str(tmp_path / "f.pgtc")})
+        prc, pout, perr = U.run(U.ours(tool), ["f.txt", W, S], cwd=str(tmp_path), env=penv(threads, PGT_PACK=tmp_path / "f.pgtc"))
         assert (prc, pout) == (0, ""), (it, perr, lines)
         c = colfile.read(tmp_path / "f.pgtc", mmap=False)
         if c["nsites"] == 0:
@@ -130,12 +149,13 @@ def test_site_parsers_agree_with_the_reference(tool, tmp_path):
 
 
 @needs_ref
-def test_maf_parser_agrees_with_the_reference(tmp_path):
+@pytest.mark.parametrize("threads", THREADS)
+def test_maf_parser_agrees_with_the_reference(threads, tmp_path):
     """dxyWindow: both populations share the site list (the two-file sync is then the identity), fuzzed
     number syntax and white space in the 7-column MAF lines; -fixedsite 1 windows and the global line."""
-    rng = np.random.default_rng(4242)
+    rng = np.random.default_rng(4242 + SEED)
     freqs = ["0.000000", "1.000000", "0.5", ".25", "1e-05", "2.5E-1", "+0.125", "0.333333", "0.999999", "1", "0"]
-    for it in range(80):
+    for it in range(80 * SCALE):
         names = ["chr1", "chr2", "scaf_7"]
         lines1, lines2 = [], []
         ci, pos = 0, 0
@@ -159,7 +179,7 @@ def test_maf_parser_agrees_with_the_reference(tmp_path):
         rc, out, err = O.run_ref("dxyWindow", args, cwd=tmp_path)
         assert rc == 0
         prc, pout, perr = U.run(U.ours("dxyWindow"), args, cwd=str(tmp_path),
-                                env={"PGT_PACK": str(tmp_path / "p1.pgtc"), "PGT_PACK2": str(tmp_path / "p2.pgtc")})
+                                env=penv(threads, PGT_PACK=tmp_path / "p1.pgtc", PGT_PACK2=tmp_path / "p2.pgtc"))
         assert (prc, pout) == (0, ""), (it, perr)
         c1, c2 = colfile.read(tmp_path / "p1.pgtc", mmap=False), colfile.read(tmp_path / "p2.pgtc", mmap=False)
         assert c1["runs"] == c2["runs"] and np.array_equal(c1["columns"]["pos"], c2["columns"]["pos"])
