@@ -108,3 +108,57 @@ def test_random_shapes_against_the_oracle():
     finally:
         pgt.tune("level1", 0)
         pgt.tune("level2", 0)
+
+
+def test_bp_mode_clustered_positions_against_the_oracle():
+    """dxyWindow bp mode with very uneven SNP density: sparse chromosomes with dense stretches.  Tiles are
+    sized for the AVERAGE density, so a dense stretch overflows a tile's shared-memory capacity and is read
+    by the consumers straight from global memory (the `staged == false` path of k_units_tiled)."""
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import popgenomicstools_b200 as pgt
+    rng = np.random.default_rng(99 + SEED)
+    try:
+        for it in range(max(6, CASES // 6)):
+            nchr = int(rng.integers(1, 4))
+            chr_len, nsites, pos = [], [], []
+            for _ in range(nchr):
+                L = int(rng.integers(200_000, 1_500_000))
+                p = [rng.choice(np.arange(1, L + 1), size=int(rng.integers(50, 2000)), replace=False)]  # sparse background
+                for _ in range(int(rng.integers(1, 4))):  # dense stretches: every bp (or every 2nd) a site
+                    st = int(rng.integers(1, L - 30000))
+                    p.append(np.arange(st, st + int(rng.integers(3000, 25000)), int(rng.integers(1, 3))))
+                p = np.unique(np.concatenate(p))
+                p = p[p <= L]
+                chr_len.append(L)
+                nsites.append(len(p))
+                pos.extend(p.tolist())
+            soff = offsets(nsites)
+            ns = int(soff[-1])
+            W = int(rng.choice([100, 1000, 5000, 20000]))
+            S = int(rng.choice([max(1, W // 10), max(1, W // 4), W]))
+            unit = int(rng.choice([0, 0, 1024, 4096]))
+            seed = int(rng.integers(1, 1000))
+            f1, f2, n1, n2 = pgt.synth_dxy(seed, 0, ns)
+            pd = torch.from_numpy(np.asarray(pos, np.int64).astype(np.int32)).cuda().view(torch.uint32)
+            h = [np.asarray(pos, np.uint32)] + [x.cpu().numpy() for x in (f1, f2, n1, n2)]
+            ref = O.dxy(T.expand_chr(nsites), h[0], h[1], h[2], h[3], h[4], 5, W, S, 0, 0, chr_len)
+            plan = pgt.WindowPlan(offsets(chr_len), W, S, mode="bp", unit_sites=unit)
+            tag = f"case {it}: W={W} S={S} u={unit} chr_len={chr_len} nsites={nsites}"
+            assert plan.num_windows == len(ref["neff"]), tag
+            for l1 in (0, 2):
+                pgt.tune("level1", l1)
+                res = npy(pgt.dxy_window(plan, pd, f1, f2, n1, n2, minind=5, site_offsets=soff))
+                P.assert_exact(res["label"], ref["label"], tag)
+                P.assert_exact(res["start_pos"].astype(np.int64), ref["start"], tag)
+                P.assert_exact(res["end_pos"].astype(np.int64), ref["end"], tag)
+                P.assert_exact(res["neffective"], ref["neff"], tag + f" neff l1={l1}")
+                P.assert_exact(res["nskip"], ref["nskip"], tag + f" nskip l1={l1}")
+                P.assert_sum_close(res["dxy"], ref["dxy"], ref["dxy"], tag + f" dxy l1={l1}")
+            pgt.tune("level1", 0)
+            hres = pgt.dxy_window(plan, *h, minind=5, site_offsets=soff)
+            P.assert_exact(hres["neffective"], ref["neff"], tag + " host neff")
+            P.assert_sum_close(hres["dxy"], ref["dxy"], ref["dxy"], tag + " host dxy")
+    finally:
+        pgt.tune("level1", 0)
