@@ -17,6 +17,7 @@ KINDS = {
     "het": (2, (("pos", np.uint32), ("geno", np.int8))),
     "maf": (3, (("pos", np.uint32), ("freq", np.float64), ("nind", np.int32))),
     "score": (4, (("pos", np.uint32), ("score", np.float64))),
+    "dxy": (5, (("pos", np.uint32), ("f1", np.float64), ("f2", np.float64), ("n1", np.int32), ("n2", np.int32))),
 }
 _BY_ID = {v[0]: (k, v[1]) for k, v in KINDS.items()}
 _HEADER = struct.Struct("<8sIIQIIQQQQ")

@@ -20,6 +20,8 @@
 // Binary columnar cache (pgt_colfile.h): PGT_PACK=<pop1.pgtc> PGT_PACK2=<pop2.pgtc> parse the two MAFs,
 // write one cache per population and exit without touching the GPU; a `.pgtc` file given in place of
 // a MAF (magic sniff, next to the gzip sniff of dxyWindow.cpp:82-83) skips the parsing of that file.
+// PGT_PACK_SYNCED=<out.pgtc> writes the SYNCED site list of the two files (kind 5) and exits: the result of the
+// two-file sync state machine of dxyWindow.cpp:315-331, for inspection and for the CPU fuzz of that logic.
 #include <map>
 
 #include "pgt_cli.h"
@@ -331,7 +333,7 @@ int main(int argc, char** argv) {
 	DeviceWarmup warm;
 	const char* pack1 = getenv("PGT_PACK");
 	const char* pack2 = getenv("PGT_PACK2");
-	if (!pack1 && !pack2) warm.start();
+	if (!pack1 && !pack2 && !getenv("PGT_PACK_SYNCED")) warm.start();
 	if (parse_maf(in1, &m1, argv[argc - 2]) != 0) return -1;
 	if (parse_maf(in2, &m2, argv[argc - 1]) != 0) return -1;
 	if (pack1 || pack2) {  // write the binary columnar caches and stop: no GPU involved
@@ -409,6 +411,14 @@ int main(int argc, char** argv) {
 	const uint64_t n = pos.size();
 	tm.sites = n;
 	tm.parse_ms = now_ms() - t_start;
+	if (const char* synced = getenv("PGT_PACK_SYNCED")) {  // the synced site list as a kind-5 .pgtc, then stop (no GPU)
+		const void* cols[5] = {pos.data(), f1.data(), f2.data(), ni1.data(), ni2.data()};
+		if (pgtcol::write_file(synced, pgtcol::KIND_DXY, runs, n, cols) != 0) {
+			fprintf(stderr, "dxyWindow: cannot write %s\n", synced);
+			return -1;
+		}
+		return 0;
+	}
 
 	// ---- plan ---------------------------------------------------------------------------------
 	const double t_scan = now_ms();

@@ -15,6 +15,8 @@
 //                            2 het (pos u32, geno i8)             hetWindow.cpp:18
 //                            3 maf (pos u32, freq f64, nInd i32)  dxyWindow.cpp:24-32 (one population)
 //                            4 score (pos u32, score f64)         ihsWindow.cpp:119,160 / xpehhWindow.cpp:165
+//                            5 dxy (pos u32, f1 f64, f2 f64, n1 i32, n2 i32): the SYNCED sites of two MAFs, written by
+//                              dxyWindow with PGT_PACK_SYNCED=<out> (inspection / tests of the two-file sync, dxyWindow.cpp:315-331)
 //   16  uint64   nsites
 //   24  uint32   nruns       runs of equal chromosome name, in file order
 //   28  uint32   ncols
@@ -31,17 +33,18 @@
 
 namespace pgtcol {
 
-enum Kind : uint32_t { KIND_FST = 1, KIND_HET = 2, KIND_MAF = 3, KIND_SCORE = 4 };
+enum Kind : uint32_t { KIND_FST = 1, KIND_HET = 2, KIND_MAF = 3, KIND_SCORE = 4, KIND_DXY = 5 };
 static const char kMagic[8] = {'P', 'G', 'T', 'C', 'O', 'L', 1, '\n'};
 static const uint64_t kAlign = 4096;
 
 inline const uint32_t* elem_sizes(uint32_t kind, uint32_t* ncols) {
-	static const uint32_t fst[3] = {4, 8, 8}, het[2] = {4, 1}, maf[3] = {4, 8, 4}, score[2] = {4, 8};
+	static const uint32_t fst[3] = {4, 8, 8}, het[2] = {4, 1}, maf[3] = {4, 8, 4}, score[2] = {4, 8}, dxy[5] = {4, 8, 8, 4, 4};
 	switch (kind) {
 		case KIND_FST: *ncols = 3; return fst;
 		case KIND_HET: *ncols = 2; return het;
 		case KIND_MAF: *ncols = 3; return maf;
 		case KIND_SCORE: *ncols = 2; return score;
+		case KIND_DXY: *ncols = 5; return dxy;
 	}
 	*ncols = 0;
 	return nullptr;
@@ -112,7 +115,7 @@ struct View {
 	uint32_t kind = 0;
 	uint64_t nsites = 0;
 	std::vector<pgtcli::ContigRun> runs;
-	const void* col[4] = {nullptr, nullptr, nullptr, nullptr};
+	const void* col[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
 };
 
 // 0 ok; -1 malformed (err says why)

@@ -11,6 +11,7 @@ import pytest
 
 import cli_util as U
 import oracle_lib as O
+import textfmt as T
 from popgenomicstools_b200 import colfile
 
 import os
@@ -190,3 +191,56 @@ def test_maf_parser_agrees_with_the_reference(threads, tmp_path):
                   c2["columns"]["nind"], minind, W, S, 1)
         assert O.dxy_rows(r, [nm[i] for i in range(len(nm))]) == out.splitlines(), (it, args, lines1[:3])
         assert O.dxy_global_row(r) == err.strip(), (it, err)
+
+
+@needs_ref
+def test_dxy_two_file_sync_agrees_with_the_reference(tmp_path):
+    """The two-file sync state machine (dxyWindow.cpp:315-331: position-only catch-up, silent stop on
+    interleaved private sites, chromosomes present in one file only) on random pairs of site lists:
+    our synced site list (PGT_PACK_SYNCED, no GPU) -> oracle, against the reference's per-site rows."""
+    rng = np.random.default_rng(31337 + SEED)
+    head = "chromo\tposition\tmajor\tminor\tref\tknownEM\tnInd\n"
+    done = 0
+    for it in range(250 * SCALE):
+        chroms = [f"c{j}" for j in range(int(rng.integers(1, 4)))]
+        rows = [[], []]
+        for c in chroms:
+            base = np.unique(rng.integers(1, 60, size=int(rng.integers(1, 25))))
+            kind = rng.integers(0, 6)
+            sets = [base, base]
+            if kind == 1:    # pop2 lacks some sites
+                sets = [base, base[rng.random(len(base)) < 0.7]]
+            elif kind == 2:  # pop1 lacks some sites
+                sets = [base[rng.random(len(base)) < 0.7], base]
+            elif kind == 3:  # private sites on both sides (the reference stops silently there)
+                sets = [base[rng.random(len(base)) < 0.8], base[rng.random(len(base)) < 0.8]]
+            elif kind == 4 and len(chroms) > 1:  # chromosome missing from one file
+                sets = [base, base[:0]] if rng.random() < 0.5 else [base[:0], base]
+            for k in (0, 1):
+                for p in sets[k]:
+                    rows[k].append((c, int(p), int(rng.integers(0, 1000001)), int(rng.integers(0, 12))))
+        if not rows[0] or not rows[1]:
+            continue
+        for k in (0, 1):
+            (tmp_path / f"p{k + 1}.mafs").write_text(head + "".join(f"{c}\t{p}\tA\tC\tA\t{T.micro_str(f)}\t{n}\n" for c, p, f, n in rows[k]))
+        minind = int(rng.integers(1, 6))
+        args = ["-winsize", 1, "-stepsize", 1, "-minind", minind, "-fixedsite", 1, "p1.mafs", "p2.mafs"]
+        rc, out, err = O.run_ref("dxyWindow", args, cwd=tmp_path)
+        prc, pout, perr = U.run(U.ours("dxyWindow"), args, cwd=str(tmp_path), env={"PGT_PACK_SYNCED": str(tmp_path / "s.pgtc")})
+        if rc != 0:  # "Chromosomes in MAF files differ" on the first line: same message, same code
+            assert (prc, perr) == (rc, err), (it, rows)
+            continue
+        assert (prc, pout, perr) == (0, "", ""), (it, perr)
+        c = colfile.read(tmp_path / "s.pgtc", mmap=False)
+        if c["nsites"] == 0:
+            assert out == "", (it, rows)
+            continue
+        ids = ids_of(c["runs"])
+        chr_id = np.repeat(np.asarray(ids, np.uint32), [n for _, n in c["runs"]])
+        nm = {i: n for (n, _), i in zip(c["runs"], ids)}
+        cols = c["columns"]
+        r = O.dxy(chr_id, cols["pos"], cols["f1"], cols["f2"], cols["n1"], cols["n2"], minind, 1, 1, 1)
+        assert O.dxy_rows(r, [nm[i] for i in range(len(nm))]) == out.splitlines(), (it, rows)
+        assert O.dxy_global_row(r) == err.strip(), (it, err, rows)
+        done += 1
+    assert done > 150 * SCALE
