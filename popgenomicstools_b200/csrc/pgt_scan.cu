@@ -25,6 +25,7 @@
 #include <cstddef>
 #include <cstdio>
 #include <cstring>
+#include <mutex>
 #include <string>
 #include <thread>
 #include <vector>
@@ -95,13 +96,17 @@ struct ProfEvent {
 	cudaEvent_t a, b;
 	int kind;
 };
-static bool g_profile = false;
+static std::atomic<bool> g_profile{false};
+static std::mutex g_prof_mutex;  // scans may run from several host threads while profiling is on
 static std::vector<ProfEvent> g_prof_events;
 static double g_prof_ms[4] = {0, 0, 0, 0};
 static uint64_t g_prof_n[4] = {0, 0, 0, 0};
 
 bool pgt_profile_enabled() { return g_profile; }
-void pgt_profile_push(int kind, void* ev_a, void* ev_b) { g_prof_events.push_back(ProfEvent{(cudaEvent_t)ev_a, (cudaEvent_t)ev_b, kind}); }
+void pgt_profile_push(int kind, void* ev_a, void* ev_b) {
+	std::lock_guard<std::mutex> lk(g_prof_mutex);
+	g_prof_events.push_back(ProfEvent{(cudaEvent_t)ev_a, (cudaEvent_t)ev_b, kind});
+}
 
 struct ProfScope {
 	cudaStream_t st;
@@ -119,6 +124,7 @@ struct ProfScope {
 	~ProfScope() {
 		if (!on) return;
 		cudaEventRecord(ev.b, st);
+		std::lock_guard<std::mutex> lk(g_prof_mutex);
 		g_prof_events.push_back(ev);
 	}
 };
@@ -130,6 +136,7 @@ extern "C" int pgt_profile(int enable) {
 
 // synchronise all recorded events and fold them into the per-kind totals
 static int prof_drain() {
+	std::lock_guard<std::mutex> lk(g_prof_mutex);
 	for (ProfEvent& e : g_prof_events) {
 		float t = 0;
 		cudaError_t err = cudaEventSynchronize(e.b);
