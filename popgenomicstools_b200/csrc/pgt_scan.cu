@@ -176,8 +176,8 @@ extern "C" int pgt_profile_read_extreme(double* units_ms, uint64_t* units_launch
 static int g_tune_level1 = 0;
 static int g_tune_level2 = 0;
 static int g_tune_stages = 2;      // tiled kernel: shared-memory stages (2..4)
-static int g_tune_stage_kb = 110;
-extern int g_tune_xgroup;         // extreme scan (pgt_extreme.cu): lanes per unit, 0 = auto  // tiled kernel: bytes per stage (stages * stage_kb <= 224)
+static int g_tune_stage_kb = 110;  // tiled kernel: KB per stage (stages * stage_kb <= 224)
+extern int g_tune_xgroup;          // extreme scan (pgt_extreme.cu): lanes per unit, 0 = auto
 
 static int num_sms() {
 	int dev = 0, n = 0;
