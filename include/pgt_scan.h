@@ -238,6 +238,8 @@ int pgt_profile_read(double* units_ms, uint64_t* units_launches, double* windows
 /* Tuning knobs for tests and experiments (never needed for correct results):
  *   "level1": 0 auto | 1 direct warp-per-unit kernel (long units only) | 2 tiled TMA-staged kernel
  *   "level2": 0 auto | 1 always warp-per-window | 2 always scan mode (block prefix/suffix scans)
+ *   "hoststage": experiment, 0 off (default) | 1 PGT_MEM_HOST from pageable (unpinned) columns through a ring of
+ *                small pinned buffers filled by several host threads instead of the driver's pageable staging
  *   "stages", "stage_kb": shared-memory ring of the tiled kernel
  *   "xgroup": lanes per unit of the extreme scan's level 1 (pgt_extreme.h), 0 auto | 4 | 8 | 16 | 32 */
 int pgt_tune(const char* key, int value);

@@ -133,6 +133,11 @@ def load():
             fn = getattr(lib, name)  # AttributeError = header/library mismatch
             fn.restype = res
             fn.argtypes = args
+        # PGT_TUNE="key=value,..." applies pgt_tune knobs at load time (experiments and forced-path test runs)
+        for kv in filter(None, os.environ.get("PGT_TUNE", "").split(",")):
+            key, _, val = kv.partition("=")
+            if lib.pgt_tune(key.strip().encode(), int(val)) != 0:
+                raise ValueError(f"PGT_TUNE: unknown knob or value {kv!r}")
         _lib = lib
     return _lib
 

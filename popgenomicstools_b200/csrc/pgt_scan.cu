@@ -22,6 +22,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <condition_variable>
 #include <cstddef>
 #include <cstdio>
 #include <cstring>
@@ -178,6 +179,8 @@ static int g_tune_level2 = 0;
 static int g_tune_stages = 2;      // tiled kernel: shared-memory stages (2..4)
 static int g_tune_stage_kb = 110;  // tiled kernel: KB per stage (stages * stage_kb <= 224)
 extern int g_tune_xgroup;          // extreme scan (pgt_extreme.cu): lanes per unit, 0 = auto
+//   hoststage: PGT_MEM_HOST from pageable columns through the pinned ring (PinnedRing below): 0 off (default), 1 on
+static int g_tune_hoststage = 0;
 
 static int num_sms() {
 	int dev = 0, n = 0;
@@ -1381,6 +1384,7 @@ extern "C" size_t pgt_scan_workspace_bytes(const pgt_plan* plan, const pgt_range
 extern "C" int pgt_tune(const char* key, int value) {
 	if (key && strcmp(key, "level1") == 0) g_tune_level1 = value;
 	else if (key && strcmp(key, "level2") == 0 && value >= 0 && value <= 2) g_tune_level2 = value;
+	else if (key && strcmp(key, "hoststage") == 0 && value >= 0 && value <= 1) g_tune_hoststage = value;
 	else if (key && strcmp(key, "stages") == 0 && value >= 2 && value <= kTileMaxStages) g_tune_stages = value;
 	else if (key && strcmp(key, "stage_kb") == 0 && value >= 8 && value <= 110) g_tune_stage_kb = value;
 	else if (key && strcmp(key, "xgroup") == 0 && (value == 0 || value == 4 || value == 8 || value == 16 || value == 32)) g_tune_xgroup = value;
@@ -1656,6 +1660,125 @@ struct HostStreams {
 	}
 };
 
+// EXPERIMENT, off by default (pgt_tune "hoststage" = 1).  PGT_MEM_HOST from PAGEABLE columns (what the CLIs
+// pass: malloc'ed arrays, the mapping of a .pgtc file) runs at 11 GB/s against 54 GB/s from pinned memory
+// (tools/probe_pageable.py).  The ring stages the copy itself: pieces of a slab are copied into a few pinned
+// buffers by several host threads and sent from there, the memcpy of piece i+1 overlapping the DMA of piece i.
+// Measured (gpurun_out/pageable_ring.log, 1.6 GB per call): results identical, parity tests green with the
+// ring forced, but NOT faster (11.5 / 5.7 GB/s): pinning 64 MB per call and the VM's ~6 GB/s per-thread memcpy
+// eat the gain at that size.  A ring that pays needs pinned buffers that outlive the call (caller-owned, like
+// the device workspace); until that is built and measured the default path is the driver's staging.
+struct CopyPool {
+	std::vector<std::thread> th;
+	std::mutex m;
+	std::condition_variable cv_go, cv_done;
+	uint64_t gen = 0;
+	unsigned left = 0;
+	bool stop = false;
+	char* dst = nullptr;
+	const char* src = nullptr;
+	size_t bytes = 0;
+	static size_t cut(size_t n, unsigned p, unsigned parts) { return p >= parts ? n : (size_t)((unsigned __int128)n * p / parts) & ~(size_t)4095; }
+	void start(unsigned nworkers) {
+		for (unsigned i = 0; i < nworkers; ++i)
+			th.emplace_back([this, i, nworkers]() {
+				uint64_t seen = 0;
+				std::unique_lock<std::mutex> lk(m);
+				for (;;) {
+					cv_go.wait(lk, [&] { return stop || gen != seen; });
+					if (stop) return;
+					seen = gen;
+					char* d = dst;
+					const char* sp = src;
+					const size_t n = bytes;
+					lk.unlock();
+					const size_t lo = cut(n, i + 1, nworkers + 1), hi = cut(n, i + 2, nworkers + 1);
+					if (hi > lo) memcpy(d + lo, sp + lo, hi - lo);
+					lk.lock();
+					if (--left == 0) cv_done.notify_one();
+				}
+			});
+	}
+	void copy(char* d, const char* sp, size_t n) {  // returns when all n bytes are in place
+		if (th.empty() || n < (1u << 20)) {
+			memcpy(d, sp, n);
+			return;
+		}
+		const unsigned parts = (unsigned)th.size() + 1;
+		{
+			std::lock_guard<std::mutex> lk(m);
+			dst = d;
+			src = sp;
+			bytes = n;
+			left = (unsigned)th.size();
+			++gen;
+		}
+		cv_go.notify_all();
+		const size_t hi = cut(n, 1, parts);
+		if (hi) memcpy(d, sp, hi);  // the calling thread takes the first part
+		std::unique_lock<std::mutex> lk(m);
+		cv_done.wait(lk, [&] { return left == 0; });
+	}
+	~CopyPool() {
+		{
+			std::lock_guard<std::mutex> lk(m);
+			stop = true;
+		}
+		cv_go.notify_all();
+		for (auto& t : th) t.join();
+	}
+};
+
+struct PinnedRing {
+	static constexpr int kBufs = 4;
+	static constexpr size_t kBufBytes = (size_t)16 << 20;
+	char* buf[kBufs] = {nullptr, nullptr, nullptr, nullptr};
+	cudaEvent_t done[kBufs] = {nullptr, nullptr, nullptr, nullptr};
+	bool used[kBufs] = {false, false, false, false};
+	int next = 0;
+	bool ready = false;
+	CopyPool pool;
+	int init() {
+		for (int k = 0; k < kBufs; ++k) {
+			PGT_CUDA(cudaHostAlloc((void**)&buf[k], kBufBytes, cudaHostAllocDefault));
+			PGT_CUDA(cudaEventCreateWithFlags(&done[k], cudaEventDisableTiming));
+		}
+		const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+		pool.start(std::min(7u, hw - 1));  // + the calling thread
+		ready = true;
+		return PGT_OK;
+	}
+	// `bytes` from pageable `src` to device `dst` on stream `copy`; the source may be reused on return
+	int push(char* dst, const char* src, size_t bytes, cudaStream_t copy) {
+		for (size_t o = 0; o < bytes; o += kBufBytes) {
+			const size_t n = std::min(kBufBytes, bytes - o);
+			const int k = next;
+			next = (next + 1) % kBufs;
+			if (used[k]) PGT_CUDA(cudaEventSynchronize(done[k]));
+			pool.copy(buf[k], src + o, n);
+			PGT_CUDA(cudaMemcpyAsync(dst + o, buf[k], n, cudaMemcpyHostToDevice, copy));
+			PGT_CUDA(cudaEventRecord(done[k], copy));
+			used[k] = true;
+		}
+		return PGT_OK;
+	}
+	~PinnedRing() {
+		for (int k = 0; k < kBufs; ++k) {
+			if (buf[k]) cudaFreeHost(buf[k]);  // synchronises with the copies still in flight
+			if (done[k]) cudaEventDestroy(done[k]);
+		}
+	}
+};
+
+static bool host_pointer_is_pageable(const void* p) {
+	cudaPointerAttributes a;
+	if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+		cudaGetLastError();  // not an error of the scan: treat as pinned (plain cudaMemcpyAsync)
+		return false;
+	}
+	return a.type == cudaMemoryTypeUnregistered;
+}
+
 template <class Stat>
 static int run_scan(const pgt_plan* plan, const pgt_range* range, pgt_stat stat, const pgt_columns* cols, int minind,
                     const uint64_t* site_offsets, const pgt_windows* out, void* workspace, size_t workspace_bytes, pgt_mem mem,
@@ -1820,6 +1943,14 @@ static int run_scan(const pgt_plan* plan, const pgt_range* range, pgt_stat stat,
 				o += L.stage_col_bytes[i];
 			}
 	}
+	// experiment (pgt_tune "hoststage" = 1): pageable columns go through the pinned ring
+	PinnedRing ring;
+	bool via_ring[8] = {false, false, false, false, false, false, false, false};
+	if (g_tune_hoststage == 1) {
+		bool any = false;
+		for (int i = 0; i < ncol; ++i) any |= (via_ring[i] = host_pointer_is_pageable(cd[i].ptr));
+		if (any) PGT_TRY(ring.init());
+	}
 	const uint64_t slab_target = L.slab_sites - kSlabSlack;
 	const uint64_t axis_end = plan->off[0] + plan->nsites;
 	uint64_t ua = L.u_lo;
@@ -1844,9 +1975,9 @@ static int run_scan(const pgt_plan* plan, const pgt_range* range, pgt_stat stat,
 		memset(&C, 0, sizeof(C));
 		C.minind = minind;
 		for (int i = 0; i < ncol; ++i) {
-			if (ns)
-				PGT_CUDA(cudaMemcpyAsync(stage[slot][i], (const char*)cd[i].ptr + (s0 - L.origin) * cd[i].elem, ns * cd[i].elem,
-				                         cudaMemcpyHostToDevice, hs.copy));
+			const char* src = (const char*)cd[i].ptr + (s0 - L.origin) * cd[i].elem;
+			if (ns && via_ring[i]) PGT_TRY(ring.push(stage[slot][i], src, ns * cd[i].elem, hs.copy));
+			else if (ns) PGT_CUDA(cudaMemcpyAsync(stage[slot][i], src, ns * cd[i].elem, cudaMemcpyHostToDevice, hs.copy));
 			const void* p = stage[slot][i];
 			memcpy((char*)&C + cd[i].offset_in_cols, &p, sizeof(p));
 		}

@@ -431,6 +431,8 @@ inline int select_device() {
 		fprintf(stderr, "%s\n", pgt_last_error());
 		return -1;
 	}
+	// PGT_HOSTSTAGE=1: pgt_tune("hoststage") -- experimental pinned staging ring for the tools' pageable columns
+	if (const char* hs = getenv("PGT_HOSTSTAGE")) pgt_tune("hoststage", atoi(hs));
 	return 0;
 }
 

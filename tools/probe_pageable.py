@@ -22,7 +22,8 @@ for kind in ("pinned", "pageable"):
     cols[kind] = (p.numpy().view(np.uint32), a.numpy(), b.numpy())
 torch.cuda.synchronize()
 ref = None
-for kind in ("pinned", "pageable", "pinned", "pageable"):
+for kind, stage in (("pinned", 0), ("pageable", 0), ("pageable", 1), ("pinned", 0), ("pageable", 0), ("pageable", 1)):
+    pgt.tune("hoststage", stage)  # 0 = plain cudaMemcpyAsync from pageable memory (default), 1 = experimental pinned ring
     p, a, b = cols[kind]
     out = pgt.fst_window(plan, p, a, b)  # warm
     t0 = time.perf_counter()
@@ -32,4 +33,5 @@ for kind in ("pinned", "pageable", "pinned", "pageable"):
     s = np.asarray(out["sum_a"]).copy()
     if ref is None:
         ref = s
-    print(f"{kind:9s}: {n / dt:.3e} sites/s, {16 * n / dt / 1e9:.1f} GB/s H2D, identical={np.array_equal(s, ref)}", flush=True)
+    tag = kind + (" (pinned ring)" if stage == 1 else " (driver staging)" if kind == "pageable" else "")
+    print(f"{tag:26s}: {n / dt:.3e} sites/s, {16 * n / dt / 1e9:.1f} GB/s H2D, identical={np.array_equal(s, ref)}", flush=True)
