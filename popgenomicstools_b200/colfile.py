@@ -8,6 +8,8 @@ PGT_PACK=<out.pgtc> and accept it wherever the text file went.  numpy only; no G
 """
 import struct
 
+import os
+
 import numpy as np
 
 MAGIC = b"PGTCOL\x01\n"
@@ -56,12 +58,18 @@ def read(path, mmap=True):
         if magic != MAGIC or ver != 1 or kid not in _BY_ID:
             raise ValueError(f"{path}: not a .pgtc file (or unsupported version)")
         kind, spec = _BY_ID[kid]
+        size = os.fstat(f.fileno()).st_size
+        # same hostile-header checks as pgt_colfile.h open_view: no field may exceed the file before it is multiplied
+        if nbytes > size or nruns > size // 8 or n > size or data_off > size or data_off % 4096:
+            raise ValueError(f"{path}: corrupt header")
         counts = np.frombuffer(f.read(8 * nruns), dtype="<u8")
         names = f.read(nbytes).split(b"\0")[:nruns]
-    if len(spec) != ncols or int(counts.sum()) != n:
+    if len(spec) != ncols or len(counts) != nruns or sum(int(c) for c in counts) != n or (nruns and int(counts.min()) == 0):
         raise ValueError(f"{path}: corrupt header")
     cols, at = {}, data_off
     for name, dt in spec:
+        if at > size or n > (size - at) // np.dtype(dt).itemsize:
+            raise ValueError(f"{path}: truncated file")
         if mmap and n:
             cols[name] = np.memmap(path, dtype=dt, mode="r", offset=at, shape=(n,))
         else:

@@ -150,7 +150,12 @@ static bool fast_maf_line(const char* p, const char* le, const char** name_b, co
 }
 
 static int load_maf(const char* path, Maf* m, const char* which, Input* keep) {
-	if (read_input(path, keep, true) != 0) {
+	const int rc = read_input(path, keep, true);
+	if (rc == -2) {  // the reference dies here with boost's gzip_error (dxyWindow.cpp:256-278): never print partial rows
+		fprintf(stderr, "Corrupt or truncated gzip stream in %s MAF file: %s\n", which, path);
+		return -1;
+	}
+	if (rc != 0) {
 		fprintf(stderr, "Unable to open %s MAF file: %s\n", which, path);
 		return -1;
 	}

@@ -47,7 +47,8 @@ struct Input {
 	}
 };
 
-// 0 ok, -1 cannot open
+// 0 ok, -1 cannot open, -2 corrupt or truncated gzip stream (the reference aborts there with boost's
+// gzip_error, dxyWindow.cpp:256-278; partial rows must never be presented as a complete result)
 inline int read_input(const char* path, Input* in, bool allow_gzip) {
 	int fd = open(path, O_RDONLY);
 	if (fd < 0) return -1;
@@ -72,7 +73,8 @@ inline int read_input(const char* path, Input* in, bool allow_gzip) {
 				return -1;
 			}
 			in->map_size = in->size;
-			madvise(in->map, in->size, MADV_SEQUENTIAL | MADV_WILLNEED);
+			madvise(in->map, in->size, MADV_SEQUENTIAL);  // advice values are an enumeration, not flags: one call each
+			madvise(in->map, in->size, MADV_WILLNEED);
 			in->data = (const char*)in->map;
 		}
 		close(fd);
@@ -86,6 +88,7 @@ inline int read_input(const char* path, Input* in, bool allow_gzip) {
 		if (inflateInit2(&zs, 15 + 32) != Z_OK) return -1;
 		zs.next_in = (Bytef*)in->data;
 		size_t in_left = in->size, produced = 0;
+		bool complete = false;  // the last member ended with Z_STREAM_END and no input is left
 		for (;;) {
 			if (zs.avail_in == 0 && in_left) {
 				uInt c = (uInt)std::min<size_t>(in_left, 1u << 30);
@@ -99,7 +102,10 @@ inline int read_input(const char* path, Input* in, bool allow_gzip) {
 			int rc = inflate(&zs, Z_NO_FLUSH);
 			produced += room - zs.avail_out;
 			if (rc == Z_STREAM_END) {
-				if (zs.avail_in == 0 && in_left == 0) break;
+				if (zs.avail_in == 0 && in_left == 0) {
+					complete = true;
+					break;
+				}
 				inflateReset(&zs);  // concatenated members (bgzip)
 			} else if (rc != Z_OK && rc != Z_BUF_ERROR) {
 				break;
@@ -108,6 +114,7 @@ inline int read_input(const char* path, Input* in, bool allow_gzip) {
 			}
 		}
 		inflateEnd(&zs);
+		if (!complete) return -2;
 		out.resize(produced);
 		if (in->map) munmap(in->map, in->map_size);
 		in->map = nullptr;

@@ -132,6 +132,12 @@ inline int open_view(const char* d, size_t n, View* v, std::string* err) {
 		*err = "unsupported .pgtc version or kind";
 		return -1;
 	}
+	// every 64-bit header field is checked against the file size BEFORE it enters a product or a sum
+	// (a crafted nsites ~ 2^61 would wrap nsites * 8 to something small)
+	if (h.names_bytes > n || (uint64_t)h.nruns > n / 8 || h.nsites > n) {
+		*err = "corrupt .pgtc header";
+		return -1;
+	}
 	const uint64_t meta_end = sizeof(Header) + 8ull * h.nruns + h.names_bytes;
 	if (h.data_offset % kAlign || meta_end > h.data_offset || h.data_offset > n) {
 		*err = "corrupt .pgtc header";
@@ -146,7 +152,7 @@ inline int open_view(const char* d, size_t n, View* v, std::string* err) {
 		uint64_t cnt;
 		memcpy(&cnt, d + sizeof(Header) + 8ull * r, 8);
 		const char* z = names < names_end ? (const char*)memchr(names, 0, (size_t)(names_end - names)) : nullptr;
-		if (!z || cnt == 0) {
+		if (!z || cnt == 0 || cnt > h.nsites - total) {
 			*err = "corrupt .pgtc run table";
 			return -1;
 		}
@@ -160,6 +166,10 @@ inline int open_view(const char* d, size_t n, View* v, std::string* err) {
 	}
 	uint64_t at = h.data_offset;
 	for (uint32_t c = 0; c < ncols; ++c) {
+		if (at > n || h.nsites > (n - at) / es[c]) {
+			*err = "truncated .pgtc file";
+			return -1;
+		}
 		const uint64_t bytes = h.nsites * es[c];
 		if (at + bytes > n) {
 			*err = "truncated .pgtc file";

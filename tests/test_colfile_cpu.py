@@ -123,3 +123,66 @@ def test_wrong_kind_and_corrupt_files_are_refused(tmp_path):
     # re-packing a columnar file reproduces it byte for byte
     rc, so, se = U.run(U.ours("hetWindow"), ["h.pgtc"], cwd=str(tmp_path), env={"PGT_PACK": str(tmp_path / "h2.pgtc")})
     assert rc == 0 and (tmp_path / "h2.pgtc").read_bytes() == blob
+
+
+def test_truncated_or_corrupt_gzip_is_an_error_not_a_short_result(tmp_path):
+    """The reference aborts with boost's gzip_error on a damaged .mafs.gz (dxyWindow.cpp:256-278); a drop-in
+    must not print the rows it managed to inflate and exit 0."""
+    names, lengths = ["chr1"], [30000]
+    rng = np.random.default_rng(4)
+    pos = np.cumsum(rng.integers(1, 9, size=30000))
+    f, nn = rng.integers(0, 1000001, size=30000), rng.integers(0, 30, size=30000)
+    (tmp_path / "p1.mafs").write_text(T.maf_text(names, lengths, pos, f, nn))
+    with gzip.open(tmp_path / "ok.mafs.gz", "wt") as g:
+        g.write(T.maf_text(names, lengths, pos, f, nn))
+    blob = (tmp_path / "ok.mafs.gz").read_bytes()
+    (tmp_path / "cut.mafs.gz").write_bytes(blob[:len(blob) // 2])          # truncated member
+    (tmp_path / "notrailer.mafs.gz").write_bytes(blob[:-4])                # CRC/ISIZE trailer cut
+    bad = bytearray(blob)
+    bad[len(bad) // 2] ^= 0xff
+    (tmp_path / "flip.mafs.gz").write_bytes(bytes(bad))                    # corrupt deflate data / CRC mismatch
+    args = ["-winsize", 10, "-stepsize", 5, "-fixedsite", 1]
+    for name in ("cut.mafs.gz", "notrailer.mafs.gz", "flip.mafs.gz"):
+        out = tmp_path / (name + ".pgtc")
+        rc, so, se = U.run(U.ours("dxyWindow"), args + ["p1.mafs", name], cwd=str(tmp_path),
+                           env={"PGT_PACK": str(tmp_path / "a.pgtc"), "PGT_PACK2": str(out)})
+        assert rc == 255 and so == "" and "gzip" in se and not out.exists(), (name, rc, se)
+    # two concatenated members (bgzip style) are still one valid input
+    (tmp_path / "two.mafs.gz").write_bytes(gzip.compress(b"chromo\tposition\tmajor\tminor\tref\tknownEM\tnInd\n") +
+                                           gzip.compress(b"chr1\t5\tA\tC\tA\t0.25\t7\n"))
+    rc, so, se = U.run(U.ours("dxyWindow"), args + ["two.mafs.gz", "two.mafs.gz"], cwd=str(tmp_path),
+                       env={"PGT_PACK": str(tmp_path / "t1.pgtc"), "PGT_PACK2": str(tmp_path / "t2.pgtc")})
+    assert (rc, se) == (0, "") and colfile.read(tmp_path / "t2.pgtc")["columns"]["pos"].tolist() == [5]
+
+
+def test_hostile_pgtc_headers_are_refused(tmp_path):
+    """64-bit header fields that wrap when multiplied (nsites ~ 2^61, huge run counts / name blocks) must be
+    rejected by the C++ view and by the Python reader, not turned into out-of-bounds column pointers."""
+    import struct
+    colfile.write(tmp_path / "ok.pgtc", "fst", [("A", 4)], dict(pos=[1, 2, 3, 4], a=[.1, .2, .3, .4], b=[1, 1, 1, 1]))
+    blob = bytearray((tmp_path / "ok.pgtc").read_bytes())
+    hdr = struct.Struct("<8sIIQIIQQQQ")
+    magic, ver, kid, n, nruns, ncols, nbytes, data_off, r0, r1 = hdr.unpack(bytes(blob[:64]))
+
+    def variant(name, **kw):
+        f = dict(n=n, nruns=nruns, nbytes=nbytes, data_off=data_off)
+        f.update(kw)
+        b = bytearray(blob)
+        b[:64] = hdr.pack(magic, ver, kid, f["n"], f["nruns"], ncols, f["nbytes"], f["data_off"], r0, r1)
+        if "count0" in kw:
+            b[64:72] = struct.pack("<Q", kw["count0"])
+        (tmp_path / name).write_bytes(bytes(b))
+        return name
+
+    cases = [variant("wrap.pgtc", n=(1 << 61) + 4, count0=(1 << 61) + 4),   # nsites * 8 wraps to 32
+             variant("wrap2.pgtc", n=1 << 63, count0=1 << 63),
+             variant("names.pgtc", nbytes=(1 << 64) - 64 - 8 + 2),          # meta_end wraps
+             variant("runs.pgtc", nruns=(1 << 32) - 1),
+             variant("off.pgtc", data_off=1 << 40),
+             variant("count.pgtc", count0=(1 << 64) - 1)]                    # run counts wrap around to nsites
+    for name in cases:
+        rc, so, se = U.run(U.ours("fstWindow"), [name, 2, 1], cwd=str(tmp_path), env={"PGT_PACK": str(tmp_path / "o.pgtc")})
+        assert rc == 255 and so == "" and ("corrupt" in se or "truncated" in se), (name, rc, se)
+        assert not (tmp_path / "o.pgtc").exists()
+        with pytest.raises(ValueError):
+            colfile.read(tmp_path / name)
