@@ -197,6 +197,16 @@ typedef struct {
 	                          scan owns (all sites for an unsharded scan; dxyWindow.cpp:382-385) */
 } pgt_windows;
 
+/* Which kernels a scan of `stat` over this plan runs -- a function of (W, S, unit_sites, stat) only, never of
+ * the input size or the shard, because it fixes the summation order (DESIGN.md "Summation order"):
+ *   PGT_PATH_UNITS    level 1 (unit partials) + level 2 (window combine): every geometry with steps of >= 32 sites
+ *   PGT_PATH_SLIDE    fine steps under long windows (e.g. W = 1000, S = 1; what the reference does at
+ *                     fstWindow.cpp:80-99 per window): windows formed straight from the sites in shared memory
+ *   PGT_PATH_PERSITE  W = S = 1, the tools' default arguments: an elementwise map
+ * Returns the path (>= 0) or a negative pgt_status. */
+enum { PGT_PATH_UNITS = 0, PGT_PATH_SLIDE = 1, PGT_PATH_PERSITE = 2 };
+int pgt_plan_scan_path(const pgt_plan* plan, pgt_stat stat);
+
 /* Device scratch needed by a scan of `stat` over `range` with columns in `mem`. */
 size_t pgt_scan_workspace_bytes(const pgt_plan* plan, const pgt_range* range, pgt_stat stat, pgt_mem mem);
 
@@ -238,6 +248,7 @@ int pgt_profile_read(double* units_ms, uint64_t* units_launches, double* windows
 /* Tuning knobs for tests and experiments (never needed for correct results):
  *   "level1": 0 auto | 1 direct warp-per-unit kernel (long units only) | 2 tiled TMA-staged kernel
  *   "level2": 0 auto | 1 always warp-per-window | 2 always scan mode (block prefix/suffix scans)
+ *   "slide": 0 auto | 1 never use the sliding-tile kernel for fine steps | 2 use it for every site-mode geometry whose block fits shared memory (W <= 1417)
  *   "hoststage": experiment, 0 off (default) | 1 PGT_MEM_HOST from pageable (unpinned) columns through a ring of
  *                small pinned buffers filled by several host threads instead of the driver's pageable staging
  *   "stages", "stage_kb": shared-memory ring of the tiled kernel

@@ -78,6 +78,7 @@ PROTOTYPES = {
     "pgt_plan_shard": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, _u64p, _u64p, _u64p, _u64p]),
     "pgt_plan_device_bytes": (C.c_size_t, [C.c_void_p]),
     "pgt_plan_bind_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "pgt_plan_scan_path": (C.c_int, [C.c_void_p, C.c_int]),
     "pgt_scan_workspace_bytes": (C.c_size_t, [C.c_void_p, C.POINTER(PgtRange), C.c_int, C.c_int]),
     "pgt_scan": (C.c_int, [C.c_void_p, C.POINTER(PgtRange), C.c_int, C.POINTER(PgtColumns), C.c_int, C.c_void_p,
                            C.POINTER(PgtWindows), C.c_void_p, C.c_size_t, C.c_int, C.c_void_p]),

@@ -37,6 +37,8 @@ uint32_t pgt_plan_seg_of_unit(const pgt_plan* p, uint64_t j);
 uint64_t pgt_plan_unit_containing(const pgt_plan* p, uint64_t x);
 // global site/entry index where global unit j starts; j == nunits gives the end of the axis
 uint64_t pgt_plan_unit_start(const pgt_plan* p, uint64_t j);
+// largest wb in (w, w_hi] such that all windows [w, wb) end at or before global site `limit` (>= w + 1)
+uint64_t pgt_plan_windows_within(const pgt_plan* p, uint64_t w, uint64_t w_hi, uint64_t limit);
 // contig c with off[c] <= x < off[c+1]
 uint32_t pgt_plan_contig_of(const pgt_plan* p, uint64_t x);
 

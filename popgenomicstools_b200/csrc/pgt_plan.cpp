@@ -162,6 +162,27 @@ uint64_t pgt_plan_unit_start(const pgt_plan* p, uint64_t j) {
 	return sg.site_base + st;
 }
 
+// Largest wb in (w, w_hi] such that every window of [w, wb) ends at or before global site `limit`
+// (exclusive end); at least w + 1.  Window ends are non-decreasing in the window index.  O(#segments walked).
+uint64_t pgt_plan_windows_within(const pgt_plan* p, uint64_t w, uint64_t w_hi, uint64_t limit) {
+	uint64_t wb = w;
+	for (uint32_t si = pgt_plan_seg_of_window(p, w); si < p->segs.size() && wb < w_hi; ++si) {
+		const pgt_seg& sg = p->segs[si];
+		if (sg.nwin == 0 || sg.win_base + sg.nwin <= wb) continue;
+		if (sg.site_base + sg.nsites <= limit) {  // the whole segment fits
+			wb = sg.win_base + sg.nwin;
+			continue;
+		}
+		// full windows k with site_base + k*S + W <= limit; a trailing partial window ends at the segment end (> limit)
+		uint64_t nfit = 0;
+		if (limit >= sg.site_base + p->g.W) nfit = std::min<uint64_t>((limit - sg.site_base - p->g.W) / p->g.S + 1, sg.nfull);
+		wb = std::max(wb, sg.win_base + nfit);
+		break;
+	}
+	if (wb > w_hi) wb = w_hi;
+	return wb > w ? wb : w + 1;
+}
+
 extern "C" int pgt_plan_window(const pgt_plan* p, uint64_t w, uint64_t* first, uint64_t* last, uint32_t* label) {
 	if (!p) return pgt_set_error(PGT_ERR_ARGS, "pgt_plan_window: plan is NULL");
 	if (w >= p->nwin) return pgt_set_error(PGT_ERR_ARGS, "pgt_plan_window: window index out of range");

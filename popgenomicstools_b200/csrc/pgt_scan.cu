@@ -29,6 +29,7 @@
 #include <mutex>
 #include <string>
 #include <thread>
+#include <type_traits>
 #include <vector>
 
 #include "../../include/pgt_extreme.h"
@@ -180,6 +181,8 @@ static int g_tune_level2 = 0;
 static int g_tune_stages = 2;      // tiled kernel: shared-memory stages (2..4)
 static int g_tune_stage_kb = 110;  // tiled kernel: KB per stage (stages * stage_kb <= 224)
 extern int g_tune_xgroup;          // extreme scan (pgt_extreme.cu): lanes per unit, 0 = auto
+//   slide: 0 auto, 1 never use the sliding-tile kernel (k_slide), 2 use it whenever it fits shared memory (any W <= 1417)
+static int g_tune_slide = 0;
 //   hoststage: PGT_MEM_HOST from pageable columns through the pinned ring (PinnedRing below): 0 off (default), 1 on
 static int g_tune_hoststage = 0;
 
@@ -543,6 +546,65 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
 	             : "memory");
 }
 
+// Producer side of a stage (all 32 lanes of the producer warp; the caller has waited for the stage to
+// drain): lane c stages elements [s0, s1) of column c.  The bulk copy covers the 16-byte-aligned SUPERSET
+// of the slice whenever that stays inside the column (always, except at the first/last elements of a
+// column that is not 16-byte aligned/padded); only then are head/tail bytes copied by hand, so nothing
+// outside [column, column + valid_elems) is ever read.
+__device__ __forceinline__ void producer_fill_stage(const TileCfg& tc, TileCtl* ctl, unsigned char* stages, uint32_t stg, uint64_t s0,
+                                                    uint64_t s1, uint32_t lane) {
+	// generic-proxy reads of this stage are done; order them before the async-proxy writes
+	asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+	unsigned char* stage = stages + (size_t)stg * tc.stage_bytes;
+	const uint32_t c = lane < tc.ncol ? lane : 0u;
+	const char* A = tc.gcol[c] + s0 * tc.elem[c];
+	const uint64_t nbytes = (s1 - s0) * tc.elem[c];
+	const uint32_t pad = (uint32_t)((uintptr_t)A & 15u);
+	const bool staged = lane < tc.ncol && pad + nbytes + 16u <= tc.col_cap[c];
+	unsigned char* region = stage + tc.col_off[c];
+	const char* col_lo = tc.gcol[c];
+	const char* col_hi = tc.gcol[c] + tc.valid_elems * tc.elem[c];
+	const char* B0 = A - pad;  // aligned superset [B0, B1)
+	const char* B1 = (const char*)(((uintptr_t)(A + nbytes) + 15u) & ~(uintptr_t)15u);
+	uint32_t nh = 0, ntl = 0;
+	if (B0 < col_lo) {  // cannot read before the column: copy the head by hand
+		B0 += 16;
+		nh = 16u - pad;
+		if (nh > nbytes) nh = (uint32_t)nbytes;
+	}
+	if (B1 > col_hi) {  // cannot read past the column: copy the tail by hand
+		B1 -= 16;
+		ntl = (uint32_t)((A + nbytes) - B1);
+		if (B1 < A + nh) ntl = (uint32_t)(nbytes - nh);
+	}
+	uint32_t tx = (staged && B1 > B0) ? (uint32_t)(B1 - B0) : 0u;
+	if (lane < tc.ncol) ctl->cp[stg][c] = staged ? (const char*)(region + pad) : A;
+	uint32_t txsum = tx;
+#pragma unroll
+	for (int m = 16; m >= 1; m >>= 1) txsum += __shfl_xor_sync(0xffffffffu, txsum, m);
+	if (lane == 0) {
+		ctl->s0[stg] = s0;
+		mbar_arrive_expect_tx(&ctl->full[stg], txsum);
+	}
+	__syncwarp();
+	if (tx) bulk_g2s(region + pad + (B0 - A), B0, tx, &ctl->full[stg]);
+	// rare: hand-copied head / tail bytes
+	const uint32_t any = __ballot_sync(0xffffffffu, staged && (nh | ntl));
+	for (uint32_t cc = 0; cc < tc.ncol; ++cc) {
+		if (!((any >> cc) & 1u)) continue;
+		const uint32_t nh_c = __shfl_sync(0xffffffffu, nh, cc), nt_c = __shfl_sync(0xffffffffu, ntl, cc);
+		const uint32_t pad_c = __shfl_sync(0xffffffffu, pad, cc);
+		const unsigned long long A_c = __shfl_sync(0xffffffffu, (unsigned long long)(uintptr_t)A, cc);
+		const unsigned long long nb_c = __shfl_sync(0xffffffffu, (unsigned long long)nbytes, cc);
+		unsigned char* reg_c = stage + tc.col_off[cc];
+		const unsigned char* Ac = (const unsigned char*)(uintptr_t)A_c;
+		if (lane < nh_c) reg_c[pad_c + lane] = __ldg(Ac + lane);
+		if (lane < nt_c) reg_c[pad_c + (uint32_t)(nb_c - nt_c) + lane] = __ldg(Ac + (nb_c - nt_c) + lane);
+	}
+	__syncwarp();
+	if (lane == 0) mbar_arrive(&ctl->full[stg]);  // control words (and any head/tail bytes) are in place
+}
+
 // global site (entry) index where global unit j starts / ends
 __device__ __forceinline__ uint64_t unit_bounds_global(const DevPlan& P, uint64_t j, uint64_t* end) {
 	const pgt_seg sg = P.segs[find_seg<true>(P, j)];
@@ -555,6 +617,52 @@ __device__ __forceinline__ uint64_t unit_bounds_global(const DevPlan& P, uint64_
 __global__ void __launch_bounds__(256) k_tile_segs(DevPlan P, uint32_t m, uint64_t ntiles, uint32_t* __restrict__ tile_seg) {
 	const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
 	if (t < ntiles) tile_seg[t] = find_seg<true>(P, P.unit_lo + t * m);
+}
+
+// hetWindow's 1-byte genotype column inside the tiled kernel: a warp reduces one unit from the staged tile
+// with 16-byte loads + byte-SIMD compare / popc (the generic per-site loop would need one load per byte).
+// The staged copy keeps the column's alignment modulo 16, so the aligned chunks are the same in shared
+// memory and -- for a slice that was too long to stage -- in global memory (generic loads serve both).
+// Integer counts: independent of the order, identical to the per-site fold.
+__device__ __forceinline__ void het_count_word(uint32_t w, uint32_t& nonmissing, uint32_t& nhet) {
+	nonmissing += __popc(~w & 0x80808080u);                 // g >= 0  (hetWindow.cpp:78)
+	nhet += __popc(__vcmpeq4(w, 0x01010101u) & 0x01010101u);  // g == 1 (hetWindow.cpp:80)
+}
+__device__ __forceinline__ void het_unit_from_tile(HetStat::Acc& acc, const char* col, uint32_t rel, uint32_t len, uint32_t lane) {
+	const int8_t* A = (const int8_t*)col + rel;
+	const int8_t* E = A + len;
+	const int8_t* A0 = (const int8_t*)(((uintptr_t)A + 15u) & ~(uintptr_t)15u);  // first aligned chunk inside
+	const int8_t* A1 = (const int8_t*)((uintptr_t)E & ~(uintptr_t)15u);          // end of the last aligned chunk
+	uint32_t nonmissing = 0, nhet = 0;
+	if (A1 > A0) {
+		const uint32_t nch = (uint32_t)(A1 - A0) >> 4;
+		for (uint32_t c = lane; c < nch; c += 32u) {
+			const uint4 v = *(reinterpret_cast<const uint4*>(A0) + c);
+			het_count_word(v.x, nonmissing, nhet);
+			het_count_word(v.y, nonmissing, nhet);
+			het_count_word(v.z, nonmissing, nhet);
+			het_count_word(v.w, nonmissing, nhet);
+		}
+		const uint32_t nh = (uint32_t)(A0 - A), nt = (uint32_t)(E - A1);  // < 16 each
+		if (lane < nh) {
+			const int g = A[lane];
+			nonmissing += (g >= 0);
+			nhet += (g == 1);
+		}
+		if (lane >= 16u && lane - 16u < nt) {
+			const int g = A1[lane - 16u];
+			nonmissing += (g >= 0);
+			nhet += (g == 1);
+		}
+	} else {
+		for (uint32_t x = lane; x < len; x += 32u) {  // < 32 bytes without an aligned chunk
+			const int g = A[x];
+			nonmissing += (g >= 0);
+			nhet += (g == 1);
+		}
+	}
+	acc.nonmissing += nonmissing;
+	acc.nhet += nhet;
 }
 
 template <class Stat, int G, bool INDIRECT>
@@ -626,56 +734,7 @@ __global__ void __launch_bounds__(kTileThreads, 1)
 				s1 = e - P.site_origin;
 			}
 			if (it >= tc.nstages) mbar_wait(&ctl->empty[stg], ((it / tc.nstages) - 1u) & 1u);
-			// generic-proxy reads of this stage are done; order them before the async-proxy writes
-			asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-			unsigned char* stage = stages + (size_t)stg * tc.stage_bytes;
-			const uint32_t c = lane < tc.ncol ? lane : 0u;
-			const char* A = tc.gcol[c] + s0 * tc.elem[c];
-			const uint64_t nbytes = (s1 - s0) * tc.elem[c];
-			const uint32_t pad = (uint32_t)((uintptr_t)A & 15u);
-			const bool staged = lane < tc.ncol && pad + nbytes + 16u <= tc.col_cap[c];
-			unsigned char* region = stage + tc.col_off[c];
-			const char* col_lo = tc.gcol[c];
-			const char* col_hi = tc.gcol[c] + tc.valid_elems * tc.elem[c];
-			const char* B0 = A - pad;  // aligned superset [B0, B1)
-			const char* B1 = (const char*)(((uintptr_t)(A + nbytes) + 15u) & ~(uintptr_t)15u);
-			uint32_t nh = 0, ntl = 0;
-			if (B0 < col_lo) {  // cannot read before the column: copy the head by hand
-				B0 += 16;
-				nh = 16u - pad;
-				if (nh > nbytes) nh = (uint32_t)nbytes;
-			}
-			if (B1 > col_hi) {  // cannot read past the column: copy the tail by hand
-				B1 -= 16;
-				ntl = (uint32_t)((A + nbytes) - B1);
-				if (B1 < A + nh) ntl = (uint32_t)(nbytes - nh);
-			}
-			uint32_t tx = (staged && B1 > B0) ? (uint32_t)(B1 - B0) : 0u;
-			if (lane < tc.ncol) ctl->cp[stg][c] = staged ? (const char*)(region + pad) : A;
-			uint32_t txsum = tx;
-#pragma unroll
-			for (int m = 16; m >= 1; m >>= 1) txsum += __shfl_xor_sync(0xffffffffu, txsum, m);
-			if (lane == 0) {
-				ctl->s0[stg] = s0;
-				mbar_arrive_expect_tx(&ctl->full[stg], txsum);
-			}
-			__syncwarp();
-			if (tx) bulk_g2s(region + pad + (B0 - A), B0, tx, &ctl->full[stg]);
-			// rare: hand-copied head / tail bytes
-			const uint32_t any = __ballot_sync(0xffffffffu, staged && (nh | ntl));
-			for (uint32_t cc = 0; cc < tc.ncol; ++cc) {
-				if (!((any >> cc) & 1u)) continue;
-				const uint32_t nh_c = __shfl_sync(0xffffffffu, nh, cc), nt_c = __shfl_sync(0xffffffffu, ntl, cc);
-				const uint32_t pad_c = __shfl_sync(0xffffffffu, pad, cc);
-				const unsigned long long A_c = __shfl_sync(0xffffffffu, (unsigned long long)(uintptr_t)A, cc);
-				const unsigned long long nb_c = __shfl_sync(0xffffffffu, (unsigned long long)nbytes, cc);
-				unsigned char* reg_c = stage + tc.col_off[cc];
-				const unsigned char* Ac = (const unsigned char*)(uintptr_t)A_c;
-				if (lane < nh_c) reg_c[pad_c + lane] = __ldg(Ac + lane);
-				if (lane < nt_c) reg_c[pad_c + (uint32_t)(nb_c - nt_c) + lane] = __ldg(Ac + (nb_c - nt_c) + lane);
-			}
-			__syncwarp();
-			if (lane == 0) mbar_arrive(&ctl->full[stg]);  // control words (and any head/tail bytes) are in place
+			producer_fill_stage(tc, ctl, stages, stg, s0, s1, lane);
 		}
 	} else {
 		// ------------------------------------------------------------------ consumers
@@ -734,7 +793,11 @@ __global__ void __launch_bounds__(kTileThreads, 1)
 				}
 				if (!active) len = 0;
 				typename Stat::Acc acc = Stat::zero();
-				for (uint32_t x = gl; x < len; x += G) Stat::fold(acc, Stat::load_tile(cp, rel + x), tc.minind);
+				if constexpr (std::is_same<Stat, HetStat>::value && G == 32) {
+					het_unit_from_tile(acc, cp[0], rel, len, lane);
+				} else {
+					for (uint32_t x = gl; x < len; x += G) Stat::fold(acc, Stat::load_tile(cp, rel + x), tc.minind);
+				}
 				acc = group_butterfly<Stat, G>(acc);
 				if (active && gl == 0) units[j - P.unit_lo] = acc;
 			}
@@ -748,10 +811,6 @@ __global__ void __launch_bounds__(kTileThreads, 1)
 // (LDG.128) and count with byte-SIMD + popc; the partial chunks at the two ends of the unit are
 // read byte by byte, so nothing outside [unit start, unit end) is touched.  Integer counts: the
 // result is independent of the order, identical to the generic kernels.
-__device__ __forceinline__ void het_count_word(uint32_t w, uint32_t& nonmissing, uint32_t& nhet) {
-	nonmissing += __popc(~w & 0x80808080u);                 // g >= 0  (hetWindow.cpp:78)
-	nhet += __popc(__vcmpeq4(w, 0x01010101u) & 0x01010101u);  // g == 1 (hetWindow.cpp:80)
-}
 // volatile asm: the eight loads of a round stay back to back (the compiler otherwise interleaves
 // them with the counting and keeps only ~3 in flight)
 __device__ __forceinline__ uint4 ldg_stream_u4(const uint4* p) {
@@ -1144,6 +1203,230 @@ __global__ void __launch_bounds__(256) k_windows_hgw(DevPlan P, const typename S
 	}
 }
 
+
+// ----------------------------------------------------------------------------- fine steps: sliding tile
+//
+// W = 1000, S = 1 and its kin: steps so short that a "unit" would be a handful of sites (pgt_geom.h:
+// units never span a step), so the two-level scheme degenerates into copying every site into the unit
+// array and scanning that array twice in global memory (~3x the compulsory traffic).  Here the windows
+// are formed straight from the sites, in shared memory, and no unit array exists:
+//
+//   * the site axis of a segment is cut into BLOCKS of W sites from the segment origin; window k
+//     (first site f = k*S, last site l) touches block m = f div W and at most block m + 1, so
+//         window = SUF_m[f mod W] (+ PRE_{m+1}[l mod W] when l is in block m + 1)
+//     with PRE / SUF the inclusive prefix / suffix sums inside a block (van Herk / Gil-Werman): only
+//     additions of true partial sums, no differences, no cancellation;
+//   * persistent CTAs take CHUNKS of consecutive windows; a chunk walks its blocks in order: the
+//     producer warp stages block b's slice of every column with bulk async copies (the ring of
+//     k_units_tiled), the 256 consumer threads scan it in registers (thread t owns elements
+//     [t*E, (t+1)*E), E = ceil(W / 256): forward total, two warp shuffle scans, warp totals through
+//     shared memory, then PRE running forward from the thread's base into `Pr` and SUF running backward
+//     in place), emit the windows that start in block b - 1 from Sf (= SUF_{b-1}) and Pr, and keep
+//     SUF_b for the next step.  Every site is read once per chunk; neighbouring chunks share W - S sites.
+//
+// Summation order: a pure function of (W, S) and the position of a site inside its block -- not of
+// chunks, CTAs, stages or shards (a chunk that starts or ends inside a block simply has the sites
+// outside its windows absent, and those only ever enter prefix / suffix values no window of the chunk
+// reads), so results are bit-identical for any GPU count.  Reference semantics: fstWindow.cpp:80-99.
+
+static constexpr int kSlideWarps = 8;                          // consumer warps
+static constexpr int kSlideConsumers = kSlideWarps * 32;       // part of the summation order (E = ceil(W / 256))
+static constexpr int kSlideThreads = kSlideConsumers + 32;     // + the producer warp (the last one)
+static constexpr uint32_t kSlideMaxE = 6;                      // W <= 1536 (and the fused block must fit shared memory: W <= 1417)
+static constexpr uint32_t kSlideWtBytes = 512;                 // warp totals: 8 x Acc (<= 40 B)
+
+struct SlideCfg {
+	uint32_t E;              // elements of a block per consumer thread
+	uint32_t sf_off, pr_off, stage_off;  // byte offsets inside the dynamic shared memory
+	uint64_t chunk_windows;  // windows per chunk
+	uint64_t nchunks;
+};
+
+template <class Acc>
+__device__ __forceinline__ Acc shfl_down_acc(const Acc& v, unsigned delta) {
+	static_assert(sizeof(Acc) % 4 == 0, "Acc is made of 32-bit words");
+	uint32_t w[sizeof(Acc) / 4];
+	memcpy(w, &v, sizeof(Acc));
+#pragma unroll
+	for (unsigned i = 0; i < sizeof(Acc) / 4; ++i) w[i] = __shfl_down_sync(0xffffffffu, w[i], delta);
+	Acc r;
+	memcpy(&r, w, sizeof(Acc));
+	return r;
+}
+
+__device__ __forceinline__ void slide_bar() { asm volatile("bar.sync 1, %0;" ::"n"(kSlideConsumers) : "memory"); }
+
+// the part of a chunk that lies in one segment: windows [ka, kb) of segment `sg` (segment-local), reading
+// the segment-local sites [lo, hi)
+struct SlideRun {
+	pgt_seg sg;
+	uint32_t si;
+	uint64_t ka, kb, lo, hi;
+};
+// first run of the chunk [wa, wb) / the run after `r`; false when the chunk is exhausted
+__device__ __forceinline__ bool slide_run_at(const DevPlan& P, uint64_t w, uint64_t wb, SlideRun& r, bool first) {
+	if (w >= wb) return false;
+	if (first) {
+		r.si = find_seg<false>(P, w);
+		r.sg = P.segs[r.si];
+	}
+	while (w - r.sg.win_base >= r.sg.nwin) {  // also skips segments without windows
+		++r.si;
+		r.sg = P.segs[r.si];
+	}
+	r.ka = w - r.sg.win_base;
+	r.kb = wb - r.sg.win_base < r.sg.nwin ? wb - r.sg.win_base : r.sg.nwin;
+	r.lo = r.ka * P.g.S;
+	const uint64_t e = (r.kb - 1) * P.g.S + P.g.W;
+	r.hi = e < r.sg.nsites ? e : r.sg.nsites;
+	return true;
+}
+
+template <class Stat, int EMAX>
+__global__ void __launch_bounds__(kSlideThreads) k_slide(DevPlan P, TileCfg tc, SlideCfg sc, const uint32_t* __restrict__ pos, pgt_windows out) {
+	typedef typename Stat::Acc Acc;
+	extern __shared__ __align__(128) unsigned char smem[];
+	TileCtl* ctl = reinterpret_cast<TileCtl*>(smem);
+	Acc* wt = reinterpret_cast<Acc*>(smem + kTileCtlBytes);
+	Acc* Sf = reinterpret_cast<Acc*>(smem + sc.sf_off);
+	Acc* Pr = reinterpret_cast<Acc*>(smem + sc.pr_off);
+	unsigned char* stages = smem + sc.stage_off;
+	const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+	const uint64_t W = P.g.W, S = P.g.S;
+
+	if (threadIdx.x == 0) {
+		for (uint32_t s = 0; s < tc.nstages; ++s) {
+			mbar_init(&ctl->full[s], 2);
+			mbar_init(&ctl->empty[s], kSlideWarps);
+		}
+		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+	}
+	__syncthreads();
+
+	if (warp == kSlideWarps) {
+		// ------------------------------------------------------------------ producer: one stage per block
+		uint32_t it = 0;
+		for (uint64_t c = blockIdx.x; c < sc.nchunks; c += gridDim.x) {
+			const uint64_t wa = P.win_lo + c * sc.chunk_windows;
+			const uint64_t wb = P.win_hi - wa < sc.chunk_windows ? P.win_hi : wa + sc.chunk_windows;
+			SlideRun r;
+			for (bool ok = slide_run_at(P, wa, wb, r, true); ok; ok = slide_run_at(P, r.sg.win_base + r.kb, wb, r, false)) {
+				for (uint64_t b = r.lo / W; b * W < r.hi; ++b, ++it) {
+					const uint64_t x0 = b * W > r.lo ? b * W : r.lo;
+					const uint64_t x1 = (b + 1) * W < r.hi ? (b + 1) * W : r.hi;
+					const uint32_t stg = it % tc.nstages;
+					if (it >= tc.nstages) mbar_wait(&ctl->empty[stg], ((it / tc.nstages) - 1u) & 1u);
+					producer_fill_stage(tc, ctl, stages, stg, r.sg.site_base + x0 - P.site_origin, r.sg.site_base + x1 - P.site_origin, lane);
+				}
+			}
+		}
+		return;
+	}
+
+	// ---------------------------------------------------------------------- consumers
+	const uint32_t t = threadIdx.x;
+	const uint32_t e0 = t * sc.E;  // first element of a block this thread owns
+	uint32_t it = 0;
+	for (uint64_t c = blockIdx.x; c < sc.nchunks; c += gridDim.x) {
+		const uint64_t wa = P.win_lo + c * sc.chunk_windows;
+		const uint64_t wb = P.win_hi - wa < sc.chunk_windows ? P.win_hi : wa + sc.chunk_windows;
+		SlideRun r;
+		for (bool ok = slide_run_at(P, wa, wb, r, true); ok; ok = slide_run_at(P, r.sg.win_base + r.kb, wb, r, false)) {
+			const uint64_t m_first = r.lo / W, m_last = (r.hi - 1) / W;
+			for (uint64_t b = m_first; b <= m_last + 1; ++b) {
+				const bool incoming = b <= m_last;  // block b arrives; the windows starting in block b - 1 leave
+				Acc leaf[EMAX];
+				Acc up = Stat::zero(), dn = Stat::zero();
+				if (incoming) {
+					const uint32_t stg = it % tc.nstages;
+					mbar_wait(&ctl->full[stg], (it / tc.nstages) & 1u);
+					++it;
+					const char* cp[kMaxTileCols];
+#pragma unroll
+					for (int cc = 0; cc < kMaxTileCols; ++cc) cp[cc] = ctl->cp[stg][cc];
+					const uint64_t x0 = b * W > r.lo ? b * W : r.lo;
+					const uint64_t x1 = (b + 1) * W < r.hi ? (b + 1) * W : r.hi;
+					// sites of the block outside [x0, x1) are absent (other chunk / beyond the segment): +0 leaves
+					const uint32_t i_lo = (uint32_t)(x0 - b * W), i_hi = (uint32_t)(x1 - b * W);
+					Acc tot = Stat::zero();
+#pragma unroll
+					for (int e = 0; e < EMAX; ++e) {
+						leaf[e] = Stat::zero();
+						const uint32_t i = e0 + (uint32_t)e;
+						if ((uint32_t)e < sc.E && i >= i_lo && i < i_hi) Stat::fold(leaf[e], Stat::load_tile(cp, i - i_lo), tc.minind);
+						Stat::add(tot, leaf[e]);
+					}
+					__syncwarp();
+					if (lane == 0) mbar_arrive(&ctl->empty[stg]);  // the block now lives in registers
+					up = tot;
+					dn = tot;
+#pragma unroll
+					for (unsigned d = 1; d < 32; d <<= 1) {
+						Acc o = shfl_up_acc(up, d);
+						if (lane >= d) {  // earlier threads first
+							Stat::add(o, up);
+							up = o;
+						}
+						Acc q = shfl_down_acc(dn, d);
+						if (lane + d < 32u) {  // later threads first
+							Stat::add(q, dn);
+							dn = q;
+						}
+					}
+					if (lane == 31u) wt[warp] = up;  // the warp's total, forward order
+				}
+				slide_bar();  // warp totals visible
+				if (incoming) {
+					Acc bpre = Stat::zero(), bsuf = Stat::zero();
+					for (uint32_t w2 = 0; w2 < warp; ++w2) Stat::add(bpre, wt[w2]);
+					for (uint32_t w2 = kSlideWarps - 1; w2 > warp; --w2) Stat::add(bsuf, wt[w2]);
+					Acc xu = shfl_up_acc(up, 1), xd = shfl_down_acc(dn, 1);
+					if (lane == 0) xu = Stat::zero();
+					if (lane == 31u) xd = Stat::zero();
+					Stat::add(bpre, xu);
+					Stat::add(bsuf, xd);
+#pragma unroll
+					for (int e = 0; e < EMAX; ++e) {  // PRE: running forward from everything before this thread
+						if ((uint32_t)e < sc.E && e0 + (uint32_t)e < (uint32_t)W) {
+							Stat::add(bpre, leaf[e]);
+							Pr[e0 + e] = bpre;
+						}
+					}
+#pragma unroll
+					for (int e = EMAX - 1; e >= 0; --e) {  // SUF: running backward from everything after it, kept in registers
+						if ((uint32_t)e < sc.E && e0 + (uint32_t)e < (uint32_t)W) {
+							Stat::add(bsuf, leaf[e]);
+							leaf[e] = bsuf;
+						}
+					}
+				}
+				slide_bar();  // Pr complete (Sf holds SUF of block b - 1)
+				if (b > m_first) {
+					const uint64_t mb = b - 1;
+					uint64_t k_lo = (mb * W + S - 1) / S, k_hi = (b * W + S - 1) / S;  // windows with mb*W <= k*S < b*W
+					if (k_lo < r.ka) k_lo = r.ka;
+					if (k_hi > r.kb) k_hi = r.kb;
+					for (uint64_t k = k_lo + t; k < k_hi; k += kSlideConsumers) {
+						const uint64_t f = k * S;
+						uint64_t l = f + W - 1;
+						if (l > r.sg.nsites - 1) l = r.sg.nsites - 1;
+						Acc acc = Sf[f - mb * W];
+						if (l >= b * W) Stat::add(acc, Pr[l - b * W]);
+						emit_window<Stat>(P, r.sg, r.sg.win_base + k, k, acc, pos, out);
+					}
+				}
+				slide_bar();  // Sf no longer read
+				if (incoming) {
+#pragma unroll
+					for (int e = 0; e < EMAX; ++e)
+						if ((uint32_t)e < sc.E && e0 + (uint32_t)e < (uint32_t)W) Sf[e0 + e] = leaf[e];
+				}
+			}
+		}
+	}
+}
+
+
 // dxyWindow's global line (dxyWindow.cpp:382-385,429-433) over the unit partials [0, n): one
 // block; thread t adds partials t, t+1024, ...; warp butterflies; counts in 64 bit.
 template <class Stat>
@@ -1212,6 +1495,23 @@ __global__ void __launch_bounds__(kGlobalBlocks) k_global_final(const double* __
 	                    (unsigned long long)partial3[3 * threadIdx.x + 2], global3);
 }
 
+// dxyWindow's global line when no unit array exists (sliding-tile and per-site scans): thread t of
+// block b folds sites i0 + b*1024 + t + k*(256*1024) of the owned range [i0, i1) (column element
+// indices) in that order, then the block reductions of k_global_partial.  Classification as
+// DxyStat::fold (dxyWindow.cpp:179-186).
+__global__ void __launch_bounds__(1024) k_global_sites(Cols cols, uint64_t i0, uint64_t i1, double* __restrict__ partial3) {
+	double d = 0.0;
+	unsigned long long ne = 0, nk = 0;
+	for (uint64_t i = i0 + (uint64_t)blockIdx.x * 1024u + threadIdx.x; i < i1; i += (uint64_t)kGlobalBlocks * 1024u) {
+		DxyStat::Acc a = DxyStat::zero();
+		DxyStat::fold(a, DxyStat::load(cols, i), cols.minind);
+		d = __dadd_rn(d, a.dxy);
+		ne += a.neff;
+		nk += a.nskip;
+	}
+	block_reduce_global(d, ne, nk, partial3 + 3 * blockIdx.x);
+}
+
 // ----------------------------------------------------------------------------- host side of a scan
 
 static const uint64_t kSlabSites = 1ull << 22;  // PGT_MEM_HOST: sites (entries) staged per slab
@@ -1256,10 +1556,75 @@ struct Layout {
 	size_t segs_off, off_off, siteoff_off, gpart_off, units_off, pre_off, bounds_off, stage_off, outs_off, tileseg_off, total;
 	uint64_t tileseg_cap;   // entries of the tile -> segment table (0 = not used: few segments)
 	bool hgw;               // level 2 in scan mode
+	bool slide;             // fine steps: windows straight from the sites (k_slide), no unit array
+	bool persite;           // W = S = 1: elementwise (k_windows_persite), no unit array
+	uint32_t slide_stages;
+	size_t slide_smem;
+	uint64_t gsite_lo, gsite_hi;  // global sites this scan owns for dxyWindow's global line
+	size_t gslab_off;             // host mode without units: one global-line triple per slab
+	uint64_t out_slab_rows;       // host mode without units: rows of each of the two slab-sized output tables
+	uint64_t gslab_cap;
 	uint64_t blk_lo, blk_hi;  // scan blocks covering [u_lo, u_hi)
 	size_t stage_col_bytes[8];
 	uint64_t slab_sites;
 };
+
+// Sliding-tile scan (k_slide): shared-memory shape, and whether the geometry takes that path at all.
+// The choice fixes the summation order, so it is a pure function of (W, S, unit, statistic) and the
+// tuning knob -- never of the input size, the window range or the shard.
+struct SlideShape {
+	uint32_t E, nstages, stage_bytes, sf_off, pr_off, stage_off;
+	uint32_t col_off[kMaxTileCols], col_cap[kMaxTileCols];
+	size_t smem;
+};
+static void slide_footprint(const pgt_geom& g, pgt_stat stat, SlideShape* sh) {
+	ColDesc d[8];
+	const int nc = stat_columns(stat, PGT_MODE_SITES, nullptr, d);
+	uint32_t o = 0;
+	for (int c = 0; c < nc; ++c) {
+		sh->col_off[c] = o;
+		sh->col_cap[c] = (uint32_t)align_up((size_t)g.W * d[c].elem + 48, 16);
+		o += sh->col_cap[c];
+	}
+	sh->stage_bytes = (uint32_t)align_up(o, 128);
+	sh->E = (g.W + kSlideConsumers - 1) / kSlideConsumers;
+	const uint32_t accb = (uint32_t)align_up((size_t)g.W * acc_bytes(stat), 128);
+	sh->sf_off = kTileCtlBytes + kSlideWtBytes;
+	sh->pr_off = sh->sf_off + accb;
+	sh->stage_off = sh->pr_off + accb;
+}
+static bool slide_shape(const pgt_geom& g, pgt_mode mode, pgt_stat stat, SlideShape* sh) {
+	if (mode != PGT_MODE_SITES || g_tune_slide == 1) return false;
+	if (g.W > (uint32_t)kSlideConsumers * kSlideMaxE) return false;
+	if (g_tune_slide != 2) {
+		// auto: no piece of a step reaches a sector of doubles (units of < 32 sites) under windows of many
+		// units -- where level 2 would otherwise run its block scans over a unit array as large as the input
+		if (g.W < 256 || g.ueff >= 32 || g.wunits <= 32) return false;
+	}
+	const size_t half = 113u * 1024u, full = 226u * 1024u;
+	// One rule for all statistics (the fused scan must equal the three single scans bit for bit): the block
+	// of the widest one -- fused, 41 B/site staged twice + two 40-byte accumulators per site -- has to fit,
+	// which bounds W at about 1400 sites.
+	slide_footprint(g, PGT_STAT_FUSED, sh);
+	if (sh->stage_off + 2 * (size_t)sh->stage_bytes > full) return false;
+	slide_footprint(g, stat, sh);
+	// two CTAs per SM when three (or two) stages fit half the shared memory, else one CTA with up to four
+	for (uint32_t ns : {3u, 2u}) {
+		if (sh->stage_off + (size_t)ns * sh->stage_bytes <= half) {
+			sh->nstages = ns;
+			sh->smem = sh->stage_off + (size_t)ns * sh->stage_bytes;
+			return true;
+		}
+	}
+	for (uint32_t ns : {4u, 3u, 2u}) {
+		if (sh->stage_off + (size_t)ns * sh->stage_bytes <= full) {
+			sh->nstages = ns;
+			sh->smem = sh->stage_off + (size_t)ns * sh->stage_bytes;
+			return true;
+		}
+	}
+	return false;
+}
 
 static int make_layout(const pgt_plan* plan, const pgt_range* range, pgt_stat stat, pgt_mem mem, Layout* L) {
 	if (!plan) return pgt_set_error(PGT_ERR_ARGS, "plan is NULL");
@@ -1297,7 +1662,20 @@ static int make_layout(const pgt_plan* plan, const pgt_range* range, pgt_stat st
 			L->g_hi = f;
 		}
 	}
-	const uint64_t nunits = L->u_hi - L->u_lo;
+	// sites owned for the global line (same boundaries as the units [u_lo, g_hi))
+	L->gsite_lo = pgt_plan_unit_start(plan, L->u_lo);
+	L->gsite_hi = pgt_plan_unit_start(plan, L->g_hi);
+	{
+		SlideShape sh;
+		L->slide = slide_shape(plan->g, plan->mode, stat, &sh);
+		if (L->slide) {
+			L->slide_stages = sh.nstages;
+			L->slide_smem = sh.smem;
+		}
+		L->persite = !L->slide && plan->mode == PGT_MODE_SITES && plan->g.W == 1 && plan->g.S == 1 && g_tune_level2 != 1;
+	}
+	const bool nounits = L->slide || L->persite;  // windows come straight from the sites: no unit array, no level 2
+	const uint64_t nunits = nounits ? 0 : L->u_hi - L->u_lo;
 	size_t o = 0;
 	L->segs_off = o;
 	o += align_up(plan->segs.size() * sizeof(pgt_seg) + 8, 256);
@@ -1321,6 +1699,7 @@ static int make_layout(const pgt_plan* plan, const pgt_range* range, pgt_stat st
 		if (g_tune_level2 == 1) L->hgw = false;
 		if (g_tune_level2 == 2 && plan->g.wunits >= 2) L->hgw = true;
 	}
+	if (nounits) L->hgw = false;
 	L->pre_off = o;
 	L->blk_lo = L->blk_hi = 0;
 	// PRE array: reserved whenever scan mode is possible, so the workspace size does not depend on the
@@ -1344,7 +1723,14 @@ static int make_layout(const pgt_plan* plan, const pgt_range* range, pgt_stat st
 		for (int s = 0; s < 2; ++s)
 			for (int i = 0; i < nc; ++i) o += L->stage_col_bytes[i];
 		L->outs_off = o;
-		o += 12 * align_up((size_t)(hi - lo) * 8 + 8, 256);  // staged per-window outputs + global[3]
+		// staged per-window outputs + global[3]: the whole table, or (no unit array: the windows are produced
+		// slab by slab) two tables of at most one slab's windows -- a window starts at its own site
+		L->out_slab_rows = std::min<uint64_t>(hi - lo, L->slab_sites);
+		if (nounits) o += 2 * 12 * align_up((size_t)L->out_slab_rows * 8 + 8, 256);
+		else o += 12 * align_up((size_t)(hi - lo) * 8 + 8, 256);
+		L->gslab_off = o;
+		L->gslab_cap = nounits ? plan->nsites / (L->slab_sites - kSlabSlack - std::min<uint64_t>(plan->g.W, L->slab_sites - kSlabSlack - 1)) + 16 : 0;
+		o += align_up((size_t)L->gslab_cap * 3 * sizeof(double), 256);
 	}
 	// tile -> first segment table of the tiled level-1 kernel (genomes of many contigs, see k_tile_segs)
 	L->tileseg_off = o;
@@ -1352,6 +1738,15 @@ static int make_layout(const pgt_plan* plan, const pgt_range* range, pgt_stat st
 	o += align_up((size_t)L->tileseg_cap * sizeof(uint32_t), 256);
 	L->total = o + 256;
 	return PGT_OK;
+}
+
+extern "C" int pgt_plan_scan_path(const pgt_plan* plan, pgt_stat stat) {
+	if (!plan) return pgt_set_error(PGT_ERR_ARGS, "pgt_plan_scan_path: plan is NULL");
+	if ((int)stat < 0 || (int)stat > (int)PGT_STAT_FUSED) return pgt_set_error(PGT_ERR_ARGS, "unknown statistic");
+	SlideShape sh;
+	if (slide_shape(plan->g, plan->mode, stat, &sh)) return PGT_PATH_SLIDE;
+	if (plan->mode == PGT_MODE_SITES && plan->g.W == 1 && plan->g.S == 1 && g_tune_level2 != 1) return PGT_PATH_PERSITE;
+	return PGT_PATH_UNITS;
 }
 
 extern "C" size_t pgt_plan_device_bytes(const pgt_plan* plan) {
@@ -1385,6 +1780,7 @@ extern "C" size_t pgt_scan_workspace_bytes(const pgt_plan* plan, const pgt_range
 extern "C" int pgt_tune(const char* key, int value) {
 	if (key && strcmp(key, "level1") == 0) g_tune_level1 = value;
 	else if (key && strcmp(key, "level2") == 0 && value >= 0 && value <= 2) g_tune_level2 = value;
+	else if (key && strcmp(key, "slide") == 0 && value >= 0 && value <= 2) g_tune_slide = value;
 	else if (key && strcmp(key, "hoststage") == 0 && value >= 0 && value <= 1) g_tune_hoststage = value;
 	else if (key && strcmp(key, "stages") == 0 && value >= 2 && value <= kTileMaxStages) g_tune_stages = value;
 	else if (key && strcmp(key, "stage_kb") == 0 && value >= 8 && value <= 110) g_tune_stage_kb = value;
@@ -1422,7 +1818,7 @@ static int launch_units_tiled(const DevPlan& P, const Cols& cols, typename Stat:
 	uint32_t stage_budget = (uint32_t)g_tune_stage_kb * 1024u;
 	if (nstages * stage_budget > 224u * 1024u) stage_budget = 224u * 1024u / nstages;
 	uint32_t tsites = (stage_budget - 48u * sc.n) / bps;
-	if (tsites > 16384u) tsites = 16384u;
+	if (tsites > 16384u && bps > 1) tsites = 16384u;  // (the 1-byte genotype column alone fills a stage with ~110 K sites)
 	uint32_t m = tsites / P.g.ueff;
 	if (m < 1) m = 1;
 	{
@@ -1526,7 +1922,9 @@ static int launch_units(const DevPlan& P, const Cols& cols, typename Stat::Acc* 
 		for (uint32_t c = 0; c < sc.n; ++c) bps += sc.elem[c];
 	}
 	const uint64_t approx_bytes = nunits * (uint64_t)P.g.ueff * bps;
-	bool tiled = P.g.gw != 32 || (bps > 1 && approx_bytes >= (256ull << 20));
+	// (hetWindow's 1-byte column: the vectorised direct kernel below ~256 MB, the ring above -- a warp of the
+	// direct kernel has nothing in flight while it counts and stores, the ring keeps ~200 KB per SM in flight)
+	bool tiled = P.g.gw != 32 || approx_bytes >= (256ull << 20);
 	if (g_tune_level1 == 2) tiled = true;
 	if (g_tune_level1 == 1 && P.g.gw == 32) tiled = false;
 	{
@@ -1624,6 +2022,68 @@ int launch_global<DxyStat>(const DxyStat::Acc* units, uint64_t n, double* scratc
 template <>
 int launch_global<FusedStat>(const FusedStat::Acc* units, uint64_t n, double* scratch, double* g3, cudaStream_t st) {
 	k_global_partial<FusedStat><<<kGlobalBlocks, 1024, 0, st>>>(units, n, scratch);
+	k_global_final<<<1, kGlobalBlocks, 0, st>>>(scratch, g3);
+	g_launches += 2;
+	PGT_CUDA(cudaGetLastError());
+	return PGT_OK;
+}
+
+// Sliding-tile scan of the windows [P.win_lo, P.win_hi): the columns' element 0 is site P.site_origin and
+// they hold `valid_elems` elements.  `pos` may be NULL (host mode gathers positions on the host).
+template <class Stat>
+static int launch_slide(const pgt_plan* plan, pgt_stat stat, const DevPlan& P, const Cols& cols, uint64_t valid_elems, const uint32_t* pos,
+                        const pgt_windows& out, cudaStream_t st) {
+	const uint64_t nwin = P.win_hi - P.win_lo;
+	if (nwin == 0) return PGT_OK;
+	SlideShape sh;
+	if (!slide_shape(plan->g, plan->mode, stat, &sh)) return pgt_set_error(PGT_ERR_ARGS, "internal: sliding-tile scan not applicable");
+	const StatCols scol = tile_columns<Stat>(cols);
+	TileCfg tc;
+	memset(&tc, 0, sizeof(tc));
+	tc.ncol = scol.n;
+	tc.nstages = sh.nstages;
+	tc.stage_bytes = sh.stage_bytes;
+	tc.minind = cols.minind;
+	tc.valid_elems = valid_elems;
+	for (uint32_t c = 0; c < scol.n; ++c) {
+		tc.gcol[c] = (const char*)scol.ptr[c];
+		tc.elem[c] = scol.elem[c];
+		tc.col_off[c] = sh.col_off[c];
+		tc.col_cap[c] = sh.col_cap[c];
+	}
+	void (*kern)(DevPlan, TileCfg, SlideCfg, const uint32_t*, pgt_windows);
+	if (sh.E <= 2) kern = k_slide<Stat, 2>;
+	else if (sh.E <= 4) kern = k_slide<Stat, 4>;
+	else kern = k_slide<Stat, 6>;
+	PGT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh.smem));
+	int per_sm = 0;
+	PGT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kSlideThreads, sh.smem));
+	if (per_sm < 1) per_sm = 1;
+	const uint64_t slots = (uint64_t)num_sms() * per_sm;
+	// chunks: ~4 per resident CTA for balance, but long enough (>= 32 blocks of windows) that the W - S sites
+	// shared with the next chunk stay a few percent of what a chunk reads
+	const uint64_t wpb = (plan->g.W + plan->g.S - 1) / plan->g.S;  // windows starting in one block
+	SlideCfg sc;
+	memset(&sc, 0, sizeof(sc));
+	sc.E = sh.E;
+	sc.sf_off = sh.sf_off;
+	sc.pr_off = sh.pr_off;
+	sc.stage_off = sh.stage_off;
+	sc.chunk_windows = std::max<uint64_t>(32 * wpb, (nwin + slots * 4 - 1) / (slots * 4));
+	sc.nchunks = (nwin + sc.chunk_windows - 1) / sc.chunk_windows;
+	const unsigned grid = (unsigned)std::min<uint64_t>(sc.nchunks, slots);
+	{
+		ProfScope prof(0, st);
+		kern<<<grid, kSlideThreads, sh.smem, st>>>(P, tc, sc, pos, out);
+	}
+	g_launches++;
+	PGT_CUDA(cudaGetLastError());
+	return PGT_OK;
+}
+
+// dxyWindow's global line straight from the columns (scans without a unit array)
+static int launch_global_sites(const Cols& cols, uint64_t i0, uint64_t i1, double* scratch, double* g3, cudaStream_t st) {
+	k_global_sites<<<kGlobalBlocks, 1024, 0, st>>>(cols, i0, i1, scratch);
 	k_global_final<<<1, kGlobalBlocks, 0, st>>>(scratch, g3);
 	g_launches += 2;
 	PGT_CUDA(cudaGetLastError());
@@ -1790,14 +2250,23 @@ static int run_scan(const pgt_plan* plan, const pgt_range* range, pgt_stat stat,
 		C.n1 = cols->n1;
 		C.n2 = cols->n2;
 		C.minind = minind;
-		if (!bp && P.g.W == 1 && P.g.S == 1 && !want_global && g_tune_level2 != 1) {
-			// default arguments of fstWindow / hetWindow: one window per site, no reduction at all
-			if (nwin) {
+		if (L.persite || L.slide) {
+			// windows straight from the sites: W = S = 1 (default arguments of fstWindow / hetWindow: an
+			// elementwise map) or the sliding tile for fine steps; no unit array, no level 2
+			if (nwin && L.persite) {
 				const uint64_t want = (nwin + 255) / 256, cap = (uint64_t)num_sms() * 8;
 				ProfScope prof(1, st);
 				k_windows_persite<Stat><<<(unsigned)(want < cap ? want : cap), 256, 0, st>>>(P, C, *out);
 				g_launches++;
 				PGT_CUDA(cudaGetLastError());
+			} else if (nwin) {
+				uint64_t last;
+				pgt_plan_window(plan, L.w_hi - 1, nullptr, &last, nullptr);
+				PGT_TRY(launch_slide<Stat>(plan, stat, P, C, last + 1 - L.origin, cols->pos, *out, st));
+			}
+			if (want_global) {
+				if (L.gsite_lo < L.origin) return pgt_set_error(PGT_ERR_ARGS, "site_origin lies after the first site this scan must read");
+				PGT_TRY(launch_global_sites(C, L.gsite_lo - L.origin, L.gsite_hi - L.origin, (double*)(ws + L.gpart_off), out->dxy_global, st));
 			}
 			return PGT_OK;
 		}
@@ -1891,11 +2360,144 @@ static int run_scan(const pgt_plan* plan, const pgt_range* range, pgt_stat stat,
 		for (int i = 0; i < ncol; ++i) any |= (via_ring[i] = host_pointer_is_pageable(cd[i].ptr));
 		if (any) PGT_TRY(ring.init());
 	}
+	// per-window values are produced into device staging, then copied back: one table for the whole scan, or --
+	// when the windows come straight from the sites, slab by slab -- two slab-sized tables used in turn
+	const bool from_units = !(L.slide || L.persite);
+	const uint64_t out_rows = from_units ? nwin : L.out_slab_rows;
+	const size_t ob = align_up((size_t)out_rows * 8 + 8, 256);
+	auto device_table = [&](int which) -> pgt_windows {
+		pgt_windows d;
+		memset(&d, 0, sizeof(d));
+		char* ob0 = ws + L.outs_off + (size_t)which * 12 * ob;
+		int k = 0;
+		auto dptr = [&](const void* want) -> void* {
+			void* r = want ? (void*)(ob0 + ob * k) : nullptr;
+			++k;
+			return r;
+		};
+		d.sum_a = (double*)dptr(out->sum_a);
+		d.sum_b = (double*)dptr(out->sum_b);
+		d.fst = (double*)dptr(out->fst);
+		d.nhet = (uint32_t*)dptr(out->nhet);
+		d.nonmissing = (uint32_t*)dptr(out->nonmissing);
+		d.het = (double*)dptr(out->het);
+		d.dxy = (double*)dptr(out->dxy);
+		d.neffective = (uint32_t*)dptr(out->neffective);
+		d.nskip = (uint32_t*)dptr(out->nskip);
+		d.dxy_global = want_global ? (double*)(ob0 + ob * 11) : nullptr;
+		return d;
+	};
+	// rows [row0, row0 + n) of the caller's arrays <- rows [0, n) of a device table, on `st`
+	auto copy_back = [&](const pgt_windows& d, uint64_t row0, uint64_t n) -> int {
+		auto back = [&](void* h, const void* dp, size_t elem) -> cudaError_t {
+			return (h && dp && n) ? cudaMemcpyAsync((char*)h + row0 * elem, dp, n * elem, cudaMemcpyDeviceToHost, st) : cudaSuccess;
+		};
+		PGT_CUDA(back(out->sum_a, d.sum_a, 8));
+		PGT_CUDA(back(out->sum_b, d.sum_b, 8));
+		PGT_CUDA(back(out->fst, d.fst, 8));
+		PGT_CUDA(back(out->nhet, d.nhet, 4));
+		PGT_CUDA(back(out->nonmissing, d.nonmissing, 4));
+		PGT_CUDA(back(out->het, d.het, 8));
+		PGT_CUDA(back(out->dxy, d.dxy, 8));
+		PGT_CUDA(back(out->neffective, d.neffective, 4));
+		PGT_CUDA(back(out->nskip, d.nskip, 4));
+		return PGT_OK;
+	};
+	const pgt_windows dev = device_table(0);
 	const uint64_t slab_target = L.slab_sites - kSlabSlack;
 	const uint64_t axis_end = plan->off[0] + plan->nsites;
-	uint64_t ua = L.u_lo;
 	int slot = 0;
 	bool slot_used[2] = {false, false};
+	// one slab: H2D of sites [s0, s0 + ns) of every column into `slot`, ordered after the kernels that last read it
+	auto stage_slab = [&](uint64_t s0, uint64_t ns, Cols* C) -> int {
+		if (slot_used[slot]) PGT_CUDA(cudaStreamWaitEvent(hs.copy, hs.freed[slot], 0));
+		memset(C, 0, sizeof(*C));
+		C->minind = minind;
+		for (int i = 0; i < ncol; ++i) {
+			const char* src = (const char*)cd[i].ptr + (s0 - L.origin) * cd[i].elem;
+			if (ns && via_ring[i]) PGT_TRY(ring.push(stage[slot][i], src, ns * cd[i].elem, hs.copy));
+			else if (ns) PGT_CUDA(cudaMemcpyAsync(stage[slot][i], src, ns * cd[i].elem, cudaMemcpyHostToDevice, hs.copy));
+			const void* p = stage[slot][i];
+			memcpy((char*)C + cd[i].offset_in_cols, &p, sizeof(p));
+		}
+		PGT_CUDA(cudaEventRecord(hs.ready[slot], hs.copy));
+		PGT_CUDA(cudaStreamWaitEvent(st, hs.ready[slot], 0));
+		return PGT_OK;
+	};
+	auto release_slab = [&]() -> int {
+		PGT_CUDA(cudaEventRecord(hs.freed[slot], st));
+		slot_used[slot] = true;
+		slot ^= 1;
+		return PGT_OK;
+	};
+	if (L.slide || L.persite) {
+		// ---- windows straight from the sites (sliding tile / W = S = 1): slabs of consecutive WINDOWS; a
+		// slab holds the sites of its windows, neighbours share the W - S sites of the overlap.  The global
+		// line is taken from the same staged sites: every slab folds the part of the owned range
+		// [gsite_lo, gsite_hi) that no earlier slab has folded, one partial triple per slab, added in slab
+		// order on the host.
+		double* gslab = (double*)(ws + L.gslab_off);
+		uint64_t ngslab = 0, gcursor = L.gsite_lo;
+		auto fold_global = [&](const Cols& C, uint64_t s0, uint64_t s1) -> int {  // owned sites inside the staged [s0, s1)
+			const uint64_t a = std::max(gcursor, s0), b = std::min(L.gsite_hi, s1);
+			if (!want_global || b <= a) return PGT_OK;
+			if (ngslab >= L.gslab_cap) return pgt_set_error(PGT_ERR_NOMEM, "internal: global-line slab table too small");
+			PGT_TRY(launch_global_sites(C, a - s0, b - s0, (double*)(ws + L.gpart_off), gslab + 3 * ngslab, st));
+			++ngslab;
+			gcursor = b;
+			return PGT_OK;
+		};
+		uint64_t w = L.w_lo;
+		while (w < L.w_hi) {
+			uint64_t fs, last;
+			pgt_plan_window(plan, w, &fs, nullptr, nullptr);
+			const uint64_t wb = pgt_plan_windows_within(plan, w, std::min<uint64_t>(L.w_hi, w + L.out_slab_rows), fs + slab_target);
+			pgt_plan_window(plan, wb - 1, nullptr, &last, nullptr);
+			// (in site mode no owned site precedes the scan's first window: only an EOF segment can lack windows)
+			const uint64_t s0 = fs;
+			const uint64_t ns = last + 1 - s0;
+			if (ns > L.slab_sites) return pgt_set_error(PGT_ERR_ARGS, "internal: window slab larger than the staging buffers");
+			Cols C;
+			PGT_TRY(stage_slab(s0, ns, &C));
+			DevPlan Ps = P;
+			Ps.win_lo = w;
+			Ps.win_hi = wb;
+			Ps.site_origin = s0;
+			const pgt_windows o = device_table(slot);  // rewritten two slabs later, after this slab's copy-back (order of `st`)
+			if (L.persite) {
+				const uint64_t want = (wb - w + 255) / 256, cap = (uint64_t)num_sms() * 8;
+				ProfScope prof(1, st);
+				k_windows_persite<Stat><<<(unsigned)(want < cap ? want : cap), 256, 0, st>>>(Ps, C, o);
+				g_launches++;
+				PGT_CUDA(cudaGetLastError());
+			} else {
+				PGT_TRY(launch_slide<Stat>(plan, stat, Ps, C, ns, nullptr, o, st));
+			}
+			PGT_TRY(fold_global(C, s0, s0 + ns));
+			PGT_TRY(copy_back(o, w - L.w_lo, wb - w));
+			PGT_TRY(release_slab());
+			w = wb;
+		}
+		// owned sites after the last window (dropped EOF partial) or of a scan without windows
+		while (want_global && gcursor < L.gsite_hi) {
+			const uint64_t ns = std::min<uint64_t>(L.gsite_hi - gcursor, slab_target);
+			const uint64_t s0 = gcursor;
+			Cols C;
+			PGT_TRY(stage_slab(s0, ns, &C));
+			PGT_TRY(fold_global(C, s0, s0 + ns));
+			PGT_TRY(release_slab());
+		}
+		if (want_global) {
+			std::vector<double> part(3 * ngslab + 3, 0.0);
+			if (ngslab) PGT_CUDA(cudaMemcpyAsync(part.data(), gslab, 3 * ngslab * sizeof(double), cudaMemcpyDeviceToHost, st));
+			PGT_CUDA(cudaStreamSynchronize(st));
+			double g3[3] = {0.0, 0.0, 0.0};
+			for (uint64_t i = 0; i < ngslab; ++i)
+				for (int q = 0; q < 3; ++q) g3[q] += part[3 * i + q];
+			memcpy(out->dxy_global, g3, sizeof(g3));
+		}
+	}
+	uint64_t ua = (L.slide || L.persite) ? L.u_hi : L.u_lo;
 	while (ua < L.u_hi) {
 		const uint64_t e0 = pgt_plan_unit_start(plan, ua);
 		uint64_t ub;
@@ -1910,19 +2512,8 @@ static int run_scan(const pgt_plan* plan, const pgt_range* range, pgt_stat stat,
 		}
 		const uint64_t ns = s1 - s0;
 		if (ns > L.slab_sites) return pgt_set_error(PGT_ERR_INPUT, "bp mode: more sites than bp in a slab (positions not strictly increasing?)");
-		if (slot_used[slot]) PGT_CUDA(cudaStreamWaitEvent(hs.copy, hs.freed[slot], 0));
 		Cols C;
-		memset(&C, 0, sizeof(C));
-		C.minind = minind;
-		for (int i = 0; i < ncol; ++i) {
-			const char* src = (const char*)cd[i].ptr + (s0 - L.origin) * cd[i].elem;
-			if (ns && via_ring[i]) PGT_TRY(ring.push(stage[slot][i], src, ns * cd[i].elem, hs.copy));
-			else if (ns) PGT_CUDA(cudaMemcpyAsync(stage[slot][i], src, ns * cd[i].elem, cudaMemcpyHostToDevice, hs.copy));
-			const void* p = stage[slot][i];
-			memcpy((char*)&C + cd[i].offset_in_cols, &p, sizeof(p));
-		}
-		PGT_CUDA(cudaEventRecord(hs.ready[slot], hs.copy));
-		PGT_CUDA(cudaStreamWaitEvent(st, hs.ready[slot], 0));
+		PGT_TRY(stage_slab(s0, ns, &C));
 		DevPlan Ps = P;
 		Ps.unit_lo = ua;
 		Ps.unit_hi = ub;
@@ -1934,48 +2525,16 @@ static int run_scan(const pgt_plan* plan, const pgt_range* range, pgt_stat stat,
 		if (bp) PGT_TRY(launch_bounds_kernel(Ps, C.pos, ns, sb, st));
 		PGT_TRY(launch_units<Stat>(Ps, C, units + (ua - L.u_lo), sb, ns, L.tileseg_cap ? (uint32_t*)(ws + L.tileseg_off) : nullptr,
 		                           L.tileseg_cap, st));
-		PGT_CUDA(cudaEventRecord(hs.freed[slot], st));
-		slot_used[slot] = true;
-		slot ^= 1;
+		PGT_TRY(release_slab());
 		ua = ub;
 	}
 
-	// per-window values are produced into device staging, then copied back
-	pgt_windows dev;
-	memset(&dev, 0, sizeof(dev));
-	const size_t ob = align_up((size_t)nwin * 8 + 8, 256);
-	char* ob0 = ws + L.outs_off;
-	int k = 0;
-	auto dptr = [&](const void* want) -> void* {
-		void* r = want ? (void*)(ob0 + ob * k) : nullptr;
-		++k;
-		return r;
-	};
-	dev.sum_a = (double*)dptr(out->sum_a);
-	dev.sum_b = (double*)dptr(out->sum_b);
-	dev.fst = (double*)dptr(out->fst);
-	dev.nhet = (uint32_t*)dptr(out->nhet);
-	dev.nonmissing = (uint32_t*)dptr(out->nonmissing);
-	dev.het = (double*)dptr(out->het);
-	dev.dxy = (double*)dptr(out->dxy);
-	dev.neffective = (uint32_t*)dptr(out->neffective);
-	dev.nskip = (uint32_t*)dptr(out->nskip);
-	dev.dxy_global = want_global ? (double*)(ob0 + ob * 11) : nullptr;
-	if (want_global) PGT_TRY(launch_global<Stat>(units, nglobal, (double*)(ws + L.gpart_off), dev.dxy_global, st));
-	PGT_TRY(launch_windows<Stat>(P, units, L.u_lo, nullptr, dev, L.hgw, (typename Stat::Acc*)(ws + L.pre_off), L.blk_lo, L.blk_hi, st));
-	auto back = [&](void* h, const void* d, size_t elem) -> cudaError_t {
-		return (h && d && nwin) ? cudaMemcpyAsync(h, d, nwin * elem, cudaMemcpyDeviceToHost, st) : cudaSuccess;
-	};
-	PGT_CUDA(back(out->sum_a, dev.sum_a, 8));
-	PGT_CUDA(back(out->sum_b, dev.sum_b, 8));
-	PGT_CUDA(back(out->fst, dev.fst, 8));
-	PGT_CUDA(back(out->nhet, dev.nhet, 4));
-	PGT_CUDA(back(out->nonmissing, dev.nonmissing, 4));
-	PGT_CUDA(back(out->het, dev.het, 8));
-	PGT_CUDA(back(out->dxy, dev.dxy, 8));
-	PGT_CUDA(back(out->neffective, dev.neffective, 4));
-	PGT_CUDA(back(out->nskip, dev.nskip, 4));
-	if (want_global) PGT_CUDA(cudaMemcpyAsync(out->dxy_global, dev.dxy_global, 3 * sizeof(double), cudaMemcpyDeviceToHost, st));
+	if (from_units) {
+		if (want_global) PGT_TRY(launch_global<Stat>(units, nglobal, (double*)(ws + L.gpart_off), dev.dxy_global, st));
+		PGT_TRY(launch_windows<Stat>(P, units, L.u_lo, nullptr, dev, L.hgw, (typename Stat::Acc*)(ws + L.pre_off), L.blk_lo, L.blk_hi, st));
+		PGT_TRY(copy_back(dev, 0, nwin));
+		if (want_global) PGT_CUDA(cudaMemcpyAsync(out->dxy_global, dev.dxy_global, 3 * sizeof(double), cudaMemcpyDeviceToHost, st));
+	}
 
 	book.join();
 	PGT_CUDA(cudaStreamSynchronize(st));

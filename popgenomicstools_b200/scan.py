@@ -105,6 +105,10 @@ class WindowPlan:
         check(self._lib.pgt_plan_shard(self._h, rank, nranks, *[C.byref(x) for x in v]))
         return tuple(x.value for x in v)
 
+    def scan_path(self, stat):
+        """'units' | 'slide' | 'persite': the kernels a scan of `stat` runs (pgt_plan_scan_path)."""
+        return ("units", "slide", "persite")[check(self._lib.pgt_plan_scan_path(self._h, stat))]
+
     def workspace_bytes(self, stat, mem, window_range=None, site_origin=0, site_count=0):
         r = _range(self, window_range, site_origin, site_count)
         return int(self._lib.pgt_scan_workspace_bytes(self._h, C.byref(r), stat, mem))
@@ -112,7 +116,7 @@ class WindowPlan:
     def workspace(self, device, stat, mem, window_range=None, site_origin=0, site_count=0):
         """Device scratch for a scan, cached per (device, stat, mem, range)."""
         torch = _torch()
-        key = (str(device), stat, mem, window_range, site_origin, site_count)
+        key = (str(device), stat, mem, window_range, site_origin, site_count, _tune_epoch[0])
         ws = self._workspaces.get(key)
         if ws is None:
             ws = torch.empty(self.workspace_bytes(stat, mem, window_range, site_origin, site_count), dtype=torch.uint8,
@@ -125,6 +129,8 @@ def _range(plan, window_range, site_origin, site_count=0):
     lo, hi = (0, plan.num_windows) if window_range is None else window_range
     return PgtRange(int(lo), int(hi), int(site_origin), int(site_count))
 
+
+_tune_epoch = [0]
 
 _COL_DTYPES = {"pos": "uint32", "a": "float64", "b": "float64", "geno": "int8", "f1": "float64", "f2": "float64",
                "n1": "int32", "n2": "int32"}
@@ -319,5 +325,7 @@ def profile_read():
 
 
 def tune(key, value):
-    """Kernel-selection knobs for tests/experiments (pgt_tune)."""
+    """Kernel-selection knobs for tests/experiments (pgt_tune).  Some knobs change the workspace a scan
+    needs, so cached workspaces are re-queried afterwards."""
     check(_cabi.load().pgt_tune(key.encode(), int(value)))
+    _tune_epoch[0] += 1
