@@ -4,19 +4,26 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--workload C4|C5] [--impl reference]
     torchrun --nnodes=1 --nproc-per-node N ... bench.py --gpus N --steps K --warmup W
 
-A step is one pass of the hot path (level-1 unit reduction + level-2 window combine, and for
-N > 1 the NCCL gather of the per-window results to rank 0) over the whole synthetic genome,
-sharded by site range with a (W-S)-site halo (strong scaling: total work fixed).  Inputs are
-generated on the device by the counter-based generator and are resident in HBM when the timed
-region starts; they are far larger than L2 (48 GB vs 126 MB), so no explicit flush is needed.
+A step is one pass of the hot path (level-1 unit reduction + level-2 window combine) over the whole synthetic
+genome, sharded by site range with a (W-S)-site halo (strong scaling: total work fixed).  There is no collective
+on the data path and no gather: the window table lives once, in rank 0's HBM, and every rank's window kernel
+writes its rows there directly (CUDA IPC mapping over NVLink, popgenomicstools_b200/sharding.py SharedTable).
+Inputs are generated on the device by the counter-based generator and are resident in HBM when the timed region
+starts; they are far larger than L2 (48 GB vs 126 MB), so no explicit flush is needed.
 
-Prints ONE JSON line (rank 0).  `value` = total sites / max-over-ranks device time;
-`e2e` = the same scan through the C ABI with HOST (pinned) columns, H2D/D2H inside the timed
-region; `roofline` = algorithmic bytes of the dominant kernel (level 1) / its mean CUDA-event
-duration, against MEASURED_PEAKS.json; `cpu_baseline` = the unmodified reference binary
-(oracle/_ref, g++ -O3) timed on this box's host cores on a bounded text sample.
+Prints ONE JSON line (rank 0).  `value` = total sites / max-over-ranks device time; `result_checksum` = an
+order-sensitive checksum of the whole window table (identical for 1/2/4/8 GPUs: the summation order is a function
+of (W, S, unit) only); `e2e` = the same scan through the C ABI with HOST (pinned) columns, H2D/D2H inside the timed
+region -- at N > 1 ONE process (rank 0) drives all N GPUs through pgt_scan_sharded and ends with ONE table;
+`roofline` = algorithmic bytes of the dominant kernel (level 1) / its mean CUDA-event duration over the timed
+region, against MEASURED_PEAKS.json; `configs` = the other BASELINE.json configurations (C1, C2 sparse / dense, C3
+per-site / 100 kb, C5 and its S = 1 stress variant), each sharded over the same N ranks: value, kernel time,
+algorithmic bytes (columns in + window rows out, SURVEY 8d), fraction of the HBM peak and the table checksum;
+`cpu_baseline` = the unmodified reference binary (oracle/_ref, g++ -O3) timed on this box's host cores on a
+bounded text sample.
 
---impl reference runs only that CPU arm (the reference's own implementation of the path).
+--impl reference runs only that CPU arm (the reference's own implementation of the path); it never imports the
+product package or loads libpgtscan.so.
 """
 import argparse
 import json
@@ -46,11 +53,23 @@ def parse_args():
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-configs", action="store_true", help="skip the per-config legs (C1, C2, C3, C5, C5-S1)")
+    ap.add_argument("--configs", default="", help="comma-separated subset of the per-config legs")
+    ap.add_argument("--config-steps", type=int, default=5)
     ap.add_argument("--cpu-sample-sites", type=float, default=4.8e7)
     return ap.parse_args()
 
 
 # ------------------------------------------------------------------------------ reference arm
+
+def load_workloads():
+    """workloads.py by path: the reference arm must not import the product package (its __init__ loads libpgtscan.so)."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("pgt_workloads", os.path.join(ROOT, "popgenomicstools_b200", "workloads.py"))
+    m = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(m)
+    return m
+
 
 def _write_contig(job):
     sys.path.insert(0, os.path.join(ROOT, "tests"))
@@ -143,7 +162,7 @@ def reference_arm(wl, sample_sites, steps, warmup, with_cli=False):
     import multiprocessing as mp
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import oracle_lib as O
-    from popgenomicstools_b200.workloads import human_like_contigs
+    human_like_contigs = load_workloads().human_like_contigs
     W, S = wl["winsize"], wl["stepsize"]
     exe = O.ref_binary("fstWindow")
     cores = os.cpu_count() or 1
@@ -193,7 +212,7 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    from popgenomicstools_b200.workloads import WORKLOADS
+    WORKLOADS = load_workloads().WORKLOADS
     wl = WORKLOADS["C4"] if args.workload == "C5" else WORKLOADS[args.workload]  # the reference has no fused tool
     steps, warmup = max(1, args.steps), max(0, args.warmup)
     # bound the whole run to a few minutes whatever K/W the driver passes
@@ -248,7 +267,7 @@ class ClockSampler:
                         self.reasons.add(name)
             except Exception:
                 pass
-            self._stop.wait(0.005)
+            self._stop.wait(0.05)  # NVML queries take milliseconds: keep them off the ranks' critical path
 
     def __enter__(self):
         if self._h is not None:
@@ -289,24 +308,209 @@ def recorded_traffic(workload, n_gpus):
         return None
 
 
+IN_BYTES = {"fst": 16, "het": 1, "dxy": 24, "fused": 41}     # compulsory column bytes per site (pos at window edges only)
+OUT_BYTES = {"fst": 44, "het": 36, "dxy": 32, "fused": 76}   # window row bytes the scan writes (label, positions, counts, statistics)
+ACC_BYTES = {"fst": 16, "het": 8, "dxy": 16, "fused": 40}
+
+# The other BASELINE.json configurations, run after the headline on the same ranks (short: a few steps each).
+# `full`: every rank holds the whole (small) input and scans only its window range; otherwise its shard + halo.
+CONFIGS = [
+    dict(name="C1", stat="fst", n=1_000_000, contigs=1, W=50000, S=10000, seed=1, unit=0, full=True,
+         desc="fstWindow, 1 Mb contig, 50 kb / 10 kb (configs[0])"),
+    dict(name="C2-sparse", stat="dxy", n=1_000_000, contigs=1, W=20000, S=5000, seed=2, unit=0, full=True, bp=10,
+         desc="dxyWindow bp mode, 10 Mb contig, 1 site per 10 bp, 20 kb / 5 kb (configs[1])"),
+    dict(name="C2-dense", stat="dxy", n=10_000_000, contigs=1, W=20000, S=5000, seed=2, unit=0, full=True, bp=1,
+         desc="dxyWindow bp mode, 10 Mb contig, every bp a site, 20 kb / 5 kb (configs[1])"),
+    dict(name="C3-1/1", stat="het", n=100_000_000, contigs=1, W=1, S=1, seed=3, unit=0, full=True,
+         desc="hetWindow, 100 Mb chromosome, single-site windows (configs[2]; output-bound: one row per site)"),
+    dict(name="C3-100k", stat="het", n=100_000_000, contigs=1, W=100000, S=100000, seed=3, unit=4096, full=True,
+         desc="hetWindow, 100 Mb chromosome, 100 kb windows (configs[2])"),
+    dict(name="C5", stat="fused", n=3_000_000_000, contigs=24, W=1000, S=100, seed=5, unit=0, full=False,
+         desc="fused fst+dxy+het, 3e9 sites / 24 contigs, 1000 / 100 (configs[4])"),
+    dict(name="C5-S1", stat="fused", n=100_000_000, contigs=24, W=1000, S=1, seed=5, unit=0, full=True,
+         desc="fused fst+dxy+het, 1e8-site subset, 1000 / 1: maximal overlap, sliding-tile path (configs[4] stress variant)"),
+]
+
+
+class Ranks:
+    """torch.distributed plumbing of one bench process."""
+
+    def __init__(self, torch, dist):
+        self.torch, self.dist = torch, dist
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        torch.cuda.set_device(self.local)
+        self.dev = torch.device(f"cuda:{self.local}")
+        if self.world > 1:
+            os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+            dist.init_process_group("nccl", device_id=self.dev)
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def reduce(self, values, op="max"):
+        t = self.torch.tensor([float(v) for v in values], device=self.dev, dtype=self.torch.float64)
+        if self.world > 1:
+            self.dist.all_reduce(t, op={"max": self.dist.ReduceOp.MAX, "sum": self.dist.ReduceOp.SUM}[op])
+        return [float(x) for x in t.tolist()]
+
+
+def make_columns(pgt, stat, seed, s_lo, n_local, offs, dev, density=1):
+    cols = dict(pos=pgt.synth_pos(seed, s_lo, n_local, offs, density, device=dev))
+    if stat in ("fst", "fused"):
+        cols["a"], cols["b"] = pgt.synth_fst(seed, s_lo, n_local, device=dev)
+    if stat in ("het", "fused"):
+        cols["geno"] = pgt.synth_het(seed, s_lo, n_local, device=dev)
+    if stat in ("dxy", "fused"):
+        cols["f1"], cols["f2"], cols["n1"], cols["n2"] = pgt.synth_dxy(seed, s_lo, n_local, device=dev)
+    return cols
+
+
+def local_units(plan, w_lo, w_hi):
+    if w_hi <= w_lo:
+        return 0
+    fu0, _ = plan.window_units(w_lo)
+    fu1, c1 = plan.window_units(w_hi - 1)
+    return (plan.num_units if w_hi == plan.num_windows else fu1 + c1) - (0 if w_lo == 0 else fu0)
+
+
+def run_config(cfg, R, pgt, steps, peak):
+    """One BASELINE configuration on the ranks of this run: resident columns, window table in rank 0's HBM, a few
+    warm-up and `steps` timed steps (CUDA events, max over ranks), per-kernel time from the library's own events."""
+    import numpy as np
+    torch, dist = R.torch, R.dist
+    from popgenomicstools_b200 import _cabi
+    from popgenomicstools_b200.scan import _STAT_OUTS
+    from popgenomicstools_b200.sharding import SharedTable
+    from popgenomicstools_b200.workloads import human_like_contigs
+    stat_id = {"fst": _cabi.PGT_STAT_FST, "het": _cabi.PGT_STAT_HET, "dxy": _cabi.PGT_STAT_DXY, "fused": _cabi.PGT_STAT_FUSED}[cfg["stat"]]
+    n, W, S = cfg["n"], cfg["W"], cfg["S"]
+    free, _ = torch.cuda.mem_get_info()
+    need = (IN_BYTES[cfg["stat"]] + 4) * (n if cfg["full"] else n // R.world) + OUT_BYTES[cfg["stat"]] * (n // S if R.rank == 0 else 0)
+    f = R.reduce([1.0 if need * 1.08 + (4 << 30) > free else 0.0])[0]
+    if f > 0:  # every rank takes the same decision
+        return dict(name=cfg["name"], skipped=f"needs {need / 1e9:.0f} GB of HBM per GPU, {free / 1e9:.0f} GB free")
+    if cfg["contigs"] == 1:
+        offs = np.array([0, n], np.uint64)
+    else:
+        _, offs = human_like_contigs(n, S)
+    extra, density = {}, cfg.get("bp", 0)
+    if density:  # dxyWindow -fixedsite 0: windows on the bp axis of a chromosome of n * density bp
+        plan = pgt.WindowPlan(np.array([0, n * density], np.uint64), W, S, mode="bp", unit_sites=cfg["unit"])
+        extra = dict(site_offsets=offs)
+    else:
+        plan = pgt.WindowPlan(offs, W, S, unit_sites=cfg["unit"])
+    w_lo, w_hi, s_lo, s_hi = plan.shard(R.rank, R.world)
+    if cfg["full"] or density:
+        s_lo, s_hi = 0, n
+    cols = make_columns(pgt, cfg["stat"], cfg["seed"], s_lo, s_hi - s_lo, offs, R.dev, density or 1)
+    tab = SharedTable(_STAT_OUTS[stat_id], plan.num_windows, R.rank, R.world, dist, torch, R.dev)
+    out = tab.rows(w_lo, w_hi)
+    kw = dict(minind=5, window_range=(w_lo, w_hi), site_origin=s_lo, out=out, **extra)
+    try:
+        for _ in range(3):
+            pgt.scan(plan, stat_id, cols, **kw)
+        R.barrier()
+        pgt.profile(True)
+        pgt.profile_read()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        R.barrier()
+        e0.record()
+        for _ in range(steps):
+            pgt.scan(plan, stat_id, cols, **kw)
+        e1.record()
+        R.barrier()
+        prof = pgt.profile_read()
+        pgt.profile(False)
+        ms_step = R.reduce([e0.elapsed_time(e1) / steps])[0]
+        path = plan.scan_path(stat_id)
+        nwin_l = w_hi - w_lo
+        # sites this rank's scan reads: its windows' span (the halo is real work of the sharded run)
+        fl = plan._lib
+        import ctypes as C
+        sites_l = 0
+        if nwin_l:
+            f0, l1 = C.c_uint64(), C.c_uint64()
+            fl.pgt_plan_window(plan.handle, w_lo, C.byref(f0), None, None)
+            fl.pgt_plan_window(plan.handle, w_hi - 1, None, C.byref(l1), None)
+            sites_l = l1.value + 1 - f0.value
+            if density:  # bp axis: the sites are those of the bp range; a shard reads its share of them
+                sites_l = int(round(sites_l / density))
+        in_b = IN_BYTES[cfg["stat"]] + (4 if density else 0)
+        algo = in_b * sites_l + OUT_BYTES[cfg["stat"]] * nwin_l
+        k_ms = (prof["units_ms"] + prof["windows_ms"]) / steps
+        ach = algo / (k_ms * 1e-3) / 1e9 if k_ms > 0 else 0.0
+        tot = R.reduce([algo, ach, k_ms, prof["units_ms"] / steps, prof["windows_ms"] / steps], "sum")
+        res = dict(name=cfg["name"], desc=cfg["desc"], path=path, n_sites=n, windows=plan.num_windows, value=n / (ms_step * 1e-3),
+                   unit=UNIT, ms_per_step=round(ms_step, 4), steps=steps,
+                   kernel_ms=round(tot[2] / R.world, 4), level1_ms=round(tot[3] / R.world, 4), level2_ms=round(tot[4] / R.world, 4),
+                   algorithmic_bytes=int(tot[0]), achieved_gbs=round(tot[1] / R.world, 1), frac=round(tot[1] / R.world / peak, 4),
+                   bytes_per_site_in=in_b, bytes_per_window_out=OUT_BYTES[cfg["stat"]])
+        R.barrier()
+        if R.rank == 0:
+            res["result_checksum"] = tab.checksum()
+        return res
+    finally:
+        pgt.profile(False)
+        del cols
+        tab.close()
+        torch.cuda.empty_cache()
+
+
+class PinnedColumns:
+    """Host columns of the WHOLE genome in page-locked memory of exactly their size (pgt_host_alloc; torch's pinned
+    allocator rounds every tensor up to a power of two, 64 GB for the 48 GB of C4)."""
+
+    def __init__(self, pgt, torch, stat, seed, n_total, offs, dev, slab=1 << 27):
+        import ctypes as C
+        import numpy as np
+        from popgenomicstools_b200 import _cabi
+        self._lib, self._ptrs = _cabi.load(), []
+        names = {"fst": ("a", "b"), "fused": ("a", "b", "geno", "f1", "f2", "n1", "n2")}[stat]
+        dt = dict(a=np.float64, b=np.float64, geno=np.int8, f1=np.float64, f2=np.float64, n1=np.int32, n2=np.int32)
+        self.cols = {}
+        for k in names:
+            p = C.c_void_p()
+            nbytes = n_total * np.dtype(dt[k]).itemsize
+            _cabi.check(self._lib.pgt_host_alloc(C.byref(p), nbytes))
+            self._ptrs.append(p.value)
+            self.cols[k] = np.frombuffer((C.c_char * nbytes).from_address(p.value), dtype=dt[k])
+        self.cols["pos"] = np.empty(n_total, np.uint32)  # pageable: gathered on the host at window edges, never copied
+        views = {k: torch.from_numpy(v) for k, v in self.cols.items() if k != "pos"}
+        for s0 in range(0, n_total, slab):  # generated on the device slab by slab, copied out
+            m = min(slab, n_total - s0)
+            c = make_columns(pgt, stat, seed, s0, m, offs, dev)
+            for k in names:
+                views[k][s0:s0 + m].copy_(c[k])
+            self.cols["pos"][s0:s0 + m] = c["pos"].cpu().numpy().view(np.uint32)
+            del c
+        torch.cuda.synchronize()
+
+    def free(self):
+        import ctypes as C
+        self.cols = {}
+        for p in self._ptrs:
+            self._lib.pgt_host_free(C.c_void_p(p))
+        self._ptrs = []
+
+
 def run_b200(args):
     import numpy as np
     import torch
     import torch.distributed as dist
     import popgenomicstools_b200 as pgt
     from popgenomicstools_b200 import _cabi
+    from popgenomicstools_b200.scan import _STAT_OUTS
+    from popgenomicstools_b200.sharding import SharedTable
     from popgenomicstools_b200.workloads import WORKLOADS, human_like_contigs
 
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the B200 arm has no CPU fallback")
-    torch.cuda.set_device(local)
-    dev = torch.device(f"cuda:{local}")
-    if world > 1:
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=dev)
+    R = Ranks(torch, dist)
+    rank, world, dev = R.rank, R.world, R.dev
     if args.gpus != world and rank == 0:
         print(f"bench.py: --gpus {args.gpus} but WORLD_SIZE={world}; using {world}", file=sys.stderr)
 
@@ -314,6 +518,7 @@ def run_b200(args):
     n_total = int(args.sites) if args.sites else wl["n_sites"]
     W, S, seed = wl["winsize"], wl["stepsize"], wl["seed"]
     fused = wl["stat"] == "fused"
+    sname = "fused" if fused else "fst"
     names, offs = human_like_contigs(n_total, S)
     # reduction unit (part of the summation order, any value gives the same results within 1e-16):
     # 512 sites fills a 110 KB tile of the 16 B/site fst stream with 13 units = one round of the 15
@@ -324,55 +529,35 @@ def run_b200(args):
     n_local, nwin_local = s_hi - s_lo, w_hi - w_lo
 
     # ---- resident synthetic columns of this rank's shard (incl. halo)
-    pos = pgt.synth_pos(seed, s_lo, n_local, offs, 1, device=dev)
-    a, b = pgt.synth_fst(seed, s_lo, n_local, device=dev)
-    cols = dict(pos=pos, a=a, b=b)
-    stat = _cabi.PGT_STAT_FST
-    bytes_per_site = 16
-    if fused:
-        stat = _cabi.PGT_STAT_FUSED
-        cols["geno"] = pgt.synth_het(seed, s_lo, n_local, device=dev)
-        cols["f1"], cols["f2"], cols["n1"], cols["n2"] = pgt.synth_dxy(seed, s_lo, n_local, device=dev)
-        bytes_per_site = 41
+    cols = make_columns(pgt, sname, seed, s_lo, n_local, offs, dev)
+    stat = _cabi.PGT_STAT_FUSED if fused else _cabi.PGT_STAT_FST
+    bytes_per_site = IN_BYTES[sname]
     torch.cuda.synchronize()
 
-    # ---- outputs live in one packed buffer so the gather to rank 0 is a single NCCL call
-    from popgenomicstools_b200.scan import _STAT_OUTS
-    from popgenomicstools_b200.sharding import PackedWindows, shard_counts
+    # ---- the window table lives once, in rank 0's HBM; every rank's window kernel writes its rows there
     fields = [k for k in _STAT_OUTS[stat] if k != "dxy_global"]
-    counts = shard_counts(dist, nwin_local, world, dev, torch)
-    pw = PackedWindows(_STAT_OUTS[stat], nwin_local, max(counts), dev, torch)
-    out = pw.views
-    gathered = [None]
+    tab = SharedTable(_STAT_OUTS[stat], plan.num_windows, rank, world, dist, torch, dev)
+    out = tab.rows(w_lo, w_hi)
 
     def step():
         pgt.scan(plan, stat, cols, minind=5, window_range=(w_lo, w_hi), site_origin=s_lo, out=out)
-        if world > 1:
-            gathered[0] = pw.gather(dist, rank, world, gathered[0])
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    # The clock sampler runs from the first warm-up step to the end of the timed region: NVML
-    # queries take milliseconds, and at 8 GPUs the timed region itself is only ~20 ms.  Warm-up is
-    # the same load, contiguous with the timed steps, and lasts at least 0.3 s.
-    n_warm = 0
-    with ClockSampler(local) as clk:
+    barrier = R.barrier
+    # Clock warm-up first (uncounted: the same load for >= 0.3 s, so that the NVML sampler -- one query every
+    # 50 ms, outside the ranks' critical path -- sees the clocks under load), then the W counted warm-up steps,
+    # then the K timed steps; the sampler runs through all three.
+    W_steps = max(0, args.warmup)
+    with ClockSampler(R.local) as clk:
         t_w = time.perf_counter()
-        for _ in range(max(3, args.warmup)):
+        for _ in range(3):
             step()
-        n_warm = max(3, args.warmup)
         barrier()
-        per = torch.tensor([(time.perf_counter() - t_w) / n_warm], device=dev, dtype=torch.float64)
-        if world > 1:  # every rank must issue the same number of collectives
-            dist.all_reduce(per, op=dist.ReduceOp.MAX)
-        extra = max(0, min(2000, int(0.3 / max(float(per.item()), 1e-5)) - n_warm))
-        for _ in range(extra):
+        per = R.reduce([(time.perf_counter() - t_w) / 3])[0]
+        for _ in range(max(0, min(4000, int(0.3 / max(per, 1e-5))))):
             step()
-        n_warm += extra
-        nw = torch.tensor([n_warm], device=dev)
+        barrier()
+        for _ in range(W_steps):
+            step()
         barrier()
         launches0 = pgt.kernel_launch_count()
         pgt.profile(True)
@@ -388,89 +573,102 @@ def run_b200(args):
     prof = pgt.profile_read()
     pgt.profile(False)
     launches = pgt.kernel_launch_count() - launches0
-    t = torch.tensor([ms_total, float(launches)], device=dev, dtype=torch.float64)
-    tmax = t.clone()
-    if world > 1:
-        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-        dist.all_reduce(t, op=dist.ReduceOp.SUM)
-    ms_step = float(tmax[0].item()) / args.steps
-    total_launches = int(t[1].item())
+    ms_step = R.reduce([ms_total])[0] / args.steps
+    total_launches = int(R.reduce([launches], "sum")[0])
     value = n_total / (ms_step * 1e-3)
+    result_checksum = tab.checksum() if rank == 0 else None
+    glob = tab.table().get("dxy_global") if (rank == 0 and fused) else None
 
     # ---- roofline of the dominant kernel (level 1) on this rank
     peak, peak_src = hbm_peak()
-    nunits_local = 0
-    if nwin_local:
-        fu0, _ = plan.window_units(w_lo)
-        fu1, c1 = plan.window_units(w_hi - 1)
-        nunits_local = (plan.num_units if w_hi == plan.num_windows else fu1 + c1) - (0 if w_lo == 0 else fu0)
-    acc_bytes = 40 if fused else 16
+    nunits_local = local_units(plan, w_lo, w_hi)
+    acc_bytes = ACC_BYTES[sname]
     algo_bytes = bytes_per_site * n_local + acc_bytes * nunits_local
     l1_ms = prof["units_ms"] / max(1, prof["units_launches"])
     achieved = algo_bytes / (l1_ms * 1e-3) / 1e9 if l1_ms > 0 else 0.0
-    ach = torch.tensor([achieved, prof["units_ms"], prof["windows_ms"]], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(ach, op=dist.ReduceOp.SUM)
-        ach /= world
-    roofline = {"bound": "hbm", "achieved": round(float(ach[0].item()), 1), "peak": peak, "unit": "GB/s",
-                "frac": round(float(ach[0].item()) / peak, 4), "traffic": recorded_traffic(args.workload, world),
-                "kernel": "k_units (level 1: per-site statistic + unit reduction)",
+    ach = R.reduce([achieved, prof["units_ms"], prof["windows_ms"]], "sum")
+    ach = [x / world for x in ach]
+    traffic = recorded_traffic(args.workload, world)
+    roofline = {"bound": "hbm", "achieved": round(ach[0], 1), "peak": peak, "unit": "GB/s",
+                "frac": round(ach[0] / peak, 4), "traffic": traffic,
+                "traffic_source": ("recorded: ncu --set full capture of this kernel, profiles/traffic.json (not measured in this run)"
+                                   if traffic is not None else None),
+                "kernel": "k_units_tiled (level 1: per-site statistic + unit reduction)",
                 "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": algo_bytes,
                 "bytes_per_site": bytes_per_site,
                 "kernel_ms_per_launch": round(l1_ms, 4),
-                "kernel_share_of_step": round(float(ach[1].item()) / args.steps / ms_step, 4),
-                "level2_ms_per_launch": round(float(ach[2].item()) / args.steps, 4),
+                "kernel_share_of_step": round(ach[1] / args.steps / ms_step, 4),
+                "level2_ms_per_launch": round(ach[2] / args.steps, 4),
+                "step_minus_kernels_ms": round(ms_step - (ach[1] + ach[2]) / args.steps, 4),
                 "note": ("pos is gathered only at the two edges of each window, so the compulsory stream is "
                          "a+b = 16 B/site (SURVEY.md 8d conservative variant)" if not fused else
                          "a,b,f1,f2 f64 + n1,n2 i32 + genotype i8 = 41 B/site; pos gathered at window edges only")}
     if not fused:
-        roofline["achieved_if_pos_counted_20B"] = round(float(ach[0].item()) * 20 / 16, 1)
+        roofline["achieved_if_pos_counted_20B"] = round(ach[0] * 20 / 16, 1)
 
-    # ---- end to end through the C ABI with host (pinned) columns
+    # ---- end to end through the C ABI with host (pinned) columns: ONE process, ONE table.  At N > 1 rank 0
+    # drives all N GPUs through pgt_scan_sharded (one host thread + stream pair per GPU, every shard's rows
+    # D2H straight into the table at its window offset); the other ranks only wait.
     e2e = None
     if not args.no_e2e:
         try:
-            hcols = {}
-            for k, v in cols.items():
-                if k == "pos":
-                    hcols[k] = v.cpu().numpy()  # gathered on the host at window edges, never copied to the device
-                else:
-                    h = torch.empty(v.shape, dtype=v.dtype, pin_memory=True)
-                    h.copy_(v)
-                    hcols[k] = h.numpy()
-            torch.cuda.synchronize()
-            hout = pgt.scan(plan, stat, hcols, minind=5, window_range=(w_lo, w_hi), site_origin=s_lo, device=dev)
-            for k in fields:  # the host path returns exactly what the resident path computed
-                assert hout[k].tobytes() == out[k].cpu().numpy().tobytes(), f"e2e result differs in {k}"
+            if rank == 0:
+                t_prep = time.perf_counter()
+                pinned = PinnedColumns(pgt, torch, sname, seed, n_total, offs, dev)
+                hcols = pinned.cols
+                prep_s = time.perf_counter() - t_prep
+                devices = list(range(world))
+                hout = pgt.scan_sharded(plan, stat, hcols, devices, minind=5)  # warm-up: contexts, workspaces
+                ref = {k: v.cpu().numpy() for k, v in tab.table().items() if k != "dxy_global"}
+                for k in fields:  # the host path returns exactly what the resident path computed
+                    assert hout[k].tobytes() == ref[k].tobytes(), f"e2e result differs in {k}"
+                del ref
+                times = []
+                for _ in range(args.e2e_steps):
+                    t0 = time.perf_counter()
+                    pgt.scan_sharded(plan, stat, hcols, devices, minind=5, out=hout)
+                    times.append(time.perf_counter() - t0)
+                e_ms = sum(times) / len(times) * 1e3
+                h2d = bytes_per_site * n_total + (world - 1) * bytes_per_site * (W - S)
+                d2h = sum(hout[k].nbytes for k in fields if k in ("sum_a", "sum_b", "fst", "nhet", "nonmissing", "het", "dxy",
+                                                                   "neffective", "nskip"))
+                e2e = {"value": n_total / (e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                       "ms_per_step": round(e_ms, 3), "steps": args.e2e_steps, "timer": "host wall clock around the (synchronous) call",
+                       "n_devices": world, "one_process_one_table": True, "table_equals_resident_table": True,
+                       "host_columns_prep_s": round(prep_s, 1),
+                       "api": "pgt_scan_sharded(plan, stat, host columns, devices[0..N-1]): pinned host columns of the whole genome -> "
+                              "per GPU: 4M-site slabs H2D (double-buffered, copy stream) -> level 1 per slab -> level 2 -> D2H of the "
+                              "shard's rows into the caller's table at its window offset; window positions/labels resolved on the host",
+                       "h2d_gbs": round(h2d / (e_ms * 1e-3) / 1e9, 2)}
+                del hcols, hout
+                pinned.free()
             barrier()
-            x0, x1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            t0 = time.perf_counter()
-            x0.record()
-            for _ in range(args.e2e_steps):
-                pgt.scan(plan, stat, hcols, minind=5, window_range=(w_lo, w_hi), site_origin=s_lo, out=hout, device=dev)
-            x1.record()
-            barrier()
-            wall = time.perf_counter() - t0
-            tt = torch.tensor([x0.elapsed_time(x1), wall * 1e3], device=dev, dtype=torch.float64)
-            if world > 1:
-                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-            e_ms = max(float(tt[0].item()), float(tt[1].item())) / args.e2e_steps
-            h2d = bytes_per_site * n_local
-            d2h = sum(hout[k].nbytes for k in fields if k in ("sum_a", "sum_b", "fst", "nhet", "nonmissing", "het", "dxy",
-                                                               "neffective", "nskip"))
-            bb = torch.tensor([float(h2d), float(d2h)], device=dev, dtype=torch.float64)
-            if world > 1:
-                dist.all_reduce(bb, op=dist.ReduceOp.SUM)
-            e2e = {"value": n_total / (e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(bb[0].item()),
-                   "d2h_bytes_per_step": int(bb[1].item()), "ms_per_step": round(e_ms, 3), "steps": args.e2e_steps,
-                   "api": "pgt_scan(..., PGT_MEM_HOST): pinned host columns -> 4M-site slabs H2D (double-buffered, "
-                          "copy stream) -> level 1 per slab -> level 2 -> D2H of per-window results; window "
-                          "positions/labels resolved on the host; per-rank window tables stay on each rank's host",
-                   "h2d_gbs": round(float(bb[0].item()) / (e_ms * 1e-3) / 1e9, 2)}
-            del hcols, hout
         except Exception as ex:  # report, never fake
             e2e = {"value": None, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0, "error": repr(ex)[:300]}
+            barrier()
+    del cols
+    tab.close()
+    torch.cuda.empty_cache()
+
+    # ---- the other BASELINE configurations, each sharded over the same ranks
+    configs = []
+    if not args.no_configs:
+        want = [c for c in args.configs.split(",") if c]
+        for cfg in CONFIGS:
+            if want and cfg["name"] not in want:
+                continue
+            if cfg["name"] == args.workload:
+                continue
+            try:
+                res = run_config(cfg, R, pgt, args.config_steps, peak)
+            except Exception as ex:
+                res = dict(name=cfg["name"], error=repr(ex)[:300])
+                try:
+                    barrier()
+                except Exception:
+                    pass
+            configs.append(res)
 
     # ---- CPU baseline next to it (rank 0, N = 1 only)
     cpu = None
@@ -483,21 +681,27 @@ def run_b200(args):
 
     if rank == 0:
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": int(nw.item()),
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": W_steps,
             "ms_per_step": round(ms_step, 4), "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": wl["desc"], "name": args.workload, "n_sites": n_total, "contigs": 24,
                        "winsize_sites": W, "stepsize_sites": S, "windows": plan.num_windows, "units": plan.num_units,
                        "unit_sites": unit_sites or 256, "sharding": f"site ranges cut at window starts, halo = W-S = {W - S} sites, {world} shard(s)",
                        "l2": "inputs (>= 6 GB per GPU) exceed the 126 MB L2; no flush needed",
-                       "gather": ("NCCL gather of the packed per-window results to rank 0 inside every timed step"
-                                  if world > 1 else "single GPU: results stay in HBM")},
+                       "clock_warmup": "uncounted steps for >= 0.3 s before the W counted warm-up steps",
+                       "gather": ("none: every rank's window kernel writes its rows into the one table in rank 0's HBM "
+                                  "(CUDA IPC mapping over NVLink); no collective inside a step" if world > 1
+                                  else "single GPU: results stay in HBM")},
+            "result_checksum": result_checksum,
             "clocks": clk.summary(),
             "e2e": e2e if e2e is not None else {"value": None, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": total_launches,
             "roofline": roofline,
+            "configs": configs,
             "cpu_baseline": cpu,
         }
+        if glob is not None:
+            line["dxy_global"] = [float(x) for x in glob]
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()

@@ -101,6 +101,13 @@ int pgt_scan_extreme(const pgt_xplan* plan, const pgt_range* range, pgt_xstat st
                      const double* score, const pgt_xwindows* out, void* workspace, size_t workspace_bytes, pgt_mem mem,
                      void* stream);
 
+/* One host column set, several GPUs of one process (see pgt_scan_sharded in pgt_scan.h): the window list is cut by
+ * pgt_xplan_shard, shard i runs on devices[i] from its own host thread and writes its rows into `out` (host arrays of
+ * pgt_xplan_num_windows elements) at its window offset.  `pos` / `score` are host columns over ALL sites.  Scratch is
+ * allocated and freed by the call.  Results are bit-identical for any device list (the reduction is exact). */
+int pgt_scan_extreme_sharded(const pgt_xplan* plan, pgt_xstat stat, double cutoff, const uint32_t* pos, const double* score,
+                             const pgt_xwindows* out, const int* devices, uint32_t ndev);
+
 /* Synthetic score column of global sites [site0, site0+n): ~N(0,1) with heavy ties removed
  * (counter-based, bit-identical to the CPU twin in pgt_synth.h).  Device pointer. */
 int pgt_synth_score(uint64_t seed, uint64_t site0, uint64_t n, double* score, void* stream);

@@ -83,6 +83,15 @@ int pgt_host_unregister(void* p);
 int pgt_device_alloc(void** p, size_t bytes);
 int pgt_device_free(void* p);
 
+/* One process per GPU: result tables shared inside a box.  The owner (rank 0) exports memory it got
+ * from pgt_device_alloc as a 64-byte handle, the other processes map it (peer access over NVLink is enabled on
+ * first use) and pass pointers into it as their pgt_windows arrays: every shard's window kernel then writes its
+ * rows straight into the owner's table, and no gather step exists.  Close before the owner frees. */
+#define PGT_IPC_HANDLE_BYTES 64
+int pgt_ipc_export(const void* devptr, void* handle, size_t handle_bytes);
+int pgt_ipc_open(const void* handle, void** devptr);
+int pgt_ipc_close(void* devptr);
+
 /* ---- plan: which windows exist (replaces the flush triggers of calcFst & co.) ----------
  *
  * contig_offsets[ncontig+1]: cumulative sizes, contig c spans [off[c], off[c+1]) in site
@@ -217,6 +226,21 @@ int pgt_scan(const pgt_plan* plan, const pgt_range* range, pgt_stat stat, const 
              const uint64_t* site_offsets, const pgt_windows* out, void* workspace, size_t workspace_bytes,
              pgt_mem mem, void* stream);
 
+/* One host column set, several GPUs of ONE process (the reference is a single process, fstWindow.cpp:158-177: a
+ * user of the drop-in tools on an 8-GPU box should not have to split the input).  The window list is cut by
+ * pgt_plan_shard into `ndev` contiguous ranges; shard i runs the PGT_MEM_HOST scan on devices[i] from its own
+ * host thread and stream, reads only the slabs of `cols` its windows cover (columns address the WHOLE axis, as
+ * for an unsharded scan with site_origin 0) and copies its rows device -> host straight into `out` at its window
+ * offset; `out` arrays hold pgt_plan_num_windows elements.  No gather, no collective.  Per-window results are
+ * bit-identical for any ndev; dxy_global is the sum of the shards' disjoint partial lines in shard order.
+ * workspaces[i] is device memory on devices[i] of at least pgt_scan_sharded_workspace_bytes(plan, stat, i, ndev);
+ * workspaces = workspace_bytes = NULL lets the call allocate and free its scratch itself.
+ * The plan must not be bound to a device (pgt_plan_bind_device). */
+size_t pgt_scan_sharded_workspace_bytes(const pgt_plan* plan, pgt_stat stat, uint32_t shard, uint32_t nshards);
+int pgt_scan_sharded(const pgt_plan* plan, pgt_stat stat, const pgt_columns* cols, int minind,
+                     const uint64_t* site_offsets, const pgt_windows* out, const int* devices, uint32_t ndev,
+                     void* const* workspaces, const size_t* workspace_bytes);
+
 /* Convenience entry points named after the tools they replace. */
 int pgt_scan_fst(const pgt_plan* plan, const pgt_range* range, const pgt_columns* cols, const pgt_windows* out,
                  void* workspace, size_t workspace_bytes, pgt_mem mem, void* stream);
@@ -248,7 +272,7 @@ int pgt_profile_read(double* units_ms, uint64_t* units_launches, double* windows
 /* Tuning knobs for tests and experiments (never needed for correct results):
  *   "level1": 0 auto | 1 direct warp-per-unit kernel (long units only) | 2 tiled TMA-staged kernel
  *   "level2": 0 auto | 1 always warp-per-window | 2 always scan mode (block prefix/suffix scans)
- *   "slide": 0 auto | 1 never use the sliding-tile kernel for fine steps | 2 use it for every site-mode geometry whose block fits shared memory (W <= 1417)
+ *   "slide": 0 auto | 1 never use the sliding-tile kernel for fine steps | 2 use it for every site-mode geometry whose block fits shared memory (W <= 1288)
  *   "hoststage": experiment, 0 off (default) | 1 PGT_MEM_HOST from pageable (unpinned) columns through a ring of
  *                small pinned buffers filled by several host threads instead of the driver's pageable staging
  *   "stages", "stage_kb": shared-memory ring of the tiled kernel

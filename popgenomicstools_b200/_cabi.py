@@ -64,6 +64,9 @@ PROTOTYPES = {
     "pgt_host_unregister": (C.c_int, [C.c_void_p]),
     "pgt_device_alloc": (C.c_int, [C.POINTER(C.c_void_p), C.c_size_t]),
     "pgt_device_free": (C.c_int, [C.c_void_p]),
+    "pgt_ipc_export": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
+    "pgt_ipc_open": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
+    "pgt_ipc_close": (C.c_int, [C.c_void_p]),
     "pgt_plan_create": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32,
                                   C.c_uint32]),
     "pgt_plan_destroy": (None, [C.c_void_p]),
@@ -82,6 +85,9 @@ PROTOTYPES = {
     "pgt_scan_workspace_bytes": (C.c_size_t, [C.c_void_p, C.POINTER(PgtRange), C.c_int, C.c_int]),
     "pgt_scan": (C.c_int, [C.c_void_p, C.POINTER(PgtRange), C.c_int, C.POINTER(PgtColumns), C.c_int, C.c_void_p,
                            C.POINTER(PgtWindows), C.c_void_p, C.c_size_t, C.c_int, C.c_void_p]),
+    "pgt_scan_sharded_workspace_bytes": (C.c_size_t, [C.c_void_p, C.c_int, C.c_uint32, C.c_uint32]),
+    "pgt_scan_sharded": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(PgtColumns), C.c_int, C.c_void_p, C.POINTER(PgtWindows),
+                                   C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p]),
     "pgt_scan_fst": (C.c_int, [C.c_void_p, C.POINTER(PgtRange), C.POINTER(PgtColumns), C.POINTER(PgtWindows),
                                C.c_void_p, C.c_size_t, C.c_int, C.c_void_p]),
     "pgt_scan_het": (C.c_int, [C.c_void_p, C.POINTER(PgtRange), C.POINTER(PgtColumns), C.POINTER(PgtWindows),
@@ -114,6 +120,8 @@ PROTOTYPES = {
     "pgt_scan_extreme_workspace_bytes": (C.c_size_t, [C.c_void_p, C.POINTER(PgtRange), C.c_int]),
     "pgt_scan_extreme": (C.c_int, [C.c_void_p, C.POINTER(PgtRange), C.c_int, C.c_double, C.c_void_p, C.c_void_p,
                                    C.POINTER(PgtXWindows), C.c_void_p, C.c_size_t, C.c_int, C.c_void_p]),
+    "pgt_scan_extreme_sharded": (C.c_int, [C.c_void_p, C.c_int, C.c_double, C.c_void_p, C.c_void_p, C.POINTER(PgtXWindows), C.c_void_p,
+                                           C.c_uint32]),
     "pgt_synth_score": (C.c_int, [C.c_uint64, C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p]),
     "pgt_profile_read_extreme": (C.c_int, [C.POINTER(C.c_double), _u64p, C.POINTER(C.c_double), _u64p]),
 }

@@ -84,6 +84,27 @@ extern "C" int pgt_device_free(void* p) {
 	PGT_CUDA(cudaFree(p));
 	return PGT_OK;
 }
+// ---- result tables shared between the processes of one box (one process per GPU): rank 0 exports
+// its table (pgt_device_alloc memory), the others map it and pass pointers into it as their `out` arrays, so the
+// window kernels write each shard's rows straight into rank 0's HBM over NVLink -- no gather step at all.
+extern "C" int pgt_ipc_export(const void* devptr, void* handle, size_t handle_bytes) {
+	if (!devptr || !handle || handle_bytes < sizeof(cudaIpcMemHandle_t)) return pgt_set_error(PGT_ERR_ARGS, "pgt_ipc_export: need a device pointer and 64 bytes for the handle");
+	cudaIpcMemHandle_t h;
+	PGT_CUDA(cudaIpcGetMemHandle(&h, const_cast<void*>(devptr)));
+	memcpy(handle, &h, sizeof(h));
+	return PGT_OK;
+}
+extern "C" int pgt_ipc_open(const void* handle, void** devptr) {
+	if (!handle || !devptr) return pgt_set_error(PGT_ERR_ARGS, "pgt_ipc_open: NULL");
+	cudaIpcMemHandle_t h;
+	memcpy(&h, handle, sizeof(h));
+	PGT_CUDA(cudaIpcOpenMemHandle(devptr, h, cudaIpcMemLazyEnablePeerAccess));
+	return PGT_OK;
+}
+extern "C" int pgt_ipc_close(void* devptr) {
+	PGT_CUDA(cudaIpcCloseMemHandle(devptr));
+	return PGT_OK;
+}
 extern "C" int pgt_host_register(void* p, size_t bytes) {
 	PGT_CUDA(cudaHostRegister(p, bytes, cudaHostRegisterDefault));
 	return PGT_OK;
@@ -181,7 +202,7 @@ static int g_tune_level2 = 0;
 static int g_tune_stages = 2;      // tiled kernel: shared-memory stages (2..4)
 static int g_tune_stage_kb = 110;  // tiled kernel: KB per stage (stages * stage_kb <= 224)
 extern int g_tune_xgroup;          // extreme scan (pgt_extreme.cu): lanes per unit, 0 = auto
-//   slide: 0 auto, 1 never use the sliding-tile kernel (k_slide), 2 use it whenever it fits shared memory (any W <= 1417)
+//   slide: 0 auto, 1 never use the sliding-tile kernel (k_slide), 2 use it whenever it fits shared memory (any W <= 1288)
 static int g_tune_slide = 0;
 //   hoststage: PGT_MEM_HOST from pageable columns through the pinned ring (PinnedRing below): 0 off (default), 1 on
 static int g_tune_hoststage = 0;
@@ -485,8 +506,9 @@ __global__ void __launch_bounds__(256) k_units(DevPlan P, Cols cols, typename St
 static constexpr int kTileThreads = 512;
 static constexpr int kTileMaxStages = 4;
 static constexpr int kTileConsumerWarps = kTileThreads / 32 - 1;
-static constexpr int kMaxTileCols = 7;
-static constexpr uint32_t kTileCtlBytes = 384;
+static constexpr int kMaxTileCols = 7;  // of a statistic; the sliding tile stages `pos` as one more (kMaxStageCols)
+static constexpr int kMaxStageCols = kMaxTileCols + 1;
+static constexpr uint32_t kTileCtlBytes = 384;  // >= sizeof(TileCtl) = 352
 
 
 // With more segments than this the tiled kernel gets a precomputed tile -> segment table: a CTA's
@@ -497,10 +519,10 @@ static constexpr size_t kTileSegTableMin = 32;
 
 struct TileCfg {
 	const uint32_t* tile_seg;  // [ntiles] segment of each tile's first unit, or NULL (few segments / bp mode)
-	const char* gcol[kMaxTileCols];  // global column pointers (element 0 = site_origin), staging order
-	uint32_t elem[kMaxTileCols];     // bytes per site
-	uint32_t col_off[kMaxTileCols];  // byte offset of the column's region inside a stage
-	uint32_t col_cap[kMaxTileCols];  // capacity of that region in bytes
+	const char* gcol[kMaxStageCols];  // global column pointers (element 0 = site_origin), staging order
+	uint32_t elem[kMaxStageCols];     // bytes per site
+	uint32_t col_off[kMaxStageCols];  // byte offset of the column's region inside a stage
+	uint32_t col_cap[kMaxStageCols];  // capacity of that region in bytes
 	uint32_t ncol;
 	uint32_t m;            // units per tile
 	uint32_t stage_bytes;
@@ -513,7 +535,7 @@ struct TileCtl {
 	uint64_t full[kTileMaxStages];
 	uint64_t empty[kTileMaxStages];
 	uint64_t s0[kTileMaxStages];                   // column element index of the tile's first site
-	const char* cp[kTileMaxStages][kMaxTileCols];  // where site s0 of each column lives (shared, or global if unstaged)
+	const char* cp[kTileMaxStages][kMaxStageCols];  // where site s0 of each column lives (shared, or global if unstaged)
 };
 static_assert(sizeof(TileCtl) <= kTileCtlBytes, "control block");
 
@@ -1218,8 +1240,8 @@ __global__ void __launch_bounds__(256) k_windows_hgw(DevPlan P, const typename S
 //     additions of true partial sums, no differences, no cancellation;
 //   * persistent CTAs take CHUNKS of consecutive windows; a chunk walks its blocks in order: the
 //     producer warp stages block b's slice of every column with bulk async copies (the ring of
-//     k_units_tiled), the 256 consumer threads scan it in registers (thread t owns elements
-//     [t*E, (t+1)*E), E = ceil(W / 256): forward total, two warp shuffle scans, warp totals through
+//     k_units_tiled), the 224 consumer threads scan it in registers (thread t owns elements
+//     [t*E, (t+1)*E), E = ceil(W / 224): forward total, two warp shuffle scans, warp totals through
 //     shared memory, then PRE running forward from the thread's base into `Pr` and SUF running backward
 //     in place), emit the windows that start in block b - 1 from Sf (= SUF_{b-1}) and Pr, and keep
 //     SUF_b for the next step.  Every site is read once per chunk; neighbouring chunks share W - S sites.
@@ -1229,15 +1251,17 @@ __global__ void __launch_bounds__(256) k_windows_hgw(DevPlan P, const typename S
 // outside its windows absent, and those only ever enter prefix / suffix values no window of the chunk
 // reads), so results are bit-identical for any GPU count.  Reference semantics: fstWindow.cpp:80-99.
 
-static constexpr int kSlideWarps = 8;                          // consumer warps
-static constexpr int kSlideConsumers = kSlideWarps * 32;       // part of the summation order (E = ceil(W / 256))
+static constexpr int kSlideWarps = 7;                          // consumer warps (+ the producer warp = 256 threads: 128 registers each at two CTAs per SM)
+static constexpr int kSlideConsumers = kSlideWarps * 32;       // part of the summation order (E = ceil(W / 224))
 static constexpr int kSlideThreads = kSlideConsumers + 32;     // + the producer warp (the last one)
-static constexpr uint32_t kSlideMaxE = 6;                      // W <= 1536 (and the fused block must fit shared memory: W <= 1417)
-static constexpr uint32_t kSlideWtBytes = 512;                 // warp totals: 8 x Acc (<= 40 B)
+static constexpr uint32_t kSlideMaxE = 6;                      // W <= 1344 (and the fused block must fit shared memory: W <= 1288)
+static constexpr uint32_t kSlideWtBytes = 512;                 // warp totals: 7 x Acc (<= 40 B)
 
 struct SlideCfg {
 	uint32_t E;              // elements of a block per consumer thread
-	uint32_t sf_off, pr_off, stage_off;  // byte offsets inside the dynamic shared memory
+	uint32_t sf_off, pr_off, pos_off, stage_off;  // byte offsets inside the dynamic shared memory
+	uint32_t pos_stride;     // elements of one of the two position buffers
+	uint32_t pos_col;        // staging index of the position column, 0xffffffff = positions not wanted
 	uint64_t chunk_windows;  // windows per chunk
 	uint64_t nchunks;
 };
@@ -1282,17 +1306,29 @@ __device__ __forceinline__ bool slide_run_at(const DevPlan& P, uint64_t w, uint6
 	return true;
 }
 
+// (register budget: two CTAs per SM for the narrow statistics -- 112 registers -- and one for the fused
+// scan, whose block fills the shared memory of an SM anyway)
+template <class Stat>
+struct SlideMinBlocks {
+	static constexpr int value = 2;
+};
+template <>
+struct SlideMinBlocks<FusedStat> {
+	static constexpr int value = 1;
+};
 template <class Stat, int EMAX>
-__global__ void __launch_bounds__(kSlideThreads) k_slide(DevPlan P, TileCfg tc, SlideCfg sc, const uint32_t* __restrict__ pos, pgt_windows out) {
+__global__ void __launch_bounds__(kSlideThreads, SlideMinBlocks<Stat>::value) k_slide(DevPlan P, TileCfg tc, SlideCfg sc, pgt_windows out) {
 	typedef typename Stat::Acc Acc;
 	extern __shared__ __align__(128) unsigned char smem[];
 	TileCtl* ctl = reinterpret_cast<TileCtl*>(smem);
 	Acc* wt = reinterpret_cast<Acc*>(smem + kTileCtlBytes);
 	Acc* Sf = reinterpret_cast<Acc*>(smem + sc.sf_off);
 	Acc* Pr = reinterpret_cast<Acc*>(smem + sc.pr_off);
+	uint32_t* posb = reinterpret_cast<uint32_t*>(smem + sc.pos_off);  // positions of the blocks b - 1 and b: [2][pos_stride]
 	unsigned char* stages = smem + sc.stage_off;
 	const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
 	const uint64_t W = P.g.W, S = P.g.S;
+	const bool has_pos = sc.pos_col != 0xffffffffu;
 
 	if (threadIdx.x == 0) {
 		for (uint32_t s = 0; s < tc.nstages; ++s) {
@@ -1333,6 +1369,14 @@ __global__ void __launch_bounds__(kSlideThreads) k_slide(DevPlan P, TileCfg tc, 
 		SlideRun r;
 		for (bool ok = slide_run_at(P, wa, wb, r, true); ok; ok = slide_run_at(P, r.sg.win_base + r.kb, wb, r, false)) {
 			const uint64_t m_first = r.lo / W, m_last = (r.hi - 1) / W;
+			// label = contig of the window's last site: the windows a thread emits go up the axis, so a cursor
+			// that only walks forward replaces a binary search per window
+			uint32_t lc = r.sg.first_contig;
+			uint64_t lc_end = r.sg.ncontig > 1 ? P.off[lc + 1] : ~0ull;  // global site where contig lc ends
+			// kc_cur = ceil(b*W / S): first window that starts at or after block b; kept incrementally
+			uint64_t kq = m_first * W / S;
+			uint32_t krem = (uint32_t)(m_first * W - kq * S);
+			uint64_t kc_cur = kq + (krem != 0u), kc_prev = kc_cur;
 			for (uint64_t b = m_first; b <= m_last + 1; ++b) {
 				const bool incoming = b <= m_last;  // block b arrives; the windows starting in block b - 1 leave
 				Acc leaf[EMAX];
@@ -1348,16 +1392,21 @@ __global__ void __launch_bounds__(kSlideThreads) k_slide(DevPlan P, TileCfg tc, 
 					const uint64_t x1 = (b + 1) * W < r.hi ? (b + 1) * W : r.hi;
 					// sites of the block outside [x0, x1) are absent (other chunk / beyond the segment): +0 leaves
 					const uint32_t i_lo = (uint32_t)(x0 - b * W), i_hi = (uint32_t)(x1 - b * W);
+					uint32_t* pb = posb + (b & 1u) * sc.pos_stride;
+					const uint32_t* pstage = has_pos ? reinterpret_cast<const uint32_t*>(ctl->cp[stg][sc.pos_col]) : nullptr;
 					Acc tot = Stat::zero();
 #pragma unroll
 					for (int e = 0; e < EMAX; ++e) {
 						leaf[e] = Stat::zero();
 						const uint32_t i = e0 + (uint32_t)e;
-						if ((uint32_t)e < sc.E && i >= i_lo && i < i_hi) Stat::fold(leaf[e], Stat::load_tile(cp, i - i_lo), tc.minind);
+						if ((uint32_t)e < sc.E && i >= i_lo && i < i_hi) {
+							Stat::fold(leaf[e], Stat::load_tile(cp, i - i_lo), tc.minind);
+							if (has_pos) pb[i] = pstage[i - i_lo];
+						}
 						Stat::add(tot, leaf[e]);
 					}
 					__syncwarp();
-					if (lane == 0) mbar_arrive(&ctl->empty[stg]);  // the block now lives in registers
+					if (lane == 0) mbar_arrive(&ctl->empty[stg]);  // the block now lives in registers (positions: in posb)
 					up = tot;
 					dn = tot;
 #pragma unroll
@@ -1378,8 +1427,12 @@ __global__ void __launch_bounds__(kSlideThreads) k_slide(DevPlan P, TileCfg tc, 
 				slide_bar();  // warp totals visible
 				if (incoming) {
 					Acc bpre = Stat::zero(), bsuf = Stat::zero();
-					for (uint32_t w2 = 0; w2 < warp; ++w2) Stat::add(bpre, wt[w2]);
-					for (uint32_t w2 = kSlideWarps - 1; w2 > warp; --w2) Stat::add(bsuf, wt[w2]);
+#pragma unroll
+					for (int w2 = 0; w2 < kSlideWarps - 1; ++w2)
+						if ((uint32_t)w2 < warp) Stat::add(bpre, wt[w2]);
+#pragma unroll
+					for (int w2 = kSlideWarps - 1; w2 > 0; --w2)
+						if ((uint32_t)w2 > warp) Stat::add(bsuf, wt[w2]);
 					Acc xu = shfl_up_acc(up, 1), xd = shfl_down_acc(dn, 1);
 					if (lane == 0) xu = Stat::zero();
 					if (lane == 31u) xd = Stat::zero();
@@ -1400,21 +1453,54 @@ __global__ void __launch_bounds__(kSlideThreads) k_slide(DevPlan P, TileCfg tc, 
 						}
 					}
 				}
-				slide_bar();  // Pr complete (Sf holds SUF of block b - 1)
+				slide_bar();  // Pr and the positions of block b complete (Sf holds SUF of block b - 1)
 				if (b > m_first) {
+					// windows with (b-1)*W <= k*S < b*W, cut to the run; everything below is relative to block b - 1
 					const uint64_t mb = b - 1;
-					uint64_t k_lo = (mb * W + S - 1) / S, k_hi = (b * W + S - 1) / S;  // windows with mb*W <= k*S < b*W
-					if (k_lo < r.ka) k_lo = r.ka;
-					if (k_hi > r.kb) k_hi = r.kb;
-					for (uint64_t k = k_lo + t; k < k_hi; k += kSlideConsumers) {
-						const uint64_t f = k * S;
-						uint64_t l = f + W - 1;
-						if (l > r.sg.nsites - 1) l = r.sg.nsites - 1;
-						Acc acc = Sf[f - mb * W];
-						if (l >= b * W) Stat::add(acc, Pr[l - b * W]);
-						emit_window<Stat>(P, r.sg, r.sg.win_base + k, k, acc, pos, out);
+					const uint64_t k_lo = kc_prev > r.ka ? kc_prev : r.ka, k_hi = kc_cur < r.kb ? kc_cur : r.kb;
+					if (k_hi > k_lo) {
+						const uint32_t cnt = (uint32_t)(k_hi - k_lo), Wu = (uint32_t)W, Su = (uint32_t)S;
+						const uint32_t j0 = (uint32_t)(k_lo * S - mb * W);
+						const uint64_t left = r.sg.nsites - mb * W;  // sites of the segment from block b - 1 on
+						const uint32_t lr_max = (left < 2ull * Wu ? (uint32_t)left : 2u * Wu) - 1u;
+						const uint64_t obase = r.sg.win_base + k_lo - P.win_lo, gbase = r.sg.site_base + mb * W;
+						const uint32_t* pm = posb + (mb & 1u) * sc.pos_stride;  // positions of block b - 1
+						const uint32_t* pn = posb + (b & 1u) * sc.pos_stride;   // positions of block b
+						for (uint32_t i = t; i < cnt; i += kSlideConsumers) {
+							const uint32_t j = j0 + i * Su;
+							uint32_t lr = j + Wu - 1u;
+							if (lr > lr_max) lr = lr_max;
+							const bool two = lr >= Wu;  // the window ends in block b
+							const uint32_t jl = two ? lr - Wu : lr;
+							Acc acc = Sf[j];
+							if (two) Stat::add(acc, Pr[jl]);
+							const uint64_t o = obase + i;
+							const uint64_t glast = gbase + lr;
+							while (glast >= lc_end) {
+								++lc;
+								lc_end = P.off[lc + 1];
+							}
+							if (out.label) out.label[o] = lc;
+							if (out.nsites) out.nsites[o] = lr - j + 1u;
+							if (has_pos) {
+								const uint32_t sp = pm[j], ep = two ? pn[jl] : pm[jl];
+								if (out.start_pos) out.start_pos[o] = sp;
+								if (out.end_pos) out.end_pos[o] = ep;
+								if (out.mid_pos) out.mid_pos[o] = (sp + ep) / 2u;  // uint32 arithmetic, fstWindow.cpp:73
+							}
+							Stat::emit(out, o, acc);
+						}
 					}
 				}
+				// ceil(b*W / S) -> ceil((b+1)*W / S) without a division
+				kc_prev = kc_cur;
+				kq += P.g.q;
+				krem += P.g.r;
+				if (krem >= (uint32_t)S) {
+					krem -= (uint32_t)S;
+					++kq;
+				}
+				kc_cur = kq + (krem != 0u);
 				slide_bar();  // Sf no longer read
 				if (incoming) {
 #pragma unroll
@@ -1425,7 +1511,6 @@ __global__ void __launch_bounds__(kSlideThreads) k_slide(DevPlan P, TileCfg tc, 
 		}
 	}
 }
-
 
 // dxyWindow's global line (dxyWindow.cpp:382-385,429-433) over the unit partials [0, n): one
 // block; thread t adds partials t, t+1024, ...; warp butterflies; counts in 64 bit.
@@ -1573,25 +1658,30 @@ struct Layout {
 // The choice fixes the summation order, so it is a pure function of (W, S, unit, statistic) and the
 // tuning knob -- never of the input size, the window range or the shard.
 struct SlideShape {
-	uint32_t E, nstages, stage_bytes, sf_off, pr_off, stage_off;
-	uint32_t col_off[kMaxTileCols], col_cap[kMaxTileCols];
+	uint32_t E, nstages, stage_bytes, sf_off, pr_off, pos_off, pos_stride, stage_off, ncol;
+	uint32_t col_off[kMaxStageCols], col_cap[kMaxStageCols];
 	size_t smem;
 };
+// (sized with the position column staged, whether or not a scan passes positions: the choice of path must
+// not depend on it)
 static void slide_footprint(const pgt_geom& g, pgt_stat stat, SlideShape* sh) {
 	ColDesc d[8];
 	const int nc = stat_columns(stat, PGT_MODE_SITES, nullptr, d);
 	uint32_t o = 0;
-	for (int c = 0; c < nc; ++c) {
+	for (int c = 0; c <= nc; ++c) {  // column nc = pos (uint32)
 		sh->col_off[c] = o;
-		sh->col_cap[c] = (uint32_t)align_up((size_t)g.W * d[c].elem + 48, 16);
+		sh->col_cap[c] = (uint32_t)align_up((size_t)g.W * (c < nc ? d[c].elem : 4) + 48, 16);
 		o += sh->col_cap[c];
 	}
+	sh->ncol = (uint32_t)nc;
 	sh->stage_bytes = (uint32_t)align_up(o, 128);
 	sh->E = (g.W + kSlideConsumers - 1) / kSlideConsumers;
 	const uint32_t accb = (uint32_t)align_up((size_t)g.W * acc_bytes(stat), 128);
 	sh->sf_off = kTileCtlBytes + kSlideWtBytes;
 	sh->pr_off = sh->sf_off + accb;
-	sh->stage_off = sh->pr_off + accb;
+	sh->pos_off = sh->pr_off + accb;
+	sh->pos_stride = (uint32_t)align_up(g.W, 32);
+	sh->stage_off = sh->pos_off + 2 * sh->pos_stride * 4;
 }
 static bool slide_shape(const pgt_geom& g, pgt_mode mode, pgt_stat stat, SlideShape* sh) {
 	if (mode != PGT_MODE_SITES || g_tune_slide == 1) return false;
@@ -1604,7 +1694,7 @@ static bool slide_shape(const pgt_geom& g, pgt_mode mode, pgt_stat stat, SlideSh
 	const size_t half = 113u * 1024u, full = 226u * 1024u;
 	// One rule for all statistics (the fused scan must equal the three single scans bit for bit): the block
 	// of the widest one -- fused, 41 B/site staged twice + two 40-byte accumulators per site -- has to fit,
-	// which bounds W at about 1400 sites.
+	// which bounds W at 1288 sites.
 	slide_footprint(g, PGT_STAT_FUSED, sh);
 	if (sh->stage_off + 2 * (size_t)sh->stage_bytes > full) return false;
 	slide_footprint(g, stat, sh);
@@ -2040,18 +2130,18 @@ static int launch_slide(const pgt_plan* plan, pgt_stat stat, const DevPlan& P, c
 	const StatCols scol = tile_columns<Stat>(cols);
 	TileCfg tc;
 	memset(&tc, 0, sizeof(tc));
-	tc.ncol = scol.n;
+	tc.ncol = scol.n + (pos ? 1u : 0u);  // positions ride the ring too: read from HBM once, gathered from shared memory
 	tc.nstages = sh.nstages;
 	tc.stage_bytes = sh.stage_bytes;
 	tc.minind = cols.minind;
 	tc.valid_elems = valid_elems;
-	for (uint32_t c = 0; c < scol.n; ++c) {
-		tc.gcol[c] = (const char*)scol.ptr[c];
-		tc.elem[c] = scol.elem[c];
+	for (uint32_t c = 0; c < tc.ncol; ++c) {
+		tc.gcol[c] = c < scol.n ? (const char*)scol.ptr[c] : (const char*)pos;
+		tc.elem[c] = c < scol.n ? scol.elem[c] : 4u;
 		tc.col_off[c] = sh.col_off[c];
 		tc.col_cap[c] = sh.col_cap[c];
 	}
-	void (*kern)(DevPlan, TileCfg, SlideCfg, const uint32_t*, pgt_windows);
+	void (*kern)(DevPlan, TileCfg, SlideCfg, pgt_windows);
 	if (sh.E <= 2) kern = k_slide<Stat, 2>;
 	else if (sh.E <= 4) kern = k_slide<Stat, 4>;
 	else kern = k_slide<Stat, 6>;
@@ -2068,13 +2158,16 @@ static int launch_slide(const pgt_plan* plan, pgt_stat stat, const DevPlan& P, c
 	sc.E = sh.E;
 	sc.sf_off = sh.sf_off;
 	sc.pr_off = sh.pr_off;
+	sc.pos_off = sh.pos_off;
+	sc.pos_stride = sh.pos_stride;
+	sc.pos_col = pos ? scol.n : 0xffffffffu;
 	sc.stage_off = sh.stage_off;
 	sc.chunk_windows = std::max<uint64_t>(32 * wpb, (nwin + slots * 4 - 1) / (slots * 4));
 	sc.nchunks = (nwin + sc.chunk_windows - 1) / sc.chunk_windows;
 	const unsigned grid = (unsigned)std::min<uint64_t>(sc.nchunks, slots);
 	{
 		ProfScope prof(0, st);
-		kern<<<grid, kSlideThreads, sh.smem, st>>>(P, tc, sc, pos, out);
+		kern<<<grid, kSlideThreads, sh.smem, st>>>(P, tc, sc, out);
 	}
 	g_launches++;
 	PGT_CUDA(cudaGetLastError());

@@ -556,10 +556,8 @@ int main(int argc, char** argv) {
 		range.w_hi = nwin;
 		range.site_count = n_used;
 		std::vector<uint64_t> soff_used(soff.begin(), soff.begin() + nchr + 1);
-		DeviceWorkspace ws;
-		ws.bytes = pgt_scan_workspace_bytes(plan, &range, PGT_STAT_DXY, PGT_MEM_HOST);
-		if (pgt_device_alloc(&ws.p, ws.bytes) != PGT_OK ||
-		    pgt_scan(plan, &range, PGT_STAT_DXY, &cols, minind, fixedsite ? nullptr : soff_used.data(), &out, ws.p, ws.bytes, PGT_MEM_HOST, nullptr) != PGT_OK) {
+		// (n_used == soff_used[nchr]: the sharded call's "up to the end of the genome" is the same range)
+		if (scan_on_devices(plan, &range, PGT_STAT_DXY, &cols, minind, fixedsite ? nullptr : soff_used.data(), &out) != PGT_OK) {
 			fprintf(stderr, "dxyWindow: %s\n", pgt_last_error());
 			return -1;
 		}

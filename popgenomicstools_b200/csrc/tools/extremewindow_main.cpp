@@ -428,15 +428,22 @@ int main(int argc, char** argv) {
 		out.ext_pos = extpos.data();
 		out.prop = prop.data();
 		out.nsites = cnt.data();
-		DeviceWorkspace ws;
-		ws.bytes = pgt_scan_extreme_workspace_bytes(plan, nullptr, PGT_MEM_HOST);
 #if defined(PGT_TOOL_IHS)
 		const pgt_xstat which = PGT_XSTAT_IHS;
 #else
 		const pgt_xstat which = PGT_XSTAT_XPEHH;
 #endif
-		if (pgt_device_alloc(&ws.p, ws.bytes) != PGT_OK ||
-		    pgt_scan_extreme(plan, nullptr, which, cutoff, pos, score, &out, ws.p, ws.bytes, PGT_MEM_HOST, nullptr) != PGT_OK) {
+		const std::vector<int>& devs = device_list();
+		DeviceWorkspace ws;
+		int rc;
+		if (devs.size() > 1) {  // PGT_DEVICES: one shard of windows per GPU, same table
+			rc = pgt_scan_extreme_sharded(plan, which, cutoff, pos, score, &out, devs.data(), (uint32_t)devs.size());
+		} else {
+			ws.bytes = pgt_scan_extreme_workspace_bytes(plan, nullptr, PGT_MEM_HOST);
+			rc = pgt_device_alloc(&ws.p, ws.bytes);
+			if (rc == PGT_OK) rc = pgt_scan_extreme(plan, nullptr, which, cutoff, pos, score, &out, ws.p, ws.bytes, PGT_MEM_HOST, nullptr);
+		}
+		if (rc != PGT_OK) {
 			fprintf(stderr, "%s: %s\n", kTool, pgt_last_error());
 			return -1;
 		}

@@ -404,27 +404,42 @@ struct DeviceWorkspace {
 	}
 };
 
-// The tools use ONE GPU (PGT_DEVICE, default 0).  CUDA start-up enumerates and initialises every
-// visible device (~0.3 s each on an 8-GPU box), so unless the user already set CUDA_VISIBLE_DEVICES
-// the process restricts itself to its device before the first CUDA call; the device is then index 0.
-inline int& device_index() {
-	static int idx = -1;
-	return idx;
+// The tools use one GPU (PGT_DEVICE, default 0) or several of one box (PGT_DEVICES=0,1,...: the window list is
+// sharded over them by pgt_scan_sharded, one host thread per GPU, same stdout).  CUDA start-up enumerates and
+// initialises every visible device (~0.3 s each on an 8-GPU box), so unless the user already set
+// CUDA_VISIBLE_DEVICES the process restricts itself to its devices before the first CUDA call; they are then
+// indices 0..n-1.
+inline std::vector<int>& device_list() {
+	static std::vector<int> list;
+	return list;
 }
 inline int chosen_device() {
-	int& idx = device_index();
-	if (idx >= 0) return idx;
-	const char* env = getenv("PGT_DEVICE");
-	const int want = env ? atoi(env) : 0;
-	if (!getenv("CUDA_VISIBLE_DEVICES") && want >= 0) {
-		char buf[16];
-		snprintf(buf, sizeof(buf), "%d", want);
-		setenv("CUDA_VISIBLE_DEVICES", buf, 1);
-		idx = 0;
-	} else {
-		idx = want;
+	std::vector<int>& list = device_list();
+	if (!list.empty()) return list[0];
+	std::vector<int> want;
+	if (const char* env = getenv("PGT_DEVICES")) {
+		for (const char* p = env; *p;) {
+			char* e = nullptr;
+			const long v = strtol(p, &e, 10);
+			if (e == p) break;
+			if (v >= 0) want.push_back((int)v);
+			p = (*e == ',') ? e + 1 : e;
+			if (*e != ',' && *e != 0) break;
+		}
 	}
-	return idx;
+	if (want.empty()) {
+		const char* env = getenv("PGT_DEVICE");
+		want.push_back(env ? atoi(env) : 0);
+	}
+	if (!getenv("CUDA_VISIBLE_DEVICES") && want[0] >= 0) {
+		std::string vis;
+		for (size_t i = 0; i < want.size(); ++i) vis += (i ? "," : "") + std::to_string(want[i]);
+		setenv("CUDA_VISIBLE_DEVICES", vis.c_str(), 1);
+		for (size_t i = 0; i < want.size(); ++i) list.push_back((int)i);
+	} else {
+		list = want;
+	}
+	return list[0];
 }
 
 inline int select_device() {
@@ -443,27 +458,37 @@ inline int select_device() {
 	return 0;
 }
 
-// CUDA start-up (driver + context, ~1-2 s on a B200 box) overlaps with text parsing: a helper
-// thread brings the device up while the parser threads run; the main thread joins it before the scan.
+// CUDA start-up (driver + context, ~1-2 s on a B200 box) overlaps with text parsing: helper threads bring the
+// device(s) up while the parser threads run; the main thread joins them before the scan.
 struct DeviceWarmup {
 	std::thread th;
 	int rc = 0;
 	double ms = 0;
 	std::string err;
 	void start() {
-		const int dev = chosen_device();  // on the calling thread, before any CUDA call
-		th = std::thread([this, dev]() {
+		chosen_device();  // on the calling thread, before any CUDA call
+		const std::vector<int> devs = device_list();
+		th = std::thread([this, devs]() {
 			const double t0 = now_ms();
 			int n = pgt_device_count();
 			if (n <= 0) {
 				rc = -1;
 				err = n < 0 ? pgt_last_error() : "device count is 0";
-			} else if (pgt_set_device(dev) != PGT_OK) {
-				rc = -1;
-				err = pgt_last_error();
 			} else {
-				void* p = nullptr;  // forces context creation
-				if (pgt_device_alloc(&p, 1 << 20) == PGT_OK) pgt_device_free(p);
+				std::vector<std::thread> per;
+				std::vector<std::string> errs(devs.size());
+				for (size_t i = 0; i < devs.size(); ++i)
+					per.emplace_back([&errs, &devs, i]() {
+						void* p = nullptr;  // forces context creation
+						if (pgt_set_device(devs[i]) != PGT_OK) errs[i] = pgt_last_error();
+						else if (pgt_device_alloc(&p, 1 << 20) == PGT_OK) pgt_device_free(p);
+					});
+				for (auto& t : per) t.join();
+				for (const std::string& e : errs)
+					if (!e.empty()) {
+						rc = -1;
+						err = e;
+					}
 			}
 			ms = now_ms() - t0;
 		});
@@ -481,6 +506,19 @@ struct DeviceWarmup {
 		if (th.joinable()) th.join();
 	}
 };
+
+// The scan of a tool: one device -> pgt_scan with a workspace from pgt_device_alloc; PGT_DEVICES with several
+// devices -> pgt_scan_sharded (the whole window table, same rows).  Prints nothing; pgt_last_error() on failure.
+inline int scan_on_devices(const pgt_plan* plan, const pgt_range* range, pgt_stat stat, const pgt_columns* cols, int minind,
+                           const uint64_t* site_offsets, const pgt_windows* out) {
+	const std::vector<int>& devs = device_list();
+	if (devs.size() > 1) return pgt_scan_sharded(plan, stat, cols, minind, site_offsets, out, devs.data(), (uint32_t)devs.size(), nullptr, nullptr);
+	DeviceWorkspace ws;
+	ws.bytes = pgt_scan_workspace_bytes(plan, range, stat, PGT_MEM_HOST);
+	const int rc = pgt_device_alloc(&ws.p, ws.bytes);
+	if (rc != PGT_OK) return rc;
+	return pgt_scan(plan, range, stat, cols, minind, site_offsets, out, ws.p, ws.bytes, PGT_MEM_HOST, nullptr);
+}
 
 struct Timing {
 	double parse_ms = 0, scan_ms = 0, format_ms = 0, total_ms = 0, cuda_init_ms = 0;

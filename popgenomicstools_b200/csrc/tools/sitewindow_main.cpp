@@ -285,9 +285,7 @@ int main(int argc, char** argv) {
 		out.nonmissing = cnt.data();  // hetWindow.cpp:87 prints nonmissing
 		const pgt_stat which = PGT_STAT_HET;
 #endif
-		DeviceWorkspace ws;
-		ws.bytes = pgt_scan_workspace_bytes(plan, nullptr, which, PGT_MEM_HOST);
-		if (pgt_device_alloc(&ws.p, ws.bytes) != PGT_OK || pgt_scan(plan, nullptr, which, &cols, 1, nullptr, &out, ws.p, ws.bytes, PGT_MEM_HOST, nullptr) != PGT_OK) {
+		if (scan_on_devices(plan, nullptr, which, &cols, 1, nullptr, &out) != PGT_OK) {
 			fprintf(stderr, "%s: %s\n", kTool, pgt_last_error());
 			return -1;
 		}

@@ -180,6 +180,22 @@ def scan_extreme(plan, stat, cutoff, pos, score, window_range=None, site_origin=
     return out
 
 
+def scan_extreme_sharded(plan, stat, cutoff, pos, score, devices):
+    """pgt_scan_extreme_sharded: numpy columns over ALL sites, one shard of windows per entry of `devices`
+    (CUDA device indices of this process); numpy arrays over all windows back, bit-identical for any list."""
+    lib = plan._lib
+    pos = None if pos is None else np.ascontiguousarray(pos, np.uint32)
+    score = np.ascontiguousarray(score, np.float64)
+    out = {k: np.empty(plan.num_windows, _X_DTYPES[k]) for k in XWINDOW_FIELDS if not (k == "ext_pos" and pos is None)}
+    w = PgtXWindows()
+    for k, v in out.items():
+        setattr(w, k, v.ctypes.data)
+    dev = (C.c_int * len(devices))(*[int(d) for d in devices])
+    check(lib.pgt_scan_extreme_sharded(plan.handle, int(stat), float(cutoff), pos.ctypes.data if pos is not None else None,
+                                       score.ctypes.data, C.byref(w), dev, len(devices)))
+    return out
+
+
 def ihs_window(plan, pos, score, cutoff=2.0, **kw):
     """Most extreme |iHS| per bp window and the proportion of |iHS| > cutoff
     (/root/reference/ihsWindow.cpp:93-187).  Returns ext_value (signed score), ext_pos, ext_site,

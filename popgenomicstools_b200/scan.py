@@ -229,6 +229,47 @@ def scan(plan, stat, cols, minind=1, site_offsets=None, window_range=None, site_
     return out
 
 
+def scan_sharded(plan, stat, cols, devices, minind=1, site_offsets=None, out=None):
+    """One host column set, several GPUs of this process (pgt_scan_sharded): `cols` are numpy arrays over the
+    WHOLE axis, `devices` a list of CUDA device indices (one shard per entry).  Returns numpy arrays over all
+    windows; per-window results are bit-identical for any device list."""
+    lib = plan._lib
+    need = _STAT_COLS[stat]
+    c = PgtColumns()
+    keep = []
+    for k in COLUMN_FIELDS:
+        v = cols.get(k)
+        if v is None or (k != "pos" and k not in need):
+            continue
+        if _is_tensor(v):
+            v = v.numpy()
+        if k == "pos" and v.dtype == np.int32:
+            v = v.view(np.uint32)
+        if v.dtype != np.dtype(_COL_DTYPES[k]) or not v.flags["C_CONTIGUOUS"]:
+            raise TypeError(f"{k}: expected contiguous {_COL_DTYPES[k]}, got {v.dtype}")
+        setattr(c, k, v.ctypes.data)
+        keep.append(v)
+    for k in need:
+        if cols.get(k) is None:
+            raise ValueError(f"column {k!r} is required")
+    nwin = plan.num_windows
+    if out is None:
+        out = {k: np.empty(3 if k == "dxy_global" else nwin, np.float64 if (k in _F64_OUT or k == "dxy_global") else np.uint32)
+               for k in _STAT_OUTS[stat]}
+    w = PgtWindows()
+    for k in WINDOW_FIELDS:
+        v = out.get(k)
+        if v is not None:
+            setattr(w, k, v.ctypes.data)
+    so = None
+    if site_offsets is not None:
+        so = np.ascontiguousarray(site_offsets, dtype=np.uint64)
+    dev = (C.c_int * len(devices))(*[int(d) for d in devices])
+    check(lib.pgt_scan_sharded(plan.handle, stat, C.byref(c), int(minind), so.ctypes.data if so is not None else None, C.byref(w),
+                               dev, len(devices), None, None))
+    return out
+
+
 def fst_window(plan, pos, a, b, **kw):
     """Sliding-window FST = sum(a)/sum(b) (/root/reference/fstWindow.cpp:69-107).
     Returns label, start_pos, end_pos, mid_pos, nsites, sum_a, sum_b, fst per window."""
