@@ -407,8 +407,8 @@ def run_config(cfg, R, pgt, steps, peak):
     if cfg["full"] or density:
         s_lo, s_hi = 0, n
     cols = make_columns(pgt, cfg["stat"], cfg["seed"], s_lo, s_hi - s_lo, offs, R.dev, density or 1)
-    tab = SharedTable(_STAT_OUTS[stat_id], plan.num_windows, R.rank, R.world, dist, torch, R.dev)
-    out = tab.rows(w_lo, w_hi)
+    tab = SharedTable(_STAT_OUTS[stat_id], plan.num_windows, R.rank, R.world, dist, torch, R.dev, w_lo=w_lo, w_hi=w_hi)
+    out = tab.rows()
     kw = dict(minind=5, window_range=(w_lo, w_hi), site_origin=s_lo, out=out, **extra)
     try:
         for _ in range(3):
@@ -450,8 +450,9 @@ def run_config(cfg, R, pgt, steps, peak):
                    algorithmic_bytes=int(tot[0]), achieved_gbs=round(tot[1] / R.world, 1), frac=round(tot[1] / R.world / peak, 4),
                    bytes_per_site_in=in_b, bytes_per_window_out=OUT_BYTES[cfg["stat"]])
         R.barrier()
-        if R.rank == 0:
-            res["result_checksum"] = tab.checksum()
+        res["table"] = ("one table in rank 0's HBM, rows written in place by every rank" if tab.placement == "rank0"
+                        else "sharded: every rank keeps its rows in its own HBM (table above 256 MB)")
+        res["result_checksum"] = tab.checksum()
         return res
     finally:
         pgt.profile(False)
@@ -536,8 +537,8 @@ def run_b200(args):
 
     # ---- the window table lives once, in rank 0's HBM; every rank's window kernel writes its rows there
     fields = [k for k in _STAT_OUTS[stat] if k != "dxy_global"]
-    tab = SharedTable(_STAT_OUTS[stat], plan.num_windows, rank, world, dist, torch, dev)
-    out = tab.rows(w_lo, w_hi)
+    tab = SharedTable(_STAT_OUTS[stat], plan.num_windows, rank, world, dist, torch, dev, w_lo=w_lo, w_hi=w_hi)
+    out = tab.rows()
 
     def step():
         pgt.scan(plan, stat, cols, minind=5, window_range=(w_lo, w_hi), site_origin=s_lo, out=out)
@@ -576,8 +577,8 @@ def run_b200(args):
     ms_step = R.reduce([ms_total])[0] / args.steps
     total_launches = int(R.reduce([launches], "sum")[0])
     value = n_total / (ms_step * 1e-3)
-    result_checksum = tab.checksum() if rank == 0 else None
-    glob = tab.table().get("dxy_global") if (rank == 0 and fused) else None
+    result_checksum = tab.checksum()
+    glob = tab.global_line() if fused else None
 
     # ---- roofline of the dominant kernel (level 1) on this rank
     peak, peak_src = hbm_peak()
@@ -619,15 +620,15 @@ def run_b200(args):
                 hcols = pinned.cols
                 prep_s = time.perf_counter() - t_prep
                 devices = list(range(world))
-                hout = pgt.scan_sharded(plan, stat, hcols, devices, minind=5)  # warm-up: contexts, workspaces
-                ref = {k: v.cpu().numpy() for k, v in tab.table().items() if k != "dxy_global"}
-                for k in fields:  # the host path returns exactly what the resident path computed
-                    assert hout[k].tobytes() == ref[k].tobytes(), f"e2e result differs in {k}"
-                del ref
+                plan_h = pgt.WindowPlan(offs, W, S, unit_sites=unit_sites)  # not bound to a device: every GPU uploads its own tables
+                hout = pgt.scan_sharded(plan_h, stat, hcols, devices, minind=5)  # warm-up: contexts on all GPUs
+                from popgenomicstools_b200.sharding import table_checksum
+                e2e_sum = table_checksum(hout, fields)  # the host path returns exactly what the resident path computed
+                assert e2e_sum == result_checksum, f"e2e table differs from the resident table: {e2e_sum} vs {result_checksum}"
                 times = []
                 for _ in range(args.e2e_steps):
                     t0 = time.perf_counter()
-                    pgt.scan_sharded(plan, stat, hcols, devices, minind=5, out=hout)
+                    pgt.scan_sharded(plan_h, stat, hcols, devices, minind=5, out=hout)
                     times.append(time.perf_counter() - t0)
                 e_ms = sum(times) / len(times) * 1e3
                 h2d = bytes_per_site * n_total + (world - 1) * bytes_per_site * (W - S)
@@ -635,7 +636,7 @@ def run_b200(args):
                                                                    "neffective", "nskip"))
                 e2e = {"value": n_total / (e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                        "ms_per_step": round(e_ms, 3), "steps": args.e2e_steps, "timer": "host wall clock around the (synchronous) call",
-                       "n_devices": world, "one_process_one_table": True, "table_equals_resident_table": True,
+                       "n_devices": world, "one_process_one_table": True, "result_checksum": e2e_sum,
                        "host_columns_prep_s": round(prep_s, 1),
                        "api": "pgt_scan_sharded(plan, stat, host columns, devices[0..N-1]): pinned host columns of the whole genome -> "
                               "per GPU: 4M-site slabs H2D (double-buffered, copy stream) -> level 1 per slab -> level 2 -> D2H of the "
@@ -648,6 +649,7 @@ def run_b200(args):
             e2e = {"value": None, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0, "error": repr(ex)[:300]}
             barrier()
     del cols
+    tab_placement = tab.placement
     tab.close()
     torch.cuda.empty_cache()
 
@@ -689,8 +691,9 @@ def run_b200(args):
                        "unit_sites": unit_sites or 256, "sharding": f"site ranges cut at window starts, halo = W-S = {W - S} sites, {world} shard(s)",
                        "l2": "inputs (>= 6 GB per GPU) exceed the 126 MB L2; no flush needed",
                        "clock_warmup": "uncounted steps for >= 0.3 s before the W counted warm-up steps",
-                       "gather": ("none: every rank's window kernel writes its rows into the one table in rank 0's HBM "
-                                  "(CUDA IPC mapping over NVLink); no collective inside a step" if world > 1
+                       "gather": (("none: every rank's window kernel writes its rows into the one table in rank 0's HBM "
+                                   "(CUDA IPC mapping over NVLink); no collective inside a step" if tab_placement == "rank0" else
+                                   "none: the table (above 256 MB) stays sharded, every rank keeps its rows in its own HBM") if world > 1
                                   else "single GPU: results stay in HBM")},
             "result_checksum": result_checksum,
             "clocks": clk.summary(),

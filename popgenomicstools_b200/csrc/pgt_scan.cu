@@ -68,7 +68,7 @@ extern "C" int pgt_set_device(int device) {
 }
 extern "C" int pgt_host_alloc(void** p, size_t bytes) {
 	if (!p) return pgt_set_error(PGT_ERR_ARGS, "pgt_host_alloc: NULL");
-	PGT_CUDA(cudaHostAlloc(p, bytes, cudaHostAllocDefault));
+	PGT_CUDA(cudaHostAlloc(p, bytes, cudaHostAllocPortable));  // page-locked for every device of the process (pgt_scan_sharded)
 	return PGT_OK;
 }
 extern "C" int pgt_host_free(void* p) {
@@ -646,9 +646,15 @@ __global__ void __launch_bounds__(256) k_tile_segs(DevPlan P, uint32_t m, uint64
 // The staged copy keeps the column's alignment modulo 16, so the aligned chunks are the same in shared
 // memory and -- for a slice that was too long to stage -- in global memory (generic loads serve both).
 // Integer counts: independent of the order, identical to the per-site fold.
-__device__ __forceinline__ void het_count_word(uint32_t w, uint32_t& nonmissing, uint32_t& nhet) {
-	nonmissing += __popc(~w & 0x80808080u);                 // g >= 0  (hetWindow.cpp:78)
-	nhet += __popc(__vcmpeq4(w, 0x01010101u) & 0x01010101u);  // g == 1 (hetWindow.cpp:80)
+// Four genotypes per word.  Both tests end in a word with 0x80 in every byte that counts, and an unsigned
+// dp4a against 0x01010101 adds 128 per such byte: the accumulators hold 128 x count (shifted down once per
+// unit; a lane sees < 2^25 bytes of a unit).  ~7 integer instructions per word and no POPC, which runs at a
+// quarter of the integer rate (the POPC / __vcmpeq4 version needed 13 and was issue-bound at 4.5 TB/s).
+__device__ __forceinline__ void het_count_word(uint32_t w, uint32_t& nonmissing128, uint32_t& nhet128) {
+	nonmissing128 = __dp4a(~w & 0x80808080u, 0x01010101u, nonmissing128);  // g >= 0  (hetWindow.cpp:78): sign bit clear
+	const uint32_t x = w ^ 0x01010101u;                                     // g == 1  (hetWindow.cpp:80): byte of x is zero
+	const uint32_t t = (x & 0x7f7f7f7fu) + 0x7f7f7f7fu;                     // bit 7 of t | x is set iff the byte of x is not zero
+	nhet128 = __dp4a(~(t | x) & 0x80808080u, 0x01010101u, nhet128);
 }
 __device__ __forceinline__ void het_unit_from_tile(HetStat::Acc& acc, const char* col, uint32_t rel, uint32_t len, uint32_t lane) {
 	const int8_t* A = (const int8_t*)col + rel;
@@ -658,13 +664,16 @@ __device__ __forceinline__ void het_unit_from_tile(HetStat::Acc& acc, const char
 	uint32_t nonmissing = 0, nhet = 0;
 	if (A1 > A0) {
 		const uint32_t nch = (uint32_t)(A1 - A0) >> 4;
+		uint32_t nm128 = 0, h128 = 0;
 		for (uint32_t c = lane; c < nch; c += 32u) {
 			const uint4 v = *(reinterpret_cast<const uint4*>(A0) + c);
-			het_count_word(v.x, nonmissing, nhet);
-			het_count_word(v.y, nonmissing, nhet);
-			het_count_word(v.z, nonmissing, nhet);
-			het_count_word(v.w, nonmissing, nhet);
+			het_count_word(v.x, nm128, h128);
+			het_count_word(v.y, nm128, h128);
+			het_count_word(v.z, nm128, h128);
+			het_count_word(v.w, nm128, h128);
 		}
+		nonmissing = nm128 >> 7;
+		nhet = h128 >> 7;
 		const uint32_t nh = (uint32_t)(A0 - A), nt = (uint32_t)(E - A1);  // < 16 each
 		if (lane < nh) {
 			const int g = A[lane];
@@ -872,6 +881,7 @@ __global__ void __launch_bounds__(256, 4) k_units_het_vec(DevPlan P, const int8_
 		const int8_t* A1 = (const int8_t*)((uintptr_t)E & ~(uintptr_t)15u);          // end of the last aligned chunk
 		uint32_t nonmissing = 0, nhet = 0;
 		if (A1 > A0) {
+			uint32_t nm128 = 0, h128 = 0;
 			const uint32_t nch = (uint32_t)(A1 - A0) >> 4;
 			// 8 x 16 bytes in flight per lane (one 4096-site unit = one round); chunks past the end read
 			// as 0x80 bytes = missing genotypes, which count for nothing
@@ -886,12 +896,14 @@ __global__ void __launch_bounds__(256, 4) k_units_het_vec(DevPlan P, const int8_
 #pragma unroll
 				for (int q = 0; q < 8; ++q) {
 					if (c0 + 32u * q >= nch) v[q] = kMissing;
-					het_count_word(v[q].x, nonmissing, nhet);
-					het_count_word(v[q].y, nonmissing, nhet);
-					het_count_word(v[q].z, nonmissing, nhet);
-					het_count_word(v[q].w, nonmissing, nhet);
+					het_count_word(v[q].x, nm128, h128);
+					het_count_word(v[q].y, nm128, h128);
+					het_count_word(v[q].z, nm128, h128);
+					het_count_word(v[q].w, nm128, h128);
 				}
 			}
+			nonmissing = nm128 >> 7;
+			nhet = h128 >> 7;
 			const uint32_t nh = (uint32_t)(A0 - A), nt = (uint32_t)(E - A1);  // < 16 each
 			if (lane < nh) {
 				const int g = __ldg(A + lane);
@@ -1094,22 +1106,60 @@ __global__ void __launch_bounds__(256) k_windows_small(DevPlan P, const typename
 
 // W = S = 1 (the tools' default arguments): every window is one site, so the window table is an
 // elementwise map of the columns; level 1 is skipped and the per-site statistic is evaluated here.
+// Output-bound (36-76 bytes of rows per 1-41 bytes of site): a thread takes four windows per turn and issues
+// their column loads together before the first row is stored; the label comes from a cached contig range
+// instead of a binary search per window.
 template <class Stat>
 __global__ void __launch_bounds__(256) k_windows_persite(DevPlan P, Cols cols, pgt_windows out) {
+	constexpr int U = 4;
 	const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
 	uint32_t si = 0xffffffffu;
 	pgt_seg sg;
 	sg.win_base = 0;
 	sg.nwin = 0;
-	for (uint64_t w = P.win_lo + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; w < P.win_hi; w += stride) {
-		if (si == 0xffffffffu || w - sg.win_base >= sg.nwin) {
-			si = find_seg<false>(P, w);
-			sg = P.segs[si];
+	uint32_t lc = 0;
+	uint64_t lc_lo = 1, lc_hi = 0;  // sites of contig lc: [lc_lo, lc_hi); empty = nothing cached
+	for (uint64_t w0 = P.win_lo + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; w0 < P.win_hi; w0 += U * stride) {
+		uint64_t site[U];
+		typename Stat::Site v[U];
+		uint32_t ps[U];
+#pragma unroll
+		for (int q = 0; q < U; ++q) {
+			const uint64_t w = w0 + q * stride;
+			site[q] = ~0ull;
+			if (w >= P.win_hi) continue;
+			if (si == 0xffffffffu || w - sg.win_base >= sg.nwin) {
+				si = find_seg<false>(P, w);
+				sg = P.segs[si];
+			}
+			site[q] = sg.site_base + (w - sg.win_base);  // window k of a segment is its site k
 		}
-		const uint64_t k = w - sg.win_base;
-		typename Stat::Acc acc = Stat::zero();
-		Stat::fold(acc, Stat::load(cols, sg.site_base + k - P.site_origin), cols.minind);
-		emit_window<Stat>(P, sg, w, k, acc, cols.pos, out);
+#pragma unroll
+		for (int q = 0; q < U; ++q) {
+			if (site[q] == ~0ull) continue;
+			v[q] = Stat::load(cols, site[q] - P.site_origin);
+			ps[q] = cols.pos ? __ldg(cols.pos + (site[q] - P.site_origin)) : 0u;
+		}
+#pragma unroll
+		for (int q = 0; q < U; ++q) {
+			if (site[q] == ~0ull) continue;
+			const uint64_t o = w0 + q * stride - P.win_lo;
+			if (site[q] < lc_lo || site[q] >= lc_hi) {
+				lc = find_contig(P.off, 0, P.ncontig, site[q]);
+				lc_lo = P.off[lc];
+				lc_hi = P.off[lc + 1];
+			}
+			typename Stat::Acc acc = Stat::zero();
+			Stat::fold(acc, v[q], cols.minind);
+			if (out.label) out.label[o] = lc;
+			if (out.nsites) out.nsites[o] = 1u;
+			if (cols.pos) {
+				if (out.start_pos) out.start_pos[o] = ps[q];
+				if (out.end_pos) out.end_pos[o] = ps[q];
+				if (out.mid_pos) out.mid_pos[o] = (ps[q] + ps[q]) / 2u;  // uint32 arithmetic, fstWindow.cpp:73
+			}
+			Stat::emit(out, o, acc);
+		}
 	}
 }
 
@@ -2012,9 +2062,10 @@ static int launch_units(const DevPlan& P, const Cols& cols, typename Stat::Acc* 
 		for (uint32_t c = 0; c < sc.n; ++c) bps += sc.elem[c];
 	}
 	const uint64_t approx_bytes = nunits * (uint64_t)P.g.ueff * bps;
-	// (hetWindow's 1-byte column: the vectorised direct kernel below ~256 MB, the ring above -- a warp of the
-	// direct kernel has nothing in flight while it counts and stores, the ring keeps ~200 KB per SM in flight)
-	bool tiled = P.g.gw != 32 || approx_bytes >= (256ull << 20);
+	// (hetWindow's 1-byte column stays on the vectorised direct kernel: measured at 3e9 sites, 4096-site units,
+	// 6.14 TB/s direct against 5.44 TB/s through the ring -- both were issue-bound on the byte counting, 4.5 and
+	// 4.3 TB/s, until it went from POPC to dp4a; the ring's het consumer remains for forced / short-unit runs)
+	bool tiled = P.g.gw != 32 || (bps > 1 && approx_bytes >= (256ull << 20));
 	if (g_tune_level1 == 2) tiled = true;
 	if (g_tune_level1 == 1 && P.g.gw == 32) tiled = false;
 	{

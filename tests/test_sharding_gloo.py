@@ -131,18 +131,21 @@ def _tworker(rank, world, port, lengths, W, S, result_path):
     ref = O.dxy(T.expand_chr(lengths), pos, f1, f2, n1, n2, 5, W, S, 1)
     fields = ("label", "start_pos", "end_pos", "dxy", "neffective", "nskip", "dxy_global")
     key = dict(label="label", start_pos="start", end_pos="end", dxy="dxy", neffective="neff", nskip="nskip")
-    tab = SharedTable(fields, plan.num_windows, rank, world, dist, backend="shm", tag="pgt_gloo_test")
-    rows = tab.rows(w_lo, w_hi)
+    tab = SharedTable(fields, plan.num_windows, rank, world, dist, torch=torch, backend="shm", tag="pgt_gloo_test", w_lo=w_lo, w_hi=w_hi)
+    rows = tab.rows()
     for k, kr in key.items():
         rows[k][:] = np.asarray(ref[kr][w_lo:w_hi]).astype(rows[k].dtype)
     # every rank's global line over the sites it owns: here simply its share of the oracle's line
     rows["dxy_global"][:] = np.array(ref["global"], np.float64) * (1.0 if rank == 0 else 0.0)
     dist.barrier()
+    checksum = tab.checksum()  # collective: every rank sums the rows it wrote
     if rank == 0:
+        from popgenomicstools_b200.sharding import table_checksum
         t = tab.table()
         ok = all(np.ascontiguousarray(t[k]).tobytes() == np.asarray(ref[kr]).astype(t[k].dtype).tobytes() for k, kr in key.items())
         ok = ok and np.array_equal(t["dxy_global"], np.array(ref["global"], np.float64))
-        open(result_path, "w").write(("ok " if ok else "mismatch ") + tab.checksum())
+        ok = ok and table_checksum(t, fields) == checksum
+        open(result_path, "w").write(("ok " if ok else "mismatch ") + checksum)
     tab.close()
     dist.barrier()
     dist.destroy_process_group()
