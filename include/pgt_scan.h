@@ -241,6 +241,29 @@ int pgt_scan_sharded(const pgt_plan* plan, pgt_stat stat, const pgt_columns* col
                      const uint64_t* site_offsets, const pgt_windows* out, const int* devices, uint32_t ndev,
                      void* const* workspaces, const size_t* workspace_bytes);
 
+/* ---- streaming upload -----------------------------------------------------------------------------------------
+ * The reference streams its input (fstWindow.cpp:123-146).  A producer that is still running -- the tools' parser
+ * threads, a reader of a binary column cache -- hands finished ranges to an uploader, which moves them to device
+ * memory through a persistent ring of `nslots` page-locked slots of `slot_bytes` each: `nthreads` copy threads fill
+ * free slots (memcpy from ordinary pageable memory, or pread from a file so that a cache never goes through a
+ * page-cache mapping) and send them on with cudaMemcpyAsync, the filling of one slot overlapping the DMA of the
+ * others (pageable cudaMemcpy: ~11 GB/s on these hosts; pinned: ~54 GB/s).  The scan then runs on the resident
+ * columns (PGT_MEM_DEVICE).  `pinned` is caller-owned page-locked memory (pgt_host_alloc) of at least
+ * pgt_uploader_pinned_bytes() that outlives the uploader, or NULL to let the uploader own its ring.  The uploader
+ * belongs to the device current at creation.  put / put_file only enqueue and return; drain waits until every
+ * queued byte is on the device (and reports how many went).  Errors of the copy threads surface at the next call. */
+typedef struct pgt_uploader pgt_uploader;
+size_t pgt_uploader_pinned_bytes(uint32_t nslots, size_t slot_bytes);
+int pgt_uploader_create(pgt_uploader** up, void* pinned, size_t pinned_bytes, uint32_t nslots, size_t slot_bytes,
+                        uint32_t nthreads);
+int pgt_uploader_put(pgt_uploader* up, void* dev_dst, const void* host_src, size_t bytes);
+int pgt_uploader_put_file(pgt_uploader* up, void* dev_dst, int fd, uint64_t file_offset, size_t bytes);
+int pgt_uploader_drain(pgt_uploader* up, uint64_t* bytes_sent);
+void pgt_uploader_destroy(pgt_uploader* up);
+/* for callers that do not link the CUDA runtime (the CLIs): synchronous device -> host copy, free / total HBM */
+int pgt_memcpy_to_host(void* host, const void* dev, size_t bytes);
+int pgt_device_mem_info(size_t* free_bytes, size_t* total_bytes);
+
 /* Convenience entry points named after the tools they replace. */
 int pgt_scan_fst(const pgt_plan* plan, const pgt_range* range, const pgt_columns* cols, const pgt_windows* out,
                  void* workspace, size_t workspace_bytes, pgt_mem mem, void* stream);
@@ -273,8 +296,6 @@ int pgt_profile_read(double* units_ms, uint64_t* units_launches, double* windows
  *   "level1": 0 auto | 1 direct warp-per-unit kernel (long units only) | 2 tiled TMA-staged kernel
  *   "level2": 0 auto | 1 always warp-per-window | 2 always scan mode (block prefix/suffix scans)
  *   "slide": 0 auto | 1 never use the sliding-tile kernel for fine steps | 2 use it for every site-mode geometry whose block fits shared memory (W <= 1288)
- *   "hoststage": experiment, 0 off (default) | 1 PGT_MEM_HOST from pageable (unpinned) columns through a ring of
- *                small pinned buffers filled by several host threads instead of the driver's pageable staging
  *   "stages", "stage_kb": shared-memory ring of the tiled kernel
  *   "xgroup": lanes per unit of the extreme scan's level 1 (pgt_extreme.h), 0 auto | 4 | 8 | 16 | 32 */
 int pgt_tune(const char* key, int value);

@@ -67,6 +67,14 @@ PROTOTYPES = {
     "pgt_ipc_export": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
     "pgt_ipc_open": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
     "pgt_ipc_close": (C.c_int, [C.c_void_p]),
+    "pgt_uploader_pinned_bytes": (C.c_size_t, [C.c_uint32, C.c_size_t]),
+    "pgt_uploader_create": (C.c_int, [C.POINTER(C.c_void_p), C.c_void_p, C.c_size_t, C.c_uint32, C.c_size_t, C.c_uint32]),
+    "pgt_uploader_put": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]),
+    "pgt_uploader_put_file": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_uint64, C.c_size_t]),
+    "pgt_uploader_drain": (C.c_int, [C.c_void_p, _u64p]),
+    "pgt_uploader_destroy": (None, [C.c_void_p]),
+    "pgt_memcpy_to_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
+    "pgt_device_mem_info": (C.c_int, [C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]),
     "pgt_plan_create": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32,
                                   C.c_uint32]),
     "pgt_plan_destroy": (None, [C.c_void_p]),

@@ -33,7 +33,6 @@
 #include <vector>
 
 #include "../../include/pgt_extreme.h"
-#include "pgt_hostcopy.h"
 #include "pgt_internal.h"
 
 // ----------------------------------------------------------------------------- utilities
@@ -204,8 +203,6 @@ static int g_tune_stage_kb = 110;  // tiled kernel: KB per stage (stages * stage
 extern int g_tune_xgroup;          // extreme scan (pgt_extreme.cu): lanes per unit, 0 = auto
 //   slide: 0 auto, 1 never use the sliding-tile kernel (k_slide), 2 use it whenever it fits shared memory (any W <= 1288)
 static int g_tune_slide = 0;
-//   hoststage: PGT_MEM_HOST from pageable columns through the pinned ring (PinnedRing below): 0 off (default), 1 on
-static int g_tune_hoststage = 0;
 
 static int num_sms() {
 	int dev = 0, n = 0;
@@ -1921,7 +1918,6 @@ extern "C" int pgt_tune(const char* key, int value) {
 	if (key && strcmp(key, "level1") == 0) g_tune_level1 = value;
 	else if (key && strcmp(key, "level2") == 0 && value >= 0 && value <= 2) g_tune_level2 = value;
 	else if (key && strcmp(key, "slide") == 0 && value >= 0 && value <= 2) g_tune_slide = value;
-	else if (key && strcmp(key, "hoststage") == 0 && value >= 0 && value <= 1) g_tune_hoststage = value;
 	else if (key && strcmp(key, "stages") == 0 && value >= 2 && value <= kTileMaxStages) g_tune_stages = value;
 	else if (key && strcmp(key, "stage_kb") == 0 && value >= 8 && value <= 110) g_tune_stage_kb = value;
 	else if (key && strcmp(key, "xgroup") == 0 && (value == 0 || value == 4 || value == 8 || value == 16 || value == 32)) g_tune_xgroup = value;
@@ -2265,64 +2261,6 @@ struct HostStreams {
 	}
 };
 
-// EXPERIMENT, off by default (pgt_tune "hoststage" = 1).  PGT_MEM_HOST from PAGEABLE columns (what the CLIs
-// pass: malloc'ed arrays, the mapping of a .pgtc file) runs at 11 GB/s against 54 GB/s from pinned memory
-// (tools/probe_pageable.py).  The ring stages the copy itself: pieces of a slab are copied into a few pinned
-// buffers by several host threads and sent from there, the memcpy of piece i+1 overlapping the DMA of piece i.
-// Measured (gpurun_out/pageable_ring.log, 1.6 GB per call): results identical, parity tests green with the
-// ring forced, but NOT faster (11.5 / 5.7 GB/s): pinning 64 MB per call and the VM's ~6 GB/s per-thread memcpy
-// eat the gain at that size.  A ring that pays needs pinned buffers that outlive the call (caller-owned, like
-// the device workspace); until that is built and measured the default path is the driver's staging.
-struct PinnedRing {
-	static constexpr int kBufs = 4;
-	static constexpr size_t kBufBytes = (size_t)16 << 20;
-	char* buf[kBufs] = {nullptr, nullptr, nullptr, nullptr};
-	cudaEvent_t done[kBufs] = {nullptr, nullptr, nullptr, nullptr};
-	bool used[kBufs] = {false, false, false, false};
-	int next = 0;
-	bool ready = false;
-	CopyPool pool;
-	int init() {
-		for (int k = 0; k < kBufs; ++k) {
-			PGT_CUDA(cudaHostAlloc((void**)&buf[k], kBufBytes, cudaHostAllocDefault));
-			PGT_CUDA(cudaEventCreateWithFlags(&done[k], cudaEventDisableTiming));
-		}
-		const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
-		pool.start(std::min(7u, hw - 1));  // + the calling thread
-		ready = true;
-		return PGT_OK;
-	}
-	// `bytes` from pageable `src` to device `dst` on stream `copy`; the source may be reused on return
-	int push(char* dst, const char* src, size_t bytes, cudaStream_t copy) {
-		for (size_t o = 0; o < bytes; o += kBufBytes) {
-			const size_t n = std::min(kBufBytes, bytes - o);
-			const int k = next;
-			next = (next + 1) % kBufs;
-			if (used[k]) PGT_CUDA(cudaEventSynchronize(done[k]));
-			pool.copy(buf[k], src + o, n);
-			PGT_CUDA(cudaMemcpyAsync(dst + o, buf[k], n, cudaMemcpyHostToDevice, copy));
-			PGT_CUDA(cudaEventRecord(done[k], copy));
-			used[k] = true;
-		}
-		return PGT_OK;
-	}
-	~PinnedRing() {
-		for (int k = 0; k < kBufs; ++k) {
-			if (buf[k]) cudaFreeHost(buf[k]);  // synchronises with the copies still in flight
-			if (done[k]) cudaEventDestroy(done[k]);
-		}
-	}
-};
-
-static bool host_pointer_is_pageable(const void* p) {
-	cudaPointerAttributes a;
-	if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
-		cudaGetLastError();  // not an error of the scan: treat as pinned (plain cudaMemcpyAsync)
-		return false;
-	}
-	return a.type == cudaMemoryTypeUnregistered;
-}
-
 template <class Stat>
 static int run_scan(const pgt_plan* plan, const pgt_range* range, pgt_stat stat, const pgt_columns* cols, int minind,
                     const uint64_t* site_offsets, const pgt_windows* out, void* workspace, size_t workspace_bytes, pgt_mem mem,
@@ -2496,14 +2434,6 @@ static int run_scan(const pgt_plan* plan, const pgt_range* range, pgt_stat stat,
 				o += L.stage_col_bytes[i];
 			}
 	}
-	// experiment (pgt_tune "hoststage" = 1): pageable columns go through the pinned ring
-	PinnedRing ring;
-	bool via_ring[8] = {false, false, false, false, false, false, false, false};
-	if (g_tune_hoststage == 1) {
-		bool any = false;
-		for (int i = 0; i < ncol; ++i) any |= (via_ring[i] = host_pointer_is_pageable(cd[i].ptr));
-		if (any) PGT_TRY(ring.init());
-	}
 	// per-window values are produced into device staging, then copied back: one table for the whole scan, or --
 	// when the windows come straight from the sites, slab by slab -- two slab-sized tables used in turn
 	const bool from_units = !(L.slide || L.persite);
@@ -2559,8 +2489,7 @@ static int run_scan(const pgt_plan* plan, const pgt_range* range, pgt_stat stat,
 		C->minind = minind;
 		for (int i = 0; i < ncol; ++i) {
 			const char* src = (const char*)cd[i].ptr + (s0 - L.origin) * cd[i].elem;
-			if (ns && via_ring[i]) PGT_TRY(ring.push(stage[slot][i], src, ns * cd[i].elem, hs.copy));
-			else if (ns) PGT_CUDA(cudaMemcpyAsync(stage[slot][i], src, ns * cd[i].elem, cudaMemcpyHostToDevice, hs.copy));
+			if (ns) PGT_CUDA(cudaMemcpyAsync(stage[slot][i], src, ns * cd[i].elem, cudaMemcpyHostToDevice, hs.copy));
 			const void* p = stage[slot][i];
 			memcpy((char*)C + cd[i].offset_in_cols, &p, sizeof(p));
 		}

@@ -556,8 +556,17 @@ int main(int argc, char** argv) {
 		range.w_hi = nwin;
 		range.site_count = n_used;
 		std::vector<uint64_t> soff_used(soff.begin(), soff.begin() + nchr + 1);
+		// the synced columns go to the device through the pinned ring (pageable cudaMemcpy would run at a fifth of
+		// the rate); two-file parsing and the sync are sequential in the site order, so there is nothing to overlap
+		StreamColumn scol[5] = {{pos.get(), 4, 0, 0}, {f1.get(), 8, 0, 4}, {f2.get(), 8, 0, 5}, {ni1.get(), 4, 0, 6}, {ni2.get(), 4, 0, 7}};
+		ColumnStreamer streamer;
+		if (n_used > 0) streamer.start(&warm, scol, 5, n_used, nwin + 65536, 32, nullptr);
+		streamer.rows_ready(0, n_used);
+		int rc;
+		if (streamer.finish(&tm) == 0) rc = streamer.scan(plan, PGT_STAT_DXY, &out, nwin, minind, &range, fixedsite ? nullptr : soff_used.data());
 		// (n_used == soff_used[nchr]: the sharded call's "up to the end of the genome" is the same range)
-		if (scan_on_devices(plan, &range, PGT_STAT_DXY, &cols, minind, fixedsite ? nullptr : soff_used.data(), &out) != PGT_OK) {
+		else rc = scan_on_devices(plan, &range, PGT_STAT_DXY, &cols, minind, fixedsite ? nullptr : soff_used.data(), &out);
+		if (rc != PGT_OK) {
 			fprintf(stderr, "dxyWindow: %s\n", pgt_last_error());
 			return -1;
 		}

@@ -15,12 +15,15 @@
 #include <zlib.h>
 
 #include <algorithm>
+#include <atomic>
 #include <charconv>
 #include <chrono>
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
+#include <condition_variable>
 #include <cstring>
+#include <mutex>
 #include <string>
 #include <thread>
 #include <vector>
@@ -453,8 +456,6 @@ inline int select_device() {
 		fprintf(stderr, "%s\n", pgt_last_error());
 		return -1;
 	}
-	// PGT_HOSTSTAGE=1: pgt_tune("hoststage") -- experimental pinned staging ring for the tools' pageable columns
-	if (const char* hs = getenv("PGT_HOSTSTAGE")) pgt_tune("hoststage", atoi(hs));
 	return 0;
 }
 
@@ -462,6 +463,7 @@ inline int select_device() {
 // device(s) up while the parser threads run; the main thread joins them before the scan.
 struct DeviceWarmup {
 	std::thread th;
+	std::atomic<int> state{0};  // 0 = not started / running, 1 = device(s) up, -1 = failed
 	int rc = 0;
 	double ms = 0;
 	std::string err;
@@ -491,6 +493,7 @@ struct DeviceWarmup {
 					}
 			}
 			ms = now_ms() - t0;
+			state.store(rc == 0 ? 1 : -1);
 		});
 	}
 	// 0 ok; on failure prints the same message as select_device()
@@ -522,14 +525,219 @@ inline int scan_on_devices(const pgt_plan* plan, const pgt_range* range, pgt_sta
 
 struct Timing {
 	double parse_ms = 0, scan_ms = 0, format_ms = 0, total_ms = 0, cuda_init_ms = 0;
+	double upload_tail_ms = 0;      // streaming upload: what was left to wait for when parsing / loading had finished
+	double upload_gbs = 0;          // bytes sent / (first byte queued .. last byte on the device)
+	uint64_t upload_bytes = 0;
+	const char* mode = "host";      // "host": columns handed to pgt_scan(PGT_MEM_HOST); "stream": resident columns via the uploader
 	uint64_t sites = 0, windows = 0;
 	unsigned threads = 0;
 	void report(const char* tool) const {
 		if (!getenv("PGT_TIMING")) return;
 		fprintf(stderr,
 		        "{\"tool\":\"%s\",\"sites\":%llu,\"windows\":%llu,\"parse_ms\":%.3f,\"scan_ms\":%.3f,\"format_ms\":%.3f,"
-		        "\"total_ms\":%.3f,\"parse_threads\":%u,\"cuda_init_ms_overlapped_with_parse\":%.3f}\n",
-		        tool, (unsigned long long)sites, (unsigned long long)windows, parse_ms, scan_ms, format_ms, total_ms, threads, cuda_init_ms);
+		        "\"total_ms\":%.3f,\"parse_threads\":%u,\"cuda_init_ms_overlapped_with_parse\":%.3f,\"mode\":\"%s\","
+		        "\"upload_bytes\":%llu,\"upload_gbs\":%.2f,\"upload_tail_ms\":%.3f}\n",
+		        tool, (unsigned long long)sites, (unsigned long long)windows, parse_ms, scan_ms, format_ms, total_ms, threads, cuda_init_ms, mode,
+		        (unsigned long long)upload_bytes, upload_gbs, upload_tail_ms);
+	}
+};
+
+// ---- streaming upload of the tools' columns (pgt_uploader, include/pgt_scan.h) -----------------------------
+//
+// One GPU, an input of some size: the columns become device-resident while the producer is still running.
+// Text: the parser threads finish chunks in file order and a feeder queues the rows of the finished prefix;
+// the uploader's copy threads stage them through the pinned ring, so the wall time is max(parse, upload), not
+// their sum.  Columnar cache: the file's column blocks are read with pread straight into the ring (no
+// page-cache mapping handed to the driver).  Afterwards the scan runs in PGT_MEM_DEVICE and only the window rows
+// come back.  Falls back (finish() != 0) when the columns do not fit the free HBM, several GPUs are selected
+// (PGT_DEVICES: the sharded host-memory scan), the input is small, or PGT_STREAM=0.
+struct StreamColumn {
+	const void* host;   // the column in host memory (text parser output / cache mapping)
+	uint32_t elem;      // bytes per site
+	uint64_t file_off;  // columnar cache: byte offset of the column in the file
+	int field;          // index into pgt_columns: 0 pos, 1 a, 2 b, 3 geno, 4 f1, 5 f2, 6 n1, 7 n2
+};
+
+struct ColumnStreamer {
+	bool on = false;
+	std::atomic<bool> failed{false};
+	std::thread th;
+	std::mutex mu;
+	bool ready = false;
+	pgt_uploader* up = nullptr;
+	StreamColumn cols[8];
+	void* dcol[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+	int ncol = 0;
+	uint64_t n = 0;
+	int fd = -1;
+	double t_first = 0;
+	std::vector<std::pair<uint64_t, uint64_t>> pending;  // row ranges that became ready before the device was up
+	std::string why;
+
+	bool active() const { return on; }
+
+	static uint64_t min_sites() {
+		const char* e = getenv("PGT_STREAM_MIN_SITES");
+		return e ? strtoull(e, nullptr, 10) : (uint64_t)8 << 20;
+	}
+
+	void put_rows_locked(uint64_t lo, uint64_t hi) {
+		if (hi <= lo || failed.load()) return;
+		if (t_first == 0) t_first = now_ms();
+		for (int c = 0; c < ncol; ++c) {
+			char* dst = (char*)dcol[c] + lo * cols[c].elem;
+			const size_t bytes = (size_t)(hi - lo) * cols[c].elem;
+			const int rc = fd >= 0 ? pgt_uploader_put_file(up, dst, fd, cols[c].file_off + lo * cols[c].elem, bytes)
+			                       : pgt_uploader_put(up, dst, (const char*)cols[c].host + lo * cols[c].elem, bytes);
+			if (rc != PGT_OK) {
+				why = pgt_last_error();
+				failed.store(true);
+				return;
+			}
+		}
+	}
+
+	// nwin_est / out_row_bytes: room to leave for the window table and the scan's workspace
+	void start(DeviceWarmup* warm, const StreamColumn* c, int nc, uint64_t nrows, uint64_t nwin_est, size_t out_row_bytes, const char* file_path) {
+		const char* env = getenv("PGT_STREAM");
+		if ((env && atoi(env) == 0) || nrows < min_sites()) return;
+		chosen_device();
+		if (device_list().size() != 1) return;
+		ncol = nc;
+		n = nrows;
+		for (int i = 0; i < nc; ++i) cols[i] = c[i];
+		if (file_path) {
+			fd = open(file_path, O_RDONLY);
+			if (fd < 0) return;
+		}
+		on = true;
+		const int dev = device_list()[0];
+		th = std::thread([this, warm, dev, nwin_est, out_row_bytes]() {
+			while (warm->state.load() == 0) std::this_thread::sleep_for(std::chrono::microseconds(200));
+			auto give_up = [this](const std::string& m) {
+				std::lock_guard<std::mutex> lk(mu);
+				why = m;
+				failed.store(true);
+			};
+			if (warm->state.load() < 0 || pgt_set_device(dev) != PGT_OK) return give_up("device not available");
+			size_t free_b = 0, total_b = 0;
+			if (pgt_device_mem_info(&free_b, &total_b) != PGT_OK) return give_up(pgt_last_error());
+			uint64_t need = (uint64_t)nwin_est * out_row_bytes + ((uint64_t)1 << 30);
+			for (int i = 0; i < ncol; ++i) need += n * cols[i].elem;
+			if ((double)need > 0.92 * (double)free_b) return give_up("columns do not fit the free device memory");
+			for (int i = 0; i < ncol; ++i)
+				if (pgt_device_alloc(&dcol[i], (size_t)(n * cols[i].elem)) != PGT_OK) return give_up(pgt_last_error());
+			// text: the parser threads own the cores and produce ~8 GB/s of columns; cache: nothing else runs
+			const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+			const unsigned nthreads = fd >= 0 ? std::min(8u, hw) : std::min(4u, hw);
+			pgt_uploader* u = nullptr;
+			if (pgt_uploader_create(&u, nullptr, 0, 2 * nthreads, (size_t)16 << 20, nthreads) != PGT_OK) return give_up(pgt_last_error());
+			std::lock_guard<std::mutex> lk(mu);
+			up = u;
+			ready = true;
+			if (fd >= 0) put_rows_locked(0, n);  // the whole file, read with pread by the copy threads
+			for (auto& r : pending) put_rows_locked(r.first, r.second);
+			pending.clear();
+		});
+	}
+
+	// rows [lo, hi) of every column are final in host memory (called by the tools' feeder thread)
+	void rows_ready(uint64_t lo, uint64_t hi) {
+		if (!on || failed.load()) return;
+		std::lock_guard<std::mutex> lk(mu);
+		if (!ready) pending.emplace_back(lo, hi);
+		else put_rows_locked(lo, hi);
+	}
+
+	// 0: every column is resident; otherwise the caller falls back to the host-memory scan
+	int finish(Timing* tm) {
+		if (!on) return -1;
+		const double t0 = now_ms();
+		if (th.joinable()) th.join();
+		uint64_t sent = 0;
+		if (!failed.load() && pgt_uploader_drain(up, &sent) != PGT_OK) {
+			why = pgt_last_error();
+			failed.store(true);
+		}
+		if (failed.load()) {
+			if (getenv("PGT_TIMING")) fprintf(stderr, "{\"stream_fallback\":\"%s\"}\n", why.c_str());
+			release();
+			return -1;
+		}
+		const double t1 = now_ms();
+		tm->mode = "stream";
+		tm->upload_bytes = sent;
+		tm->upload_tail_ms = t1 - t0;
+		tm->upload_gbs = t1 > t_first && t_first > 0 ? (double)sent / ((t1 - t_first) * 1e6) : 0.0;
+		return 0;
+	}
+
+	// device-mode scan over the resident columns; `out` holds HOST arrays of nwin rows (any may be NULL)
+	int scan(const pgt_plan* plan, pgt_stat stat, const pgt_windows* out, uint64_t nwin, int minind = 1, const pgt_range* range = nullptr,
+	         const uint64_t* site_offsets = nullptr) {
+		pgt_columns dc;
+		memset(&dc, 0, sizeof(dc));
+		const void** slots[8] = {(const void**)&dc.pos, (const void**)&dc.a, (const void**)&dc.b, (const void**)&dc.geno,
+		                         (const void**)&dc.f1, (const void**)&dc.f2, (const void**)&dc.n1, (const void**)&dc.n2};
+		for (int c = 0; c < ncol; ++c) *slots[cols[c].field] = dcol[c];
+		struct Field {
+			void* host;
+			void** dev;
+			size_t elem;
+		};
+		pgt_windows dw;
+		memset(&dw, 0, sizeof(dw));
+		Field f[14] = {{out->label, (void**)&dw.label, 4},       {out->start_pos, (void**)&dw.start_pos, 4}, {out->end_pos, (void**)&dw.end_pos, 4},
+		               {out->mid_pos, (void**)&dw.mid_pos, 4},   {out->nsites, (void**)&dw.nsites, 4},       {out->sum_a, (void**)&dw.sum_a, 8},
+		               {out->sum_b, (void**)&dw.sum_b, 8},       {out->fst, (void**)&dw.fst, 8},             {out->nhet, (void**)&dw.nhet, 4},
+		               {out->nonmissing, (void**)&dw.nonmissing, 4}, {out->het, (void**)&dw.het, 8},         {out->dxy, (void**)&dw.dxy, 8},
+		               {out->neffective, (void**)&dw.neffective, 4}, {out->nskip, (void**)&dw.nskip, 4}};
+		std::vector<void*> owned;
+		auto cleanup = [&]() {
+			for (void* p : owned) pgt_device_free(p);
+		};
+		int rc = PGT_OK;
+		for (Field& x : f) {
+			if (!x.host) continue;
+			void* p = nullptr;
+			if ((rc = pgt_device_alloc(&p, (size_t)std::max<uint64_t>(nwin, 1) * x.elem)) != PGT_OK) break;
+			owned.push_back(p);
+			*x.dev = p;
+		}
+		void* dglobal = nullptr;
+		if (rc == PGT_OK && out->dxy_global) {
+			if ((rc = pgt_device_alloc(&dglobal, 3 * sizeof(double))) == PGT_OK) {
+				owned.push_back(dglobal);
+				dw.dxy_global = (double*)dglobal;
+			}
+		}
+		void* ws = nullptr;
+		size_t ws_bytes = 0;
+		if (rc == PGT_OK) {
+			ws_bytes = pgt_scan_workspace_bytes(plan, range, stat, PGT_MEM_DEVICE);
+			if ((rc = pgt_device_alloc(&ws, ws_bytes)) == PGT_OK) owned.push_back(ws);
+		}
+		if (rc == PGT_OK) rc = pgt_scan(plan, range, stat, &dc, minind, site_offsets, &dw, ws, ws_bytes, PGT_MEM_DEVICE, nullptr);
+		for (Field& x : f)
+			if (rc == PGT_OK && x.host) rc = pgt_memcpy_to_host(x.host, *x.dev, (size_t)nwin * x.elem);
+		if (rc == PGT_OK && out->dxy_global) rc = pgt_memcpy_to_host(out->dxy_global, dglobal, 3 * sizeof(double));
+		cleanup();
+		return rc;
+	}
+
+	void release() {
+		if (up) pgt_uploader_destroy(up);
+		up = nullptr;
+		for (int c = 0; c < 8; ++c) {
+			if (dcol[c]) pgt_device_free(dcol[c]);
+			dcol[c] = nullptr;
+		}
+		if (fd >= 0) close(fd);
+		fd = -1;
+	}
+	~ColumnStreamer() {
+		if (th.joinable()) th.join();
+		release();
 	}
 };
 

@@ -107,7 +107,10 @@ int main(int argc, char** argv) {
 	const size_t n_eff = columnar ? 0 : effective_size(in.data, in.size);
 	const unsigned nt = n_eff < parallel_min_bytes() ? 1 : parse_threads();
 	tm.threads = nt;
-	std::vector<size_t> starts = chunk_starts(in.data, 0, n_eff, nt);
+	// Many more chunks than threads, handed out in file order: the prefix of finished rows advances steadily,
+	// and the uploader below sends it to the device while the rest is still being parsed.
+	const unsigned nchunk_want = (nt > 1 && n_eff >= ((size_t)64 << 20)) ? nt * 8 : nt;
+	std::vector<size_t> starts = chunk_starts(in.data, 0, n_eff, nchunk_want);
 	std::vector<Chunk> chunks(starts.size() - 1);
 	for (size_t i = 0; i + 1 < starts.size(); ++i) {
 		chunks[i].begin = starts[i];
@@ -125,11 +128,18 @@ int main(int argc, char** argv) {
 		}
 		c.nlines = k;
 	};
-	{
+	// run `fn(chunk)` over all chunks on nt threads, chunks taken in file order
+	auto for_chunks = [&](auto fn) {
+		std::atomic<size_t> next{0};
+		auto worker = [&]() {
+			for (size_t i = next++; i < chunks.size(); i = next++) fn(chunks[i]);
+		};
 		std::vector<std::thread> th;
-		for (Chunk& c : chunks) th.emplace_back(count_lines, std::ref(c));
+		for (unsigned t = 1; t < nt && t < chunks.size(); ++t) th.emplace_back(worker);
+		worker();
 		for (auto& x : th) x.join();
-	}
+	};
+	for_chunks(count_lines);
 	uint64_t n = 0;
 	for (Chunk& c : chunks) {
 		c.row0 = n;
@@ -149,6 +159,22 @@ int main(int argc, char** argv) {
 		fprintf(stderr, "%s: out of memory for %llu sites\n", kTool, (unsigned long long)n);
 		return -1;
 	}
+#if defined(PGT_TOOL_FST)
+	StreamColumn scol[3] = {{pos, 4, columnar ? (uint64_t)((const char*)view.col[0] - in.data) : 0, 0},
+	                        {col_a, 8, columnar ? (uint64_t)((const char*)view.col[1] - in.data) : 0, 1},
+	                        {col_b, 8, columnar ? (uint64_t)((const char*)view.col[2] - in.data) : 0, 2}};
+	const int nscol = 3;
+#else
+	StreamColumn scol[2] = {{pos, 4, columnar ? (uint64_t)((const char*)view.col[0] - in.data) : 0, 0},
+	                        {geno, 1, columnar ? (uint64_t)((const char*)view.col[1] - in.data) : 0, 3}};
+	const int nscol = 2;
+#endif
+	// Streaming upload (pgt_cli.h ColumnStreamer): device-resident columns filled while the parser runs (text) or
+	// straight from the cache file (pread into the pinned ring); the scan then reads HBM, not host memory.
+	ColumnStreamer streamer;
+	if (!pack_path && n > 0) streamer.start(&warm, scol, nscol, n, (uint64_t)n / stepsize + 65536, 28, columnar ? argv[1] : nullptr);
+	std::vector<std::atomic<unsigned char>> chunk_done(chunks.size());
+	for (auto& f : chunk_done) f.store(0);
 	auto parse_chunk = [&](Chunk& c) {
 		const char* p = in.data + c.begin;
 		const char* e = in.data + c.end;
@@ -209,9 +235,36 @@ int main(int argc, char** argv) {
 		}
 	};
 	{
-		std::vector<std::thread> th;
-		for (Chunk& c : chunks) th.emplace_back(parse_chunk, std::ref(c));
-		for (auto& x : th) x.join();
+		// the feeder follows the prefix of finished chunks and queues its rows for upload
+		std::atomic<bool> parse_over{false};
+		std::thread feeder;
+		if (streamer.active() && !columnar) {
+			feeder = std::thread([&]() {
+				size_t ci = 0;
+				uint64_t sent = 0;
+				while (ci < chunks.size()) {
+					if (!chunk_done[ci].load(std::memory_order_acquire)) {
+						if (parse_over.load()) break;  // a chunk failed: nothing more will arrive
+						std::this_thread::sleep_for(std::chrono::microseconds(200));
+						continue;
+					}
+					uint64_t upto = chunks[ci].row0 + chunks[ci].nlines;
+					while (ci + 1 < chunks.size() && chunk_done[ci + 1].load(std::memory_order_acquire)) {
+						++ci;
+						upto = chunks[ci].row0 + chunks[ci].nlines;
+					}
+					++ci;
+					streamer.rows_ready(sent, upto);
+					sent = upto;
+				}
+			});
+		}
+		for_chunks([&](Chunk& c) {
+			parse_chunk(c);
+			chunk_done[&c - chunks.data()].store(1, std::memory_order_release);
+		});
+		parse_over.store(true);
+		if (feeder.joinable()) feeder.join();
 	}
 	std::vector<ContigRun> runs;
 	if (columnar) runs = view.runs;
@@ -285,7 +338,13 @@ int main(int argc, char** argv) {
 		out.nonmissing = cnt.data();  // hetWindow.cpp:87 prints nonmissing
 		const pgt_stat which = PGT_STAT_HET;
 #endif
-		if (scan_on_devices(plan, nullptr, which, &cols, 1, nullptr, &out) != PGT_OK) {
+		int rc;
+		if (streamer.finish(&tm) == 0) {  // columns are resident in HBM: scan there, copy the rows back
+			rc = streamer.scan(plan, which, &out, nwin);
+		} else {
+			rc = scan_on_devices(plan, nullptr, which, &cols, 1, nullptr, &out);
+		}
+		if (rc != PGT_OK) {
 			fprintf(stderr, "%s: %s\n", kTool, pgt_last_error());
 			return -1;
 		}

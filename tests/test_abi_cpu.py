@@ -87,22 +87,22 @@ def test_scan_fails_loudly_without_device():
 
 def test_tune_knobs_and_the_env_hook():
     """pgt_tune accepts the documented knobs and rejects others; PGT_TUNE applies knobs when the
-    Python layer loads the library (forced-path test runs: `PGT_TUNE=hoststage=1 pytest -m gpu`)."""
+    Python layer loads the library (forced-path test runs: `PGT_TUNE=slide=2 pytest -m gpu`)."""
     import subprocess
     import sys
     from popgenomicstools_b200 import _cabi
     lib = _cabi.load()
-    for key, good, bad in ((b"level1", 2, None), (b"level2", 2, 3), (b"hoststage", 1, 2), (b"stages", 3, 9),
+    for key, good, bad in ((b"level1", 2, None), (b"level2", 2, 3), (b"slide", 2, 3), (b"stages", 3, 9),
                            (b"stage_kb", 64, 500), (b"xgroup", 8, 5)):
         assert lib.pgt_tune(key, good) == 0, key
         if bad is not None:
             assert lib.pgt_tune(key, bad) == _cabi.PGT_ERR_ARGS, key
     assert lib.pgt_tune(b"nonsense", 1) == _cabi.PGT_ERR_ARGS
-    for key, dflt in ((b"level1", 0), (b"level2", 0), (b"hoststage", 0), (b"stages", 2), (b"stage_kb", 110), (b"xgroup", 0)):
+    for key, dflt in ((b"level1", 0), (b"level2", 0), (b"slide", 0), (b"stages", 2), (b"stage_kb", 110), (b"xgroup", 0)):
         assert lib.pgt_tune(key, dflt) == 0
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     run = lambda v: subprocess.run([sys.executable, "-c", "import popgenomicstools_b200"], cwd=root,
                                    env=dict(os.environ, PGT_TUNE=v), capture_output=True, text=True)
-    assert run("hoststage=1,level2=1").returncode == 0
+    assert run("slide=1,level2=1").returncode == 0
     r = run("bogus=1")
     assert r.returncode != 0 and "PGT_TUNE" in r.stderr

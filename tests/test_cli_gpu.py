@@ -193,3 +193,44 @@ def test_columnar_cache_gives_the_same_rows_as_the_text(tmp_path):
         t = U.run(U.ours(tool), [f"{f}.norm"] + args, cwd=d)
         c = U.run(U.ours(tool), [f"{f}.pgtc"] + args, cwd=d)
         assert t[0] == 0 and len(t[1].splitlines()) > 50 and c == t, tool
+
+
+def test_streaming_upload_gives_the_same_rows(tmp_path):
+    """Large single-GPU inputs take the streaming path (pgt_uploader: rows of the finished parse prefix / the cache
+    file's column blocks go through a persistent pinned ring into device-resident columns, the scan then runs in
+    PGT_MEM_DEVICE).  PGT_STREAM_MIN_SITES=1 forces it on small files: stdout and stderr must be what the
+    host-memory path (PGT_STREAM=0) prints, for text and cache inputs, single- and multi-chunk parsing."""
+    import json
+    names = ["chr1", "chr2", "chr3"]
+    offs = np.array([0, 200000, 290000, 291500], np.uint64)
+    d = str(tmp_path)
+    stream = {"PGT_STREAM_MIN_SITES": "1"}
+    for kind, tool, argsets in (("fst", "fstWindow", ([5000, 1000], [1000, 1], [])), ("het", "hetWindow", ([4096, 512], [], [100000, 100000]))):
+        O.write_text(kind, os.path.join(d, f"s.{kind}"), names, offs, seed=4, density=3)
+        assert U.run(U.ours(tool), [f"s.{kind}"], cwd=d, env={"PGT_PACK": os.path.join(d, f"s.{kind}.pgtc")})[0] == 0
+        for args in argsets:
+            base = U.run(U.ours(tool), [f"s.{kind}"] + args, cwd=d, env={"PGT_STREAM": "0"})
+            assert base[0] == 0 and base[2] == "" and len(base[1].splitlines()) > 50
+            for src in (f"s.{kind}", f"s.{kind}.pgtc"):
+                for extra in ({}, {"PGT_PARALLEL_MIN_BYTES": "1", "PGT_THREADS": "5"}):
+                    got = U.run(U.ours(tool), [src] + args, cwd=d, env=dict(stream, **extra))
+                    assert got == base, (tool, args, src, extra, got[2][:200])
+        rc, out, err = U.run(U.ours(tool), [f"s.{kind}.pgtc"] + list(argsets[0]), cwd=d, env=dict(stream, PGT_TIMING="1"))
+        t = json.loads(err.strip().splitlines()[-1])
+        assert rc == 0 and t["mode"] == "stream" and t["upload_bytes"] == int(offs[-1]) * (20 if kind == "fst" else 5), t
+        rc, out, err = U.run(U.ours(tool), [f"s.{kind}"] + list(argsets[0]), cwd=d, env={"PGT_STREAM": "0", "PGT_TIMING": "1"})
+        assert json.loads(err.strip().splitlines()[-1])["mode"] == "host"
+    for pop in (1, 2):
+        O.write_text("maf", os.path.join(d, f"p{pop}.mafs"), names, offs, seed=4, density=3, pop=pop)
+    chr_len = [int(offs[i + 1] - offs[i]) * 3 + 5 for i in range(3)]
+    open(os.path.join(d, "sizes.txt"), "w").write(T.sizes_text(names, chr_len))
+    for opts in (["-winsize", 2000, "-stepsize", 500, "-minind", 5, "-fixedsite", 1],
+                 ["-winsize", 20000, "-stepsize", 5000, "-minind", 5, "-sizefile", "sizes.txt"],
+                 ["-winsize", 1000, "-stepsize", 3, "-minind", 5, "-fixedsite", 1]):
+        base = U.run(U.ours("dxyWindow"), opts + ["p1.mafs", "p2.mafs"], cwd=d, env={"PGT_STREAM": "0"})
+        got = U.run(U.ours("dxyWindow"), opts + ["p1.mafs", "p2.mafs"], cwd=d, env=stream)
+        assert base[0] == 0 and len(base[1].splitlines()) > 50
+        # rows identical; the global line (stderr) is summed over units vs over sites in the two modes: same counts, sum to 1e-12
+        assert got[0] == 0 and got[1] == base[1], opts
+        gb, gg = base[2].split(), got[2].split()
+        assert gb[1:] == gg[1:] and abs(float(gb[0]) - float(gg[0])) <= 1e-5 * abs(float(gb[0])), (base[2], got[2])
