@@ -8,7 +8,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libpgtscan.so")
+# PGT_LIB: another build of the same library, e.g. libpgtscan_bounds.so (-DPGT_BOUNDS: every kernel index checked)
+LIB_PATH = os.environ.get("PGT_LIB") or os.path.join(_HERE, "libpgtscan.so")
 
 PGT_OK, PGT_ERR_ARGS, PGT_ERR_CUDA, PGT_ERR_NOMEM, PGT_ERR_INPUT = 0, -1, -2, -3, -4
 PGT_MEM_DEVICE, PGT_MEM_HOST = 0, 1

@@ -213,6 +213,23 @@ static int num_sms() {
 
 static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
+// -DPGT_BOUNDS (make -C csrc bounds -> libpgtscan_bounds.so): every index a kernel forms from the plan is checked
+// against the extent it must stay in -- column slices against the elements the caller's columns hold, positions
+// inside a shared-memory stage against the staged slice, unit / window / block indices against this launch's ranges
+// -- and a violation traps (the launch fails with an error instead of reading or writing out of bounds).  The GPU
+// test-suite is run against this build with PGT_LIB=.../libpgtscan_bounds.so (tools/run_bounds_gpu.sh).
+#ifdef PGT_BOUNDS
+#define PGT_CHECK(cond)                                                                             \
+	do {                                                                                            \
+		if (!(cond)) {                                                                              \
+			printf("PGT_BOUNDS violated at %s:%d: %s\n", __FILE__, __LINE__, #cond);                \
+			__trap();                                                                               \
+		}                                                                                           \
+	} while (0)
+#else
+#define PGT_CHECK(cond) ((void)0)
+#endif
+
 // ----------------------------------------------------------------------------- device plan
 
 struct Cols {
@@ -238,6 +255,7 @@ struct DevPlan {
 	uint64_t win_lo, win_hi;    // global window range of this scan
 	uint64_t site_origin;       // global index of element 0 of the columns
 	uint64_t nunits_total;
+	uint64_t col_elems;         // elements the columns hold from element 0 (PGT_BOUNDS checks; ~0 = unknown)
 	int mode;
 };
 
@@ -470,6 +488,7 @@ __global__ void __launch_bounds__(256) k_units(DevPlan P, Cols cols, typename St
 			len = pgt_unit_range(P.g, sg.nsites, j - sg.unit_base, &st);
 			i0 = sg.site_base + st - P.site_origin + lane;
 		}
+		PGT_CHECK(len == 0 || (i0 - lane) + len <= P.col_elems);
 		typename Stat::Acc acc = Stat::zero();
 		if (UPL > 0 && len <= 32u * UPL) {
 			typename Stat::Site v[UPL > 0 ? UPL : 1];
@@ -505,7 +524,7 @@ static constexpr int kTileMaxStages = 4;
 static constexpr int kTileConsumerWarps = kTileThreads / 32 - 1;
 static constexpr int kMaxTileCols = 7;  // of a statistic; the sliding tile stages `pos` as one more (kMaxStageCols)
 static constexpr int kMaxStageCols = kMaxTileCols + 1;
-static constexpr uint32_t kTileCtlBytes = 384;  // >= sizeof(TileCtl) = 352
+static constexpr uint32_t kTileCtlBytes = 384;  // >= sizeof(TileCtl) = 368
 
 
 // With more segments than this the tiled kernel gets a precomputed tile -> segment table: a CTA's
@@ -532,6 +551,7 @@ struct TileCtl {
 	uint64_t full[kTileMaxStages];
 	uint64_t empty[kTileMaxStages];
 	uint64_t s0[kTileMaxStages];                   // column element index of the tile's first site
+	uint32_t ns[kTileMaxStages];                   // elements staged (PGT_BOUNDS checks)
 	const char* cp[kTileMaxStages][kMaxStageCols];  // where site s0 of each column lives (shared, or global if unstaged)
 };
 static_assert(sizeof(TileCtl) <= kTileCtlBytes, "control block");
@@ -572,6 +592,7 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
 // outside [column, column + valid_elems) is ever read.
 __device__ __forceinline__ void producer_fill_stage(const TileCfg& tc, TileCtl* ctl, unsigned char* stages, uint32_t stg, uint64_t s0,
                                                     uint64_t s1, uint32_t lane) {
+	PGT_CHECK(s0 <= s1 && s1 <= tc.valid_elems && stg < tc.nstages);
 	// generic-proxy reads of this stage are done; order them before the async-proxy writes
 	asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 	unsigned char* stage = stages + (size_t)stg * tc.stage_bytes;
@@ -601,8 +622,10 @@ __device__ __forceinline__ void producer_fill_stage(const TileCfg& tc, TileCtl* 
 	uint32_t txsum = tx;
 #pragma unroll
 	for (int m = 16; m >= 1; m >>= 1) txsum += __shfl_xor_sync(0xffffffffu, txsum, m);
+	PGT_CHECK(!tx || (B0 >= col_lo && B1 <= col_hi && (uint32_t)(pad + (B0 - A)) + tx <= tc.col_cap[c] && tc.col_off[c] + tc.col_cap[c] <= tc.stage_bytes));
 	if (lane == 0) {
 		ctl->s0[stg] = s0;
+		ctl->ns[stg] = (uint32_t)(s1 - s0);
 		mbar_arrive_expect_tx(&ctl->full[stg], txsum);
 	}
 	__syncwarp();
@@ -820,6 +843,7 @@ __global__ void __launch_bounds__(kTileThreads, 1)
 					rel = (uint32_t)(sg.site_base + st - P.site_origin - s0);
 				}
 				if (!active) len = 0;
+				PGT_CHECK(len == 0 || (rel + len <= ctl->ns[stg] && j >= P.unit_lo && j < P.unit_hi));
 				typename Stat::Acc acc = Stat::zero();
 				if constexpr (std::is_same<Stat, HetStat>::value && G == 32) {
 					het_unit_from_tile(acc, cp[0], rel, len, lane);
@@ -874,6 +898,7 @@ __global__ void __launch_bounds__(256, 4) k_units_het_vec(DevPlan P, const int8_
 		}
 		const int8_t* A = geno + i0;
 		const int8_t* E = A + len;
+		PGT_CHECK(len == 0 || i0 + len <= P.col_elems);
 		const int8_t* A0 = (const int8_t*)(((uintptr_t)A + 15u) & ~(uintptr_t)15u);  // first aligned chunk inside
 		const int8_t* A1 = (const int8_t*)((uintptr_t)E & ~(uintptr_t)15u);          // end of the last aligned chunk
 		uint32_t nonmissing = 0, nhet = 0;
@@ -1012,6 +1037,7 @@ __global__ void __launch_bounds__(256) k_windows(DevPlan P, const typename Stat:
 			ep = __ldg(pos + (sg.site_base + fs + nsites - 1 - P.site_origin));
 		}
 		const typename Stat::Acc* up = units + (sg.unit_base + fu - units_base);
+		PGT_CHECK(sg.unit_base + fu >= P.unit_lo && sg.unit_base + fu + cnt <= P.unit_hi && w >= P.win_lo && w < P.win_hi);
 		typename Stat::Acc acc = Stat::zero();
 		for (uint64_t x = lane; x < cnt; x += 128u) {  // four partials per lane in flight; added in index order
 			typename Stat::Acc v[4];
@@ -1068,6 +1094,7 @@ __device__ __forceinline__ void emit_window(const DevPlan& P, const pgt_seg& sg,
 		ep = (uint32_t)(last - P.off[label]) + 1u;
 		have = true;
 	} else if (pos) {
+		PGT_CHECK(first >= P.site_origin && last - P.site_origin < P.col_elems);
 		sp = have_edges ? edge_start : __ldg(pos + (first - P.site_origin));  // the caller may have fetched them early
 		ep = have_edges ? edge_end : __ldg(pos + (last - P.site_origin));
 		have = true;
@@ -1096,6 +1123,7 @@ __global__ void __launch_bounds__(256) k_windows_small(DevPlan P, const typename
 		const uint64_t k = w - sg.win_base;
 		uint64_t fu;
 		const uint32_t cnt = (uint32_t)pgt_window_units(P.g, sg, k, &fu);
+		PGT_CHECK(cnt <= (uint32_t)P2 && sg.unit_base + fu >= P.unit_lo && sg.unit_base + fu + cnt <= P.unit_hi);
 		const typename Stat::Acc acc = SmallTree<Stat, P2, 1>::eval(units + (sg.unit_base + fu - units_base), 0u, cnt);
 		emit_window<Stat>(P, sg, w, k, acc, pos, out);
 	}
@@ -1134,6 +1162,7 @@ __global__ void __launch_bounds__(256) k_windows_persite(DevPlan P, Cols cols, p
 #pragma unroll
 		for (int q = 0; q < U; ++q) {
 			if (site[q] == ~0ull) continue;
+			PGT_CHECK(site[q] >= P.site_origin && site[q] - P.site_origin < P.col_elems);
 			v[q] = Stat::load(cols, site[q] - P.site_origin);
 			ps[q] = cols.pos ? __ldg(cols.pos + (site[q] - P.site_origin)) : 0u;
 		}
@@ -1234,6 +1263,7 @@ __global__ void __launch_bounds__(256) k_block_scan(DevPlan P, typename Stat::Ac
 		if (u0 < P.unit_lo) u0 = P.unit_lo;
 		if (u1 > P.unit_hi) u1 = P.unit_hi;
 		if (u1 <= u0) continue;
+		PGT_CHECK(u0 >= units_base && u0 >= P.unit_lo && u1 <= P.unit_hi);
 		cta_scan_dir<Stat, false>(units, pre, u0 - units_base, u1 - units_base, s_wtot, &s_carry);  // PRE (reads raw units)
 		cta_scan_dir<Stat, true>(units, units, u0 - units_base, u1 - units_base, s_wtot, &s_carry);  // SUF in place
 	}
@@ -1258,6 +1288,7 @@ __global__ void __launch_bounds__(256) k_windows_hgw(DevPlan P, const typename S
 		const uint64_t cnt = pgt_window_units(P.g, sg, k, &fu);
 		const uint64_t lu = fu + cnt - 1;  // segment-local first / last unit
 		const uint64_t gf = sg.unit_base + fu - units_base, gl = sg.unit_base + lu - units_base;
+		PGT_CHECK(sg.unit_base + fu >= P.unit_lo && sg.unit_base + lu < P.unit_hi);
 		typename Stat::Acc acc = Stat::zero();
 		if (fu / B == lu / B) {
 			// inside one block: block-aligned start (PRE up to the last unit), or it runs to the block /
@@ -1447,6 +1478,7 @@ __global__ void __launch_bounds__(kSlideThreads, SlideMinBlocks<Stat>::value) k_
 						leaf[e] = Stat::zero();
 						const uint32_t i = e0 + (uint32_t)e;
 						if ((uint32_t)e < sc.E && i >= i_lo && i < i_hi) {
+							PGT_CHECK(i - i_lo < ctl->ns[stg] && i < sc.pos_stride);
 							Stat::fold(leaf[e], Stat::load_tile(cp, i - i_lo), tc.minind);
 							if (has_pos) pb[i] = pstage[i - i_lo];
 						}
@@ -1519,6 +1551,7 @@ __global__ void __launch_bounds__(kSlideThreads, SlideMinBlocks<Stat>::value) k_
 							if (lr > lr_max) lr = lr_max;
 							const bool two = lr >= Wu;  // the window ends in block b
 							const uint32_t jl = two ? lr - Wu : lr;
+							PGT_CHECK(j < Wu && jl < Wu && obase + i < P.win_hi - P.win_lo);
 							Acc acc = Sf[j];
 							if (two) Stat::add(acc, Pr[jl]);
 							const uint64_t o = obase + i;
@@ -2308,6 +2341,7 @@ static int run_scan(const pgt_plan* plan, const pgt_range* range, pgt_stat stat,
 	P.win_hi = L.w_hi;
 	P.site_origin = L.origin;
 	P.nunits_total = plan->nunits;
+	P.col_elems = ~0ull;
 	P.mode = (int)plan->mode;
 
 	typename Stat::Acc* units = (typename Stat::Acc*)(ws + L.units_off);
@@ -2335,6 +2369,11 @@ static int run_scan(const pgt_plan* plan, const pgt_range* range, pgt_stat stat,
 		if (L.persite || L.slide) {
 			// windows straight from the sites: W = S = 1 (default arguments of fstWindow / hetWindow: an
 			// elementwise map) or the sliding tile for fine steps; no unit array, no level 2
+			if (nwin) {
+				uint64_t last_site;
+				pgt_plan_window(plan, L.w_hi - 1, nullptr, &last_site, nullptr);
+				P.col_elems = last_site + 1 - L.origin;
+			}
 			if (nwin && L.persite) {
 				const uint64_t want = (nwin + 255) / 256, cap = (uint64_t)num_sms() * 8;
 				ProfScope prof(1, st);
@@ -2355,6 +2394,7 @@ static int run_scan(const pgt_plan* plan, const pgt_range* range, pgt_stat stat,
 		if (bp && nunits) PGT_TRY(launch_bounds_kernel(P, cols->pos, ndata, bounds, st));
 		// elements the caller's columns are known to hold: up to the end of the last unit read
 		const uint64_t valid = bp ? ndata : pgt_plan_unit_start(plan, L.u_hi) - L.origin;
+		P.col_elems = valid;
 		PGT_TRY(launch_units<Stat>(P, C, units, bounds, valid, L.tileseg_cap ? (uint32_t*)(ws + L.tileseg_off) : nullptr, L.tileseg_cap, st));
 		// the global line reads the raw unit partials: before level 2, which may scan them in place
 		if (want_global) PGT_TRY(launch_global<Stat>(units, nglobal, (double*)(ws + L.gpart_off), out->dxy_global, st));
@@ -2536,6 +2576,7 @@ static int run_scan(const pgt_plan* plan, const pgt_range* range, pgt_stat stat,
 			Ps.win_lo = w;
 			Ps.win_hi = wb;
 			Ps.site_origin = s0;
+			Ps.col_elems = ns;
 			const pgt_windows o = device_table(slot);  // rewritten two slabs later, after this slab's copy-back (order of `st`)
 			if (L.persite) {
 				const uint64_t want = (wb - w + 255) / 256, cap = (uint64_t)num_sms() * 8;
@@ -2591,6 +2632,7 @@ static int run_scan(const pgt_plan* plan, const pgt_range* range, pgt_stat stat,
 		Ps.unit_lo = ua;
 		Ps.unit_hi = ub;
 		Ps.site_origin = s0;
+		Ps.col_elems = ns;
 		uint64_t* sb = bounds ? bounds + (ua - L.u_lo) : nullptr;
 		// bp: bounds are relative to the staged slice.  Slab i writes entries [ua, ub]; the shared
 		// entry ub is rewritten by slab i+1 relative to ITS slice, after slab i's unit kernel

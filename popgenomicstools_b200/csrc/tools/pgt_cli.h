@@ -629,7 +629,8 @@ struct ColumnStreamer {
 				if (pgt_device_alloc(&dcol[i], (size_t)(n * cols[i].elem)) != PGT_OK) return give_up(pgt_last_error());
 			// text: the parser threads own the cores and produce ~8 GB/s of columns; cache: nothing else runs
 			const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
-			const unsigned nthreads = fd >= 0 ? std::min(8u, hw) : std::min(4u, hw);
+			unsigned nthreads = fd >= 0 ? std::min(16u, hw) : std::min(4u, hw);
+			if (const char* e = getenv("PGT_UPLOAD_THREADS")) nthreads = std::max(1, atoi(e));
 			pgt_uploader* u = nullptr;
 			if (pgt_uploader_create(&u, nullptr, 0, 2 * nthreads, (size_t)16 << 20, nthreads) != PGT_OK) return give_up(pgt_last_error());
 			std::lock_guard<std::mutex> lk(mu);

@@ -205,16 +205,15 @@ def test_streaming_upload_gives_the_same_rows(tmp_path):
     offs = np.array([0, 200000, 290000, 291500], np.uint64)
     d = str(tmp_path)
     stream = {"PGT_STREAM_MIN_SITES": "1"}
-    for kind, tool, argsets in (("fst", "fstWindow", ([5000, 1000], [1000, 1], [])), ("het", "hetWindow", ([4096, 512], [], [100000, 100000]))):
+    for kind, tool, argsets in (("fst", "fstWindow", ([5000, 1000], [1000, 1])), ("het", "hetWindow", ([4096, 512], []))):
         O.write_text(kind, os.path.join(d, f"s.{kind}"), names, offs, seed=4, density=3)
         assert U.run(U.ours(tool), [f"s.{kind}"], cwd=d, env={"PGT_PACK": os.path.join(d, f"s.{kind}.pgtc")})[0] == 0
         for args in argsets:
             base = U.run(U.ours(tool), [f"s.{kind}"] + args, cwd=d, env={"PGT_STREAM": "0"})
             assert base[0] == 0 and base[2] == "" and len(base[1].splitlines()) > 50
-            for src in (f"s.{kind}", f"s.{kind}.pgtc"):
-                for extra in ({}, {"PGT_PARALLEL_MIN_BYTES": "1", "PGT_THREADS": "5"}):
-                    got = U.run(U.ours(tool), [src] + args, cwd=d, env=dict(stream, **extra))
-                    assert got == base, (tool, args, src, extra, got[2][:200])
+            for src, extra in ((f"s.{kind}", {"PGT_PARALLEL_MIN_BYTES": "1", "PGT_THREADS": "5"}), (f"s.{kind}.pgtc", {})):
+                got = U.run(U.ours(tool), [src] + args, cwd=d, env=dict(stream, **extra))
+                assert got == base, (tool, args, src, extra, got[2][:200])
         rc, out, err = U.run(U.ours(tool), [f"s.{kind}.pgtc"] + list(argsets[0]), cwd=d, env=dict(stream, PGT_TIMING="1"))
         t = json.loads(err.strip().splitlines()[-1])
         assert rc == 0 and t["mode"] == "stream" and t["upload_bytes"] == int(offs[-1]) * (20 if kind == "fst" else 5), t
