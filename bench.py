@@ -53,6 +53,9 @@ def parse_args():
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-cli-large", action="store_true", help="skip the large-input legs of the drop-in fstWindow (N = 1 only)")
+    ap.add_argument("--cli-large-cache-sites", type=float, default=6e8)
+    ap.add_argument("--cli-large-text-sites", type=float, default=2.4e8)
     ap.add_argument("--no-configs", action="store_true", help="skip the per-config legs (C1, C2, C3, C5, C5-S1)")
     ap.add_argument("--configs", default="", help="comma-separated subset of the per-config legs")
     ap.add_argument("--config-steps", type=int, default=5)
@@ -681,6 +684,46 @@ def run_b200(args):
         except Exception as ex:
             cpu = {"value": None, "unit": UNIT, "cores": 0, "kind": "reference", "sample": "failed: " + repr(ex)[:200]}
 
+    # ---- the drop-in fstWindow on LARGE inputs (the 48 M-site sample above mostly measures CUDA start-up): a 12 GB
+    # columnar cache and a 7.6 GB text file, streaming upload (default) against the host-memory path from pageable columns
+    cli_large = None
+    if rank == 0 and world == 1 and not args.no_cli_large and not args.no_cpu_baseline:
+        try:
+            sys.path.insert(0, os.path.join(ROOT, "tools"))
+            import probe_cli_large as PL
+            work = "/dev/shm" if os.path.isdir("/dev/shm") else tempfile.gettempdir()
+            exe = os.path.join(ROOT, "popgenomicstools_b200", "bin", "fstWindow")
+            cli_large = []
+            nc, ntx = int(args.cli_large_cache_sites), int(args.cli_large_text_sites)
+            if nc:
+                path = os.path.join(work, "pgt_bench_large.pgtc")
+                PL.write_cache(path, nc)
+                torch.cuda.empty_cache()
+                for env, label in (({}, "cache/stream"), ({"PGT_STREAM": "0"}, "cache/host-pageable")):
+                    r = PL.run_tool(exe, path, env, label)
+                    r["input_bytes"] = os.path.getsize(path)
+                    cli_large.append(r)
+                os.remove(path)
+            if ntx:
+                lnames, loffs = human_like_contigs(ntx, 10000)
+                import multiprocessing as mp
+                jobs = [(os.path.join(work, f"pgt_bench_large_{nm}.fst"), nm, int(loffs[i]), int(loffs[i + 1]), 4) for i, nm in enumerate(lnames)]
+                with mp.get_context("fork").Pool(min(24, os.cpu_count() or 1)) as pool:
+                    pool.map(PL._write_contig, jobs)
+                path = os.path.join(work, "pgt_bench_large.fst")
+                with open(path, "wb") as wf:
+                    for j in jobs:
+                        with open(j[0], "rb") as rf:
+                            shutil.copyfileobj(rf, wf, 1 << 24)
+                        os.remove(j[0])
+                for env, label in (({}, "text/stream"), ({"PGT_STREAM": "0"}, "text/host-pageable")):
+                    r = PL.run_tool(exe, path, env, label)
+                    r["input_bytes"] = os.path.getsize(path)
+                    cli_large.append(r)
+                os.remove(path)
+        except Exception as ex:
+            cli_large = {"error": repr(ex)[:300]}
+
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": W_steps,
@@ -702,6 +745,7 @@ def run_b200(args):
             "roofline": roofline,
             "configs": configs,
             "cpu_baseline": cpu,
+            "our_cli_large": cli_large,
         }
         if glob is not None:
             line["dxy_global"] = [float(x) for x in glob]

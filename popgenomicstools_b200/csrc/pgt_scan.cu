@@ -1667,12 +1667,22 @@ __global__ void __launch_bounds__(kGlobalBlocks) k_global_final(const double* __
 __global__ void __launch_bounds__(1024) k_global_sites(Cols cols, uint64_t i0, uint64_t i1, double* __restrict__ partial3) {
 	double d = 0.0;
 	unsigned long long ne = 0, nk = 0;
-	for (uint64_t i = i0 + (uint64_t)blockIdx.x * 1024u + threadIdx.x; i < i1; i += (uint64_t)kGlobalBlocks * 1024u) {
-		DxyStat::Acc a = DxyStat::zero();
-		DxyStat::fold(a, DxyStat::load(cols, i), cols.minind);
-		d = __dadd_rn(d, a.dxy);
-		ne += a.neff;
-		nk += a.nskip;
+	constexpr int U = 4;  // four sites' column loads in flight per thread; folded in index order
+	const uint64_t stride = (uint64_t)kGlobalBlocks * 1024u;
+	for (uint64_t i = i0 + (uint64_t)blockIdx.x * 1024u + threadIdx.x; i < i1; i += U * stride) {
+		DxyStat::Site v[U];
+#pragma unroll
+		for (int q = 0; q < U; ++q)
+			if (i + q * stride < i1) v[q] = DxyStat::load(cols, i + q * stride);
+#pragma unroll
+		for (int q = 0; q < U; ++q) {
+			if (i + q * stride >= i1) break;
+			DxyStat::Acc a = DxyStat::zero();
+			DxyStat::fold(a, v[q], cols.minind);
+			d = __dadd_rn(d, a.dxy);
+			ne += a.neff;
+			nk += a.nskip;
+		}
 	}
 	block_reduce_global(d, ne, nk, partial3 + 3 * blockIdx.x);
 }
