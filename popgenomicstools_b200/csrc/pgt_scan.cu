@@ -201,7 +201,7 @@ static int g_tune_level2 = 0;
 static int g_tune_stages = 2;      // tiled kernel: shared-memory stages (2..4)
 static int g_tune_stage_kb = 110;  // tiled kernel: KB per stage (stages * stage_kb <= 224)
 extern int g_tune_xgroup;          // extreme scan (pgt_extreme.cu): lanes per unit, 0 = auto
-//   slide: 0 auto, 1 never use the sliding-tile kernel (k_slide), 2 use it whenever it fits shared memory (any W <= 1288)
+//   slide: 0 auto, 1 never use the sliding-tile kernel (k_slide), 2 use it whenever it fits shared memory (any W <= 1048)
 static int g_tune_slide = 0;
 
 static int num_sms() {
@@ -1316,13 +1316,17 @@ __global__ void __launch_bounds__(256) k_windows_hgw(DevPlan P, const typename S
 //         window = SUF_m[f mod W] (+ PRE_{m+1}[l mod W] when l is in block m + 1)
 //     with PRE / SUF the inclusive prefix / suffix sums inside a block (van Herk / Gil-Werman): only
 //     additions of true partial sums, no differences, no cancellation;
-//   * persistent CTAs take CHUNKS of consecutive windows; a chunk walks its blocks in order: the
-//     producer warp stages block b's slice of every column with bulk async copies (the ring of
-//     k_units_tiled), the 224 consumer threads scan it in registers (thread t owns elements
-//     [t*E, (t+1)*E), E = ceil(W / 224): forward total, two warp shuffle scans, warp totals through
-//     shared memory, then PRE running forward from the thread's base into `Pr` and SUF running backward
-//     in place), emit the windows that start in block b - 1 from Sf (= SUF_{b-1}) and Pr, and keep
-//     SUF_b for the next step.  Every site is read once per chunk; neighbouring chunks share W - S sites.
+//   * persistent CTAs take CHUNKS of consecutive windows; a chunk walks its blocks in order, G blocks per
+//     step: the producer warp stages the step's slice of every column (positions included) with bulk
+//     async copies (the ring of k_units_tiled); every block is scanned by its own team of WPB warps
+//     (thread q of a team owns elements [q*E, (q+1)*E) of its block: forward total, two warp shuffle scans,
+//     the team's warp totals through shared memory, then PRE running forward from the thread's base and
+//     SUF running backward from it); the windows that start in the blocks of the step -- all but its last
+//     block, plus the last block of the step before -- are emitted from SUF and PRE in shared memory with
+//     coalesced row stores.  SUF and the positions are double-buffered by step parity, so a step has two
+//     CTA-wide barriers.  Every site is read once per chunk; neighbouring chunks share W - S sites.
+//     (E, WPB, G) are chosen per W so that a step covers as many sites as the 7 consumer warps can own:
+//     W = 1000: E = 5, one block of 7 warps; W = 256: E = 4, three blocks of 2 warps.
 //
 // Summation order: a pure function of (W, S) and the position of a site inside its block -- not of
 // chunks, CTAs, stages or shards (a chunk that starts or ends inside a block simply has the sites
@@ -1330,15 +1334,36 @@ __global__ void __launch_bounds__(256) k_windows_hgw(DevPlan P, const typename S
 // reads), so results are bit-identical for any GPU count.  Reference semantics: fstWindow.cpp:80-99.
 
 static constexpr int kSlideWarps = 7;                          // consumer warps (+ the producer warp = 256 threads: 128 registers each at two CTAs per SM)
-static constexpr int kSlideConsumers = kSlideWarps * 32;       // part of the summation order (E = ceil(W / 224))
+static constexpr int kSlideConsumers = kSlideWarps * 32;
 static constexpr int kSlideThreads = kSlideConsumers + 32;     // + the producer warp (the last one)
-static constexpr uint32_t kSlideMaxE = 6;                      // W <= 1344 (and the fused block must fit shared memory: W <= 1288)
+static constexpr uint32_t kSlideMaxE = 6;                      // W <= 1344 (and the fused step must fit shared memory: W <= 1048)
 static constexpr uint32_t kSlideWtBytes = 512;                 // warp totals: 7 x Acc (<= 40 B)
 
+// The team shape for a window size: E elements per thread, WPB warps per block, G = 7 / WPB blocks per step --
+// the (E, WPB) with the most sites per step, the smaller E on ties.  Part of the summation order.
+struct SlideTeam {
+	uint32_t E, wpb, G;
+};
+// (a step holds at most 1024 sites -- G * (W rounded up to 32) -- so that the fused statistic's step fits shared memory)
+__host__ __device__ inline SlideTeam slide_team(uint32_t W) {
+	SlideTeam best{1, kSlideWarps, 0};
+	const uint32_t wp = (W + 31u) / 32u * 32u;
+	for (uint32_t E = 1; E <= kSlideMaxE; ++E) {
+		const uint32_t tpb = (W + E - 1) / E;
+		const uint32_t wpb = (tpb + 31) / 32;
+		if (wpb > (uint32_t)kSlideWarps) continue;
+		uint32_t G = (uint32_t)kSlideWarps / wpb;
+		if (G > 1024u / wp) G = 1024u / wp;
+		if (G < 1) G = 1;
+		if (G > best.G) best = SlideTeam{E, wpb, G};
+	}
+	return best;
+}
+
 struct SlideCfg {
-	uint32_t E;              // elements of a block per consumer thread
+	uint32_t E, wpb, G;      // slide_team(W)
+	uint32_t wp;             // stride of one block's arrays in shared memory (W rounded up to 32)
 	uint32_t sf_off, pr_off, pos_off, stage_off;  // byte offsets inside the dynamic shared memory
-	uint32_t pos_stride;     // elements of one of the two position buffers
 	uint32_t pos_col;        // staging index of the position column, 0xffffffff = positions not wanted
 	uint64_t chunk_windows;  // windows per chunk
 	uint64_t nchunks;
@@ -1384,8 +1409,8 @@ __device__ __forceinline__ bool slide_run_at(const DevPlan& P, uint64_t w, uint6
 	return true;
 }
 
-// (register budget: two CTAs per SM for the narrow statistics -- 112 registers -- and one for the fused
-// scan, whose block fills the shared memory of an SM anyway)
+// (register budget: two CTAs per SM for the narrow statistics -- 128 registers -- and one for the fused
+// scan, whose step fills the shared memory of an SM anyway)
 template <class Stat>
 struct SlideMinBlocks {
 	static constexpr int value = 2;
@@ -1394,18 +1419,21 @@ template <>
 struct SlideMinBlocks<FusedStat> {
 	static constexpr int value = 1;
 };
-template <class Stat, int EMAX>
+// MULTI = several blocks per step (G > 1, W <= 512); with one block per step the team arithmetic folds away
+template <class Stat, int EMAX, bool MULTI>
 __global__ void __launch_bounds__(kSlideThreads, SlideMinBlocks<Stat>::value) k_slide(DevPlan P, TileCfg tc, SlideCfg sc, pgt_windows out) {
 	typedef typename Stat::Acc Acc;
 	extern __shared__ __align__(128) unsigned char smem[];
 	TileCtl* ctl = reinterpret_cast<TileCtl*>(smem);
 	Acc* wt = reinterpret_cast<Acc*>(smem + kTileCtlBytes);
-	Acc* Sf = reinterpret_cast<Acc*>(smem + sc.sf_off);
-	Acc* Pr = reinterpret_cast<Acc*>(smem + sc.pr_off);
-	uint32_t* posb = reinterpret_cast<uint32_t*>(smem + sc.pos_off);  // positions of the blocks b - 1 and b: [2][pos_stride]
+	Acc* SfBase = reinterpret_cast<Acc*>(smem + sc.sf_off);           // SUF of the step's blocks: [2][G * wp], by step parity
+	Acc* Pr = reinterpret_cast<Acc*>(smem + sc.pr_off);               // PRE of the step's blocks: [G * wp]
+	uint32_t* PosBase = reinterpret_cast<uint32_t*>(smem + sc.pos_off);  // positions of the step's blocks: [2][G * wp]
 	unsigned char* stages = smem + sc.stage_off;
 	const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
 	const uint64_t W = P.g.W, S = P.g.S;
+	const uint32_t Wu = P.g.W, Su = P.g.S, G = MULTI ? sc.G : 1u, gw = G * sc.wp;
+	const uint32_t wpb = MULTI ? sc.wpb : (uint32_t)kSlideWarps;
 	const bool has_pos = sc.pos_col != 0xffffffffu;
 
 	if (threadIdx.x == 0) {
@@ -1418,16 +1446,16 @@ __global__ void __launch_bounds__(kSlideThreads, SlideMinBlocks<Stat>::value) k_
 	__syncthreads();
 
 	if (warp == kSlideWarps) {
-		// ------------------------------------------------------------------ producer: one stage per block
+		// ------------------------------------------------------------------ producer: one stage per step (G blocks)
 		uint32_t it = 0;
 		for (uint64_t c = blockIdx.x; c < sc.nchunks; c += gridDim.x) {
 			const uint64_t wa = P.win_lo + c * sc.chunk_windows;
 			const uint64_t wb = P.win_hi - wa < sc.chunk_windows ? P.win_hi : wa + sc.chunk_windows;
 			SlideRun r;
 			for (bool ok = slide_run_at(P, wa, wb, r, true); ok; ok = slide_run_at(P, r.sg.win_base + r.kb, wb, r, false)) {
-				for (uint64_t b = r.lo / W; b * W < r.hi; ++b, ++it) {
+				for (uint64_t b = r.lo / W; b * W < r.hi; b += G, ++it) {
 					const uint64_t x0 = b * W > r.lo ? b * W : r.lo;
-					const uint64_t x1 = (b + 1) * W < r.hi ? (b + 1) * W : r.hi;
+					const uint64_t x1 = (b + G) * W < r.hi ? (b + G) * W : r.hi;
 					const uint32_t stg = it % tc.nstages;
 					if (it >= tc.nstages) mbar_wait(&ctl->empty[stg], ((it / tc.nstages) - 1u) & 1u);
 					producer_fill_stage(tc, ctl, stages, stg, r.sg.site_base + x0 - P.site_origin, r.sg.site_base + x1 - P.site_origin, lane);
@@ -1439,8 +1467,11 @@ __global__ void __launch_bounds__(kSlideThreads, SlideMinBlocks<Stat>::value) k_
 
 	// ---------------------------------------------------------------------- consumers
 	const uint32_t t = threadIdx.x;
-	const uint32_t e0 = t * sc.E;  // first element of a block this thread owns
-	uint32_t it = 0;
+	const uint32_t team = MULTI ? warp / wpb : 0u;  // which block of a step this thread works on (>= G: none)
+	const uint32_t tw = warp - team * wpb;          // warp inside its team
+	const uint32_t e0 = (tw * 32u + lane) * sc.E;   // first element of the block this thread owns
+	const bool member = MULTI ? team < G : true;
+	uint32_t it = 0, step = 0;  // `step` selects the halves of the double buffers
 	for (uint64_t c = blockIdx.x; c < sc.nchunks; c += gridDim.x) {
 		const uint64_t wa = P.win_lo + c * sc.chunk_windows;
 		const uint64_t wb = P.win_hi - wa < sc.chunk_windows ? P.win_hi : wa + sc.chunk_windows;
@@ -1451,41 +1482,49 @@ __global__ void __launch_bounds__(kSlideThreads, SlideMinBlocks<Stat>::value) k_
 			// that only walks forward replaces a binary search per window
 			uint32_t lc = r.sg.first_contig;
 			uint64_t lc_end = r.sg.ncontig > 1 ? P.off[lc + 1] : ~0ull;  // global site where contig lc ends
-			// kc_cur = ceil(b*W / S): first window that starts at or after block b; kept incrementally
+			// kc = ceil(b*W / S): first window that starts at or after block b; kept incrementally
 			uint64_t kq = m_first * W / S;
 			uint32_t krem = (uint32_t)(m_first * W - kq * S);
-			uint64_t kc_cur = kq + (krem != 0u), kc_prev = kc_cur;
-			for (uint64_t b = m_first; b <= m_last + 1; ++b) {
-				const bool incoming = b <= m_last;  // block b arrives; the windows starting in block b - 1 leave
+			uint64_t kc_from = kq + (krem != 0u);  // first window not yet emitted (by block start)
+			for (uint64_t b = m_first; b <= m_last; b += G, ++step) {
+				// blocks [b, b + gi) arrive; the windows starting in blocks [b - 1, b + gi - 2] leave -- and those of
+				// block b + gi - 1 too when it is the run's last block (they end inside it)
+				const uint32_t gi = (uint32_t)(m_last + 1 - b < G ? m_last + 1 - b : G);
+				Acc* Sf = SfBase + (step & 1u) * gw;
+				const Acc* SfPrev = SfBase + ((step & 1u) ^ 1u) * gw + (G - 1u) * sc.wp;  // SUF of block b - 1
+				uint32_t* Pos = PosBase + (step & 1u) * gw;
+				const uint32_t* PosPrev = PosBase + ((step & 1u) ^ 1u) * gw + (G - 1u) * sc.wp;
+				const uint32_t stg = it % tc.nstages;
+				mbar_wait(&ctl->full[stg], (it / tc.nstages) & 1u);
+				++it;
 				Acc leaf[EMAX];
+				uint32_t pv[EMAX];
 				Acc up = Stat::zero(), dn = Stat::zero();
-				if (incoming) {
-					const uint32_t stg = it % tc.nstages;
-					mbar_wait(&ctl->full[stg], (it / tc.nstages) & 1u);
-					++it;
+				{
 					const char* cp[kMaxTileCols];
 #pragma unroll
 					for (int cc = 0; cc < kMaxTileCols; ++cc) cp[cc] = ctl->cp[stg][cc];
-					const uint64_t x0 = b * W > r.lo ? b * W : r.lo;
-					const uint64_t x1 = (b + 1) * W < r.hi ? (b + 1) * W : r.hi;
-					// sites of the block outside [x0, x1) are absent (other chunk / beyond the segment): +0 leaves
-					const uint32_t i_lo = (uint32_t)(x0 - b * W), i_hi = (uint32_t)(x1 - b * W);
-					uint32_t* pb = posb + (b & 1u) * sc.pos_stride;
 					const uint32_t* pstage = has_pos ? reinterpret_cast<const uint32_t*>(ctl->cp[stg][sc.pos_col]) : nullptr;
+					const uint64_t x0 = b * W > r.lo ? b * W : r.lo;            // first staged site
+					const uint64_t x1 = (b + gi) * W < r.hi ? (b + gi) * W : r.hi;
+					// sites of a block outside [x0, x1) are absent (other chunk / beyond the segment): +0 leaves
+					const uint32_t s_lo = (uint32_t)(x0 - b * W), s_hi = (uint32_t)(x1 - b * W);  // relative to block b
+					const uint32_t base = team * Wu + e0;                                          // this thread's first element, same frame
 					Acc tot = Stat::zero();
 #pragma unroll
 					for (int e = 0; e < EMAX; ++e) {
 						leaf[e] = Stat::zero();
-						const uint32_t i = e0 + (uint32_t)e;
-						if ((uint32_t)e < sc.E && i >= i_lo && i < i_hi) {
-							PGT_CHECK(i - i_lo < ctl->ns[stg] && i < sc.pos_stride);
-							Stat::fold(leaf[e], Stat::load_tile(cp, i - i_lo), tc.minind);
-							if (has_pos) pb[i] = pstage[i - i_lo];
+						pv[e] = 0u;
+						const uint32_t i = base + (uint32_t)e;
+						if (member && (uint32_t)e < sc.E && e0 + (uint32_t)e < Wu && i >= s_lo && i < s_hi) {
+							PGT_CHECK(i - s_lo < ctl->ns[stg]);
+							Stat::fold(leaf[e], Stat::load_tile(cp, i - s_lo), tc.minind);
+							if (has_pos) pv[e] = pstage[i - s_lo];
 						}
 						Stat::add(tot, leaf[e]);
 					}
 					__syncwarp();
-					if (lane == 0) mbar_arrive(&ctl->empty[stg]);  // the block now lives in registers (positions: in posb)
+					if (lane == 0) mbar_arrive(&ctl->empty[stg]);  // the step's sites now live in registers
 					up = tot;
 					dn = tot;
 #pragma unroll
@@ -1503,57 +1542,83 @@ __global__ void __launch_bounds__(kSlideThreads, SlideMinBlocks<Stat>::value) k_
 					}
 					if (lane == 31u) wt[warp] = up;  // the warp's total, forward order
 				}
-				slide_bar();  // warp totals visible
-				if (incoming) {
+				slide_bar();  // warp totals visible; every thread has left the emit phase of the step before
+				{
 					Acc bpre = Stat::zero(), bsuf = Stat::zero();
 #pragma unroll
-					for (int w2 = 0; w2 < kSlideWarps - 1; ++w2)
-						if ((uint32_t)w2 < warp) Stat::add(bpre, wt[w2]);
+					for (int w2 = 0; w2 < kSlideWarps - 1; ++w2)  // the team's warps before this one, in order
+						if ((uint32_t)w2 < tw && member) Stat::add(bpre, wt[team * wpb + w2]);
 #pragma unroll
-					for (int w2 = kSlideWarps - 1; w2 > 0; --w2)
-						if ((uint32_t)w2 > warp) Stat::add(bsuf, wt[w2]);
+					for (int w2 = kSlideWarps - 1; w2 > 0; --w2)  // the team's warps after it, last first
+						if ((uint32_t)w2 > tw && (uint32_t)w2 < wpb && member) Stat::add(bsuf, wt[team * wpb + w2]);
 					Acc xu = shfl_up_acc(up, 1), xd = shfl_down_acc(dn, 1);
 					if (lane == 0) xu = Stat::zero();
 					if (lane == 31u) xd = Stat::zero();
 					Stat::add(bpre, xu);
 					Stat::add(bsuf, xd);
+					const uint32_t o0 = team * sc.wp + e0;
 #pragma unroll
 					for (int e = 0; e < EMAX; ++e) {  // PRE: running forward from everything before this thread
-						if ((uint32_t)e < sc.E && e0 + (uint32_t)e < (uint32_t)W) {
+						if (member && (uint32_t)e < sc.E && e0 + (uint32_t)e < Wu) {
 							Stat::add(bpre, leaf[e]);
-							Pr[e0 + e] = bpre;
+							Pr[o0 + e] = bpre;
+							if (has_pos) Pos[o0 + e] = pv[e];
 						}
 					}
 #pragma unroll
-					for (int e = EMAX - 1; e >= 0; --e) {  // SUF: running backward from everything after it, kept in registers
-						if ((uint32_t)e < sc.E && e0 + (uint32_t)e < (uint32_t)W) {
+					for (int e = EMAX - 1; e >= 0; --e) {  // SUF: running backward from everything after it
+						if (member && (uint32_t)e < sc.E && e0 + (uint32_t)e < Wu) {
 							Stat::add(bsuf, leaf[e]);
-							leaf[e] = bsuf;
+							Sf[o0 + e] = bsuf;
 						}
 					}
 				}
-				slide_bar();  // Pr and the positions of block b complete (Sf holds SUF of block b - 1)
-				if (b > m_first) {
-					// windows with (b-1)*W <= k*S < b*W, cut to the run; everything below is relative to block b - 1
-					const uint64_t mb = b - 1;
-					const uint64_t k_lo = kc_prev > r.ka ? kc_prev : r.ka, k_hi = kc_cur < r.kb ? kc_cur : r.kb;
-					if (k_hi > k_lo) {
-						const uint32_t cnt = (uint32_t)(k_hi - k_lo), Wu = (uint32_t)W, Su = (uint32_t)S;
-						const uint32_t j0 = (uint32_t)(k_lo * S - mb * W);
-						const uint64_t left = r.sg.nsites - mb * W;  // sites of the segment from block b - 1 on
-						const uint32_t lr_max = (left < 2ull * Wu ? (uint32_t)left : 2u * Wu) - 1u;
-						const uint64_t obase = r.sg.win_base + k_lo - P.win_lo, gbase = r.sg.site_base + mb * W;
-						const uint32_t* pm = posb + (mb & 1u) * sc.pos_stride;  // positions of block b - 1
-						const uint32_t* pn = posb + (b & 1u) * sc.pos_stride;   // positions of block b
+				slide_bar();  // PRE, SUF and the positions of the step's blocks complete
+				{
+					// windows that start in blocks [eb_lo, eb_hi]; everything below is relative to the start of block b - 1
+					const uint64_t eb_lo = b > m_first ? b - 1 : b;
+					const uint64_t eb_hi = (b + gi - 1 == m_last) ? m_last : b + gi - 2;  // may be eb_lo - 1: nothing to emit yet
+					// ceil((eb_hi + 1) * W / S): the quotient / remainder of (blocks emitted so far) * W / S stepped forward
+					uint64_t kc_to = kc_from;
+					if (eb_hi + 1 > eb_lo) {
+						const uint32_t nb = (uint32_t)(eb_hi + 1 - eb_lo);
+						kq += (uint64_t)nb * P.g.q;
+						krem += nb * P.g.r;
+						while (krem >= Su) {
+							krem -= Su;
+							++kq;
+						}
+						kc_to = kq + (krem != 0u);
+					}
+					const uint64_t k_lo = kc_from > r.ka ? kc_from : r.ka, k_hi = kc_to < r.kb ? kc_to : r.kb;
+					if (eb_hi + 1 > eb_lo && k_hi > k_lo) {
+						const uint32_t cnt = (uint32_t)(k_hi - k_lo);
+						const uint32_t rel0 = (uint32_t)(k_lo * S + W - b * W);  // first window's start, relative to block b - 1
+						const uint64_t left = r.sg.nsites + W - b * W;            // sites of the segment from block b - 1 on
+						const uint32_t last_rel = (uint32_t)(left < (uint64_t)(G + 2u) * Wu ? left : (uint64_t)(G + 2u) * Wu) - 1u;
+						const uint64_t obase = r.sg.win_base + k_lo - P.win_lo;
+						const uint64_t gbase = r.sg.site_base + b * W - W;  // global site of relative position 0
 						for (uint32_t i = t; i < cnt; i += kSlideConsumers) {
-							const uint32_t j = j0 + i * Su;
-							uint32_t lr = j + Wu - 1u;
-							if (lr > lr_max) lr = lr_max;
-							const bool two = lr >= Wu;  // the window ends in block b
-							const uint32_t jl = two ? lr - Wu : lr;
-							PGT_CHECK(j < Wu && jl < Wu && obase + i < P.win_hi - P.win_lo);
-							Acc acc = Sf[j];
-							if (two) Stat::add(acc, Pr[jl]);
+							const uint32_t rel = rel0 + i * Su;
+							uint32_t blk = 0, brel = 0;  // blk = rel / W; brel = blk * W
+							if (MULTI) {
+								while (rel >= brel + Wu) {  // <= G <= 7 steps
+									brel += Wu;
+									++blk;
+								}
+							} else if (rel >= Wu) {
+								brel = Wu;
+								blk = 1u;
+							}
+							const uint32_t j = rel - brel;  // blk = 0: block b - 1; blk = 1 + g: block g of this step
+							uint32_t lr = rel + Wu - 1u;
+							if (lr > last_rel) lr = last_rel;
+							const bool two = lr >= brel + Wu;  // the window ends in the next block
+							const uint32_t jl = two ? lr - brel - Wu : lr - brel;
+							PGT_CHECK(j < Wu && jl < Wu && blk <= gi && (!two || blk < gi) && obase + i < P.win_hi - P.win_lo);
+							const uint32_t boff = (blk - 1u) * sc.wp;  // (unused when blk == 0)
+							Acc acc = blk == 0u ? SfPrev[j] : Sf[boff + j];
+							if (two) Stat::add(acc, Pr[blk * sc.wp + jl]);
 							const uint64_t o = obase + i;
 							const uint64_t glast = gbase + lr;
 							while (glast >= lc_end) {
@@ -1561,9 +1626,11 @@ __global__ void __launch_bounds__(kSlideThreads, SlideMinBlocks<Stat>::value) k_
 								lc_end = P.off[lc + 1];
 							}
 							if (out.label) out.label[o] = lc;
-							if (out.nsites) out.nsites[o] = lr - j + 1u;
+							if (out.nsites) out.nsites[o] = lr - rel + 1u;
 							if (has_pos) {
-								const uint32_t sp = pm[j], ep = two ? pn[jl] : pm[jl];
+								const uint32_t* ps = blk == 0u ? PosPrev : Pos + boff;  // positions of the window's first block
+								const uint32_t sp = ps[j];
+								const uint32_t ep = two ? Pos[blk * sc.wp + jl] : ps[jl];
 								if (out.start_pos) out.start_pos[o] = sp;
 								if (out.end_pos) out.end_pos[o] = ep;
 								if (out.mid_pos) out.mid_pos[o] = (sp + ep) / 2u;  // uint32 arithmetic, fstWindow.cpp:73
@@ -1571,21 +1638,7 @@ __global__ void __launch_bounds__(kSlideThreads, SlideMinBlocks<Stat>::value) k_
 							Stat::emit(out, o, acc);
 						}
 					}
-				}
-				// ceil(b*W / S) -> ceil((b+1)*W / S) without a division
-				kc_prev = kc_cur;
-				kq += P.g.q;
-				krem += P.g.r;
-				if (krem >= (uint32_t)S) {
-					krem -= (uint32_t)S;
-					++kq;
-				}
-				kc_cur = kq + (krem != 0u);
-				slide_bar();  // Sf no longer read
-				if (incoming) {
-#pragma unroll
-					for (int e = 0; e < EMAX; ++e)
-						if ((uint32_t)e < sc.E && e0 + (uint32_t)e < (uint32_t)W) Sf[e0 + e] = leaf[e];
+					if (eb_hi + 1 > eb_lo) kc_from = kc_to;
 				}
 			}
 		}
@@ -1748,30 +1801,33 @@ struct Layout {
 // The choice fixes the summation order, so it is a pure function of (W, S, unit, statistic) and the
 // tuning knob -- never of the input size, the window range or the shard.
 struct SlideShape {
-	uint32_t E, nstages, stage_bytes, sf_off, pr_off, pos_off, pos_stride, stage_off, ncol;
+	uint32_t E, wpb, G, wp, nstages, stage_bytes, sf_off, pr_off, pos_off, stage_off, ncol;
 	uint32_t col_off[kMaxStageCols], col_cap[kMaxStageCols];
 	size_t smem;
 };
 // (sized with the position column staged, whether or not a scan passes positions: the choice of path must
 // not depend on it)
 static void slide_footprint(const pgt_geom& g, pgt_stat stat, SlideShape* sh) {
+	const SlideTeam tm = slide_team(g.W);
+	sh->E = tm.E;
+	sh->wpb = tm.wpb;
+	sh->G = tm.G;
+	sh->wp = (uint32_t)align_up(g.W, 32);
 	ColDesc d[8];
 	const int nc = stat_columns(stat, PGT_MODE_SITES, nullptr, d);
 	uint32_t o = 0;
-	for (int c = 0; c <= nc; ++c) {  // column nc = pos (uint32)
+	for (int c = 0; c <= nc; ++c) {  // column nc = pos (uint32); a stage holds the G blocks of a step
 		sh->col_off[c] = o;
-		sh->col_cap[c] = (uint32_t)align_up((size_t)g.W * (c < nc ? d[c].elem : 4) + 48, 16);
+		sh->col_cap[c] = (uint32_t)align_up((size_t)tm.G * g.W * (c < nc ? d[c].elem : 4) + 48, 16);
 		o += sh->col_cap[c];
 	}
 	sh->ncol = (uint32_t)nc;
 	sh->stage_bytes = (uint32_t)align_up(o, 128);
-	sh->E = (g.W + kSlideConsumers - 1) / kSlideConsumers;
-	const uint32_t accb = (uint32_t)align_up((size_t)g.W * acc_bytes(stat), 128);
+	const uint32_t accb = (uint32_t)align_up((size_t)tm.G * sh->wp * acc_bytes(stat), 128);
 	sh->sf_off = kTileCtlBytes + kSlideWtBytes;
-	sh->pr_off = sh->sf_off + accb;
+	sh->pr_off = sh->sf_off + 2 * accb;              // SUF: two halves (step parity)
 	sh->pos_off = sh->pr_off + accb;
-	sh->pos_stride = (uint32_t)align_up(g.W, 32);
-	sh->stage_off = sh->pos_off + 2 * sh->pos_stride * 4;
+	sh->stage_off = sh->pos_off + 2 * tm.G * sh->wp * 4;  // positions: two halves
 }
 static bool slide_shape(const pgt_geom& g, pgt_mode mode, pgt_stat stat, SlideShape* sh) {
 	if (mode != PGT_MODE_SITES || g_tune_slide == 1) return false;
@@ -1779,12 +1835,12 @@ static bool slide_shape(const pgt_geom& g, pgt_mode mode, pgt_stat stat, SlideSh
 	if (g_tune_slide != 2) {
 		// auto: no piece of a step reaches a sector of doubles (units of < 32 sites) under windows of many
 		// units -- where level 2 would otherwise run its block scans over a unit array as large as the input
-		if (g.W < 256 || g.ueff >= 32 || g.wunits <= 32) return false;
+		if (g.ueff >= 32 || g.wunits <= 32) return false;
 	}
 	const size_t half = 113u * 1024u, full = 226u * 1024u;
 	// One rule for all statistics (the fused scan must equal the three single scans bit for bit): the block
 	// of the widest one -- fused, 41 B/site staged twice + two 40-byte accumulators per site -- has to fit,
-	// which bounds W at 1288 sites.
+	// which bounds W at 1048 sites.
 	slide_footprint(g, PGT_STAT_FUSED, sh);
 	if (sh->stage_off + 2 * (size_t)sh->stage_bytes > full) return false;
 	slide_footprint(g, stat, sh);
@@ -2232,24 +2288,32 @@ static int launch_slide(const pgt_plan* plan, pgt_stat stat, const DevPlan& P, c
 		tc.col_cap[c] = sh.col_cap[c];
 	}
 	void (*kern)(DevPlan, TileCfg, SlideCfg, pgt_windows);
-	if (sh.E <= 2) kern = k_slide<Stat, 2>;
-	else if (sh.E <= 4) kern = k_slide<Stat, 4>;
-	else kern = k_slide<Stat, 6>;
+	if (sh.G > 1) {
+		if (sh.E <= 2) kern = k_slide<Stat, 2, true>;
+		else if (sh.E <= 4) kern = k_slide<Stat, 4, true>;
+		else kern = k_slide<Stat, 6, true>;
+	} else {
+		if (sh.E <= 4) kern = k_slide<Stat, 4, false>;
+		else if (sh.E == 5) kern = k_slide<Stat, 5, false>;  // W = 1000
+		else kern = k_slide<Stat, 6, false>;
+	}
 	PGT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh.smem));
 	int per_sm = 0;
 	PGT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kSlideThreads, sh.smem));
 	if (per_sm < 1) per_sm = 1;
 	const uint64_t slots = (uint64_t)num_sms() * per_sm;
-	// chunks: ~4 per resident CTA for balance, but long enough (>= 32 blocks of windows) that the W - S sites
+	// chunks: ~4 per resident CTA for balance, but long enough (>= 32 steps of windows) that the W - S sites
 	// shared with the next chunk stay a few percent of what a chunk reads
-	const uint64_t wpb = (plan->g.W + plan->g.S - 1) / plan->g.S;  // windows starting in one block
+	const uint64_t wpb = ((uint64_t)sh.G * plan->g.W + plan->g.S - 1) / plan->g.S;  // windows starting in one step
 	SlideCfg sc;
 	memset(&sc, 0, sizeof(sc));
 	sc.E = sh.E;
+	sc.wpb = sh.wpb;
+	sc.G = sh.G;
+	sc.wp = sh.wp;
 	sc.sf_off = sh.sf_off;
 	sc.pr_off = sh.pr_off;
 	sc.pos_off = sh.pos_off;
-	sc.pos_stride = sh.pos_stride;
 	sc.pos_col = pos ? scol.n : 0xffffffffu;
 	sc.stage_off = sh.stage_off;
 	sc.chunk_windows = std::max<uint64_t>(32 * wpb, (nwin + slots * 4 - 1) / (slots * 4));

@@ -78,12 +78,12 @@ def check_fused(res, refs, tag):
 
 
 SHAPES = [(1, 1), (2, 1), (5, 2), (31, 1), (64, 64), (255, 7), (256, 1), (257, 3), (300, 299), (777, 13), (1000, 1), (1000, 7),
-          (1024, 32), (1279, 5), (1288, 1), (1288, 1288)]
+          (1024, 32), (1047, 5), (1048, 1), (1048, 1048), (129, 1), (192, 5), (500, 3), (700, 1)]
 
 
 @pytest.mark.parametrize("W,S", SHAPES)
 def test_sliding_tile_forced_on_every_shape_matches_the_oracle(pgt, W, S):
-    """pgt_tune slide=2 sends every site-mode geometry with W <= 1288 through k_slide: blocks shorter and
+    """pgt_tune slide=2 sends every site-mode geometry with W <= 1048 through k_slide: blocks shorter and
     longer than the consumer team, steps that do not divide the window, windows straddling two blocks, the
     cross-contig carry (first contig), trailing partial windows, contigs shorter than a window, EOF drop."""
     lengths = [W + 4 * S, 6011, 3, W // 2 + 1, 2 * W + 1, 4000, max(1, W - S)]
@@ -129,12 +129,13 @@ def test_sliding_tile_forced_on_every_shape_matches_the_oracle(pgt, W, S):
 
 
 def test_path_selection_is_a_function_of_the_geometry_only(pgt):
-    """auto: sliding tile iff no piece of a step reaches 32 sites (max(W % S, S - W % S) < 32) under windows of
-    256..1288 sites (the fused statistic's block must fit shared memory; one rule for all statistics) and more than 32 units."""
+    """auto: sliding tile iff no piece of a step reaches 32 sites (max(W % S, S - W % S) < 32) under windows of more
+    than 32 units and at most 1048 sites (the fused statistic's step must fit shared memory; one rule for all statistics)."""
     offs = offsets([50000, 7000])
-    want = {(1000, 1): "slide", (1000, 7): "slide", (1280, 16): "slide", (1288, 1): "slide", (1289, 1): "units", (1000, 31): "slide", (1000, 32): "slide",
-            (1010, 40): "slide",  # pieces of 10 and 30 sites
-            (1000, 40): "units", (1024, 32): "units", (1000, 100): "units", (255, 1): "units", (2048, 1): "units",
+    want = {(1000, 1): "slide", (1000, 7): "slide", (1040, 16): "slide", (1048, 1): "slide", (1049, 1): "units", (1000, 31): "slide",
+            (1000, 32): "slide", (1010, 40): "slide",  # pieces of 10 and 30 sites
+            (255, 1): "slide", (64, 1): "slide", (100, 3): "slide", (32, 1): "units",  # 32 one-site units: thread-per-window level 2
+            (1000, 40): "units", (1024, 32): "units", (1000, 100): "units", (2048, 1): "units",
             (50000, 10000): "units", (1, 1): "persite"}
     for (W, S), path in want.items():
         for stat in (_cabi.PGT_STAT_FST, _cabi.PGT_STAT_HET, _cabi.PGT_STAT_DXY, _cabi.PGT_STAT_FUSED):
@@ -147,7 +148,7 @@ def test_path_selection_is_a_function_of_the_geometry_only(pgt):
         pgt.tune("slide", 0)
 
 
-@pytest.mark.parametrize("W,S", [(1000, 1), (1000, 7), (1280, 2)])
+@pytest.mark.parametrize("W,S", [(1000, 1), (1000, 7), (300, 2)])
 def test_auto_path_against_oracle_and_against_the_unit_path(pgt, W, S):
     """Default knobs at the stress shape: the sliding tile is chosen, matches the oracle, agrees with the
     two-level unit path (slide=1) within the summation tolerance and exactly on everything integer, and

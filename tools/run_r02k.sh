@@ -1,0 +1,6 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout 1200 python -m pytest tests/test_slide_gpu.py tests/test_soak_gpu.py tests/test_guard_pages_gpu.py -m gpu -x -q > gpurun_out/r02k_tests.log 2>&1
+echo "tests rc=$?" >> gpurun_out/r02k_tests.log
+timeout 600 python tools/probe_bw.py fst,1e8,1000,1,0,0 fst,1e8,1000,7,0,0 fused,1e8,1000,1,0,0 het,1e8,1000,1,0,0 fst,1e8,256,1,0,0 fst,1e8,500,1,0,0 fst,1e8,100,1,0,0 > gpurun_out/r02k_probe.log 2>&1
+tail -n 5 gpurun_out/r02k_tests.log; cat gpurun_out/r02k_probe.log
