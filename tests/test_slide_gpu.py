@@ -227,3 +227,33 @@ def test_default_arguments_in_host_mode_need_no_unit_array(pgt):
     P.assert_exact(rd["dxy"], ref["dxy"], "per-site dxy (bit-exact: no FMA, dxyWindow.cpp:381)")
     assert rd["dxy_global"][1] == ref["global"][1] and rd["dxy_global"][2] == ref["global"][2]
     assert abs(rd["dxy_global"][0] - ref["global"][0]) <= 1e-9 * ref["global"][0]
+
+
+def test_host_mode_over_several_slabs_equals_device_mode(pgt):
+    """PGT_MEM_HOST stages 4 Mi-site slabs; sliding-tile scans go slab by slab over WINDOWS (neighbouring slabs share
+    W - S sites, the rows of a slab are copied back while the next one uploads).  9e6 sites = three slabs, several
+    contigs with the slab cuts falling inside them: the table must equal the device-mode table bit for bit, also
+    through pgt_scan_sharded with three shards."""
+    lengths = [5_000_003, 2_999_999, 17, 1_000_000]
+    offs = offsets(lengths)
+    d, h = columns(pgt, 14, offs)
+    for W, S in ((1000, 3), (200, 1)):
+        plan = pgt.WindowPlan(offs, W, S)
+        assert plan.scan_path(_cabi.PGT_STAT_FST) == "slide"
+        dev = npy(pgt.fst_window(plan, d["pos"], d["a"], d["b"]))
+        host = pgt.fst_window(plan, h["pos"], h["a"], h["b"])
+        for k in dev:
+            assert host[k].tobytes() == dev[k].tobytes(), (W, S, k)
+        plan_h = pgt.WindowPlan(offs, W, S)  # an unbound plan for the one-process multi-device call
+        sh = pgt.scan_sharded(plan_h, _cabi.PGT_STAT_FST, dict(pos=h["pos"], a=h["a"], b=h["b"]), [0, 0, 0])
+        for k in dev:
+            assert sh[k].tobytes() == dev[k].tobytes(), (W, S, k)
+    # dxy with the global line over the slabs (per-slab partial lines added in order)
+    plan = pgt.WindowPlan(offs, 1000, 3)
+    dd = npy(pgt.dxy_window(plan, d["pos"], d["f1"], d["f2"], d["n1"], d["n2"], minind=5))
+    hd = pgt.dxy_window(plan, h["pos"], h["f1"], h["f2"], h["n1"], h["n2"], minind=5)
+    for k in dd:
+        if k == "dxy_global":
+            assert hd[k][1] == dd[k][1] and hd[k][2] == dd[k][2] and abs(hd[k][0] - dd[k][0]) <= 1e-12 * dd[k][0]
+        else:
+            assert hd[k].tobytes() == dd[k].tobytes(), k
