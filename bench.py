@@ -102,9 +102,9 @@ def cli_arm(tmp, jobs, W, S):
         for j in jobs:
             with open(j[0], "rb") as r:
                 shutil.copyfileobj(r, w, 1 << 24)
-    best = None
+    best, walls = None, []
     ours_out = os.path.join(tmp, "ours.tsv")
-    for _ in range(2):  # second run = warm page cache + warm driver
+    for _ in range(3):  # best of three: CUDA start-up of a fresh process varies between 0.3 and 3.5 s on these boxes
         t0 = time.perf_counter()
         with open(ours_out, "wb") as fo:
             p = subprocess.run([exe, allp, str(W), str(S)], stdout=fo, stderr=subprocess.PIPE, text=True,
@@ -114,7 +114,10 @@ def cli_arm(tmp, jobs, W, S):
             return {"error": p.stderr[-200:]}
         t = json.loads(p.stderr.strip().splitlines()[-1])
         t["wall_s_incl_process_and_cuda_startup"] = round(wall, 3)
-        best = t
+        walls.append(round(wall, 3))
+        if best is None or wall < best["wall_s_incl_process_and_cuda_startup"]:
+            best = t
+    best["walls_s_all_runs"] = walls
     best["sites_per_s_parse_scan_format"] = round(best["sites"] / (best["total_ms"] * 1e-3), 1)
     # the same input as a binary columnar cache (PGT_PACK, csrc/tools/pgt_colfile.h): no text parsing at all
     try:
@@ -123,14 +126,15 @@ def cli_arm(tmp, jobs, W, S):
         subprocess.run([exe, allp, str(W), str(S)], check=True, env=dict(os.environ, PGT_PACK=cache))
         pack_s = time.perf_counter() - t0
         cache_out = os.path.join(tmp, "cache.tsv")
-        ct = None
-        for _ in range(2):
+        ct, cwall = None, None
+        for _ in range(3):
             t0 = time.perf_counter()
             with open(cache_out, "wb") as fo:
                 p = subprocess.run([exe, cache, str(W), str(S)], stdout=fo, stderr=subprocess.PIPE, text=True,
                                    env=dict(os.environ, PGT_TIMING="1"), check=True)
-            cwall = time.perf_counter() - t0
-            ct = json.loads(p.stderr.strip().splitlines()[-1])
+            w1 = time.perf_counter() - t0
+            if cwall is None or w1 < cwall:
+                cwall, ct = w1, json.loads(p.stderr.strip().splitlines()[-1])
         best["columnar_cache"] = {"pack_s": round(pack_s, 3), "file_bytes": os.path.getsize(cache), "load_ms": ct["parse_ms"],
                                   "scan_ms": ct["scan_ms"], "format_ms": ct["format_ms"], "total_ms": ct["total_ms"],
                                   "wall_s_incl_process_and_cuda_startup": round(cwall, 3),
