@@ -1,0 +1,324 @@
+// pgt_level2.cuh -- level 2: unit partials -> window rows.  Warp per window, thread per window for fine windows, the per-site map (W = S = 1), scan mode (block prefix / suffix scans)
+// Part of the one translation unit pgt_scan.cu (device code only; included from there, in this order:
+// pgt_kernels_common.cuh, pgt_level1.cuh, pgt_level2.cuh, pgt_slide.cuh).
+#ifndef PGT_LEVEL2_CUH
+#define PGT_LEVEL2_CUH
+
+// ----------------------------------------------------------------------------- level 2
+
+template <class Stat>
+__device__ __forceinline__ void emit_window(const DevPlan& P, const pgt_seg& sg, uint64_t w, uint64_t k, const typename Stat::Acc& acc,
+                                            const uint32_t* __restrict__ pos, const pgt_windows& out, bool have_edges = false,
+                                            uint32_t edge_start = 0, uint32_t edge_end = 0);
+
+// One warp per window: lane l adds unit partials l, l+32, ... (from +0.0, so a window of
+// -0.0 values sums to +0.0 exactly as the reference's `double asum = 0`), then the butterfly.
+// units_base = global index of units[0].
+template <class Stat>
+__global__ void __launch_bounds__(256) k_windows(DevPlan P, const typename Stat::Acc* __restrict__ units, uint64_t units_base,
+                                                  const uint32_t* __restrict__ pos, pgt_windows out) {
+	const uint32_t lane = threadIdx.x & 31u;
+	const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+	const uint64_t nwarp = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+	// The per-window work is a chain of dependent memory round trips; keep it short: the segment is
+	// cached (w only grows, so it changes a few dozen times per warp instead of costing a binary
+	// search in global memory per window), and lane 0 fetches the two edge positions BEFORE the
+	// partials are summed, so that gather overlaps the partial loads instead of following them.
+	// Every warp takes a contiguous run of windows, so the segment only ever moves forward by a step or
+	// two: one binary search per warp, then a walk (genomes of 1e5 contigs with W larger than the contigs
+	// paid a 17-probe search in L2 per window: 0.86 ms for 1e5 windows).
+	uint32_t si = 0xffffffffu;
+	pgt_seg sg;
+	sg.win_base = 0;
+	sg.nwin = 0;
+	const uint64_t nwin_all = P.win_hi - P.win_lo;
+	const uint64_t per = (nwin_all + nwarp - 1) / nwarp;
+	const uint64_t w_begin = P.win_lo + warp * per;
+	const uint64_t w_end = w_begin + per < P.win_hi ? w_begin + per : P.win_hi;
+	for (uint64_t w = w_begin; w < w_end; ++w) {
+		if (si == 0xffffffffu) {
+			si = find_seg<false>(P, w);
+			sg = P.segs[si];
+		}
+		while (w - sg.win_base >= sg.nwin) {  // also skips segments without windows
+			++si;
+			sg = P.segs[si];
+		}
+		const uint64_t k = w - sg.win_base;
+		uint64_t fu;
+		const uint64_t cnt = pgt_window_units(P.g, sg, k, &fu);
+		uint32_t sp = 0, ep = 0;
+		if (lane == 0 && pos && P.mode != PGT_MODE_BP) {
+			uint64_t fs;
+			const uint32_t nsites = pgt_window_sites(P.g, sg, k, &fs);
+			sp = __ldg(pos + (sg.site_base + fs - P.site_origin));
+			ep = __ldg(pos + (sg.site_base + fs + nsites - 1 - P.site_origin));
+		}
+		const typename Stat::Acc* up = units + (sg.unit_base + fu - units_base);
+		PGT_CHECK(sg.unit_base + fu >= P.unit_lo && sg.unit_base + fu + cnt <= P.unit_hi && w >= P.win_lo && w < P.win_hi);
+		typename Stat::Acc acc = Stat::zero();
+		for (uint64_t x = lane; x < cnt; x += 128u) {  // four partials per lane in flight; added in index order
+			typename Stat::Acc v[4];
+#pragma unroll
+			for (int q = 0; q < 4; ++q)
+				if (x + 32u * q < cnt) v[q] = up[x + 32u * q];
+#pragma unroll
+			for (int q = 0; q < 4; ++q)
+				if (x + 32u * q < cnt) Stat::add(acc, v[q]);
+		}
+		acc = warp_butterfly<Stat>(acc);
+		if (lane == 0) emit_window<Stat>(P, sg, w, k, acc, pos, out, true, sp, ep);
+	}
+}
+
+// Fine windows (<= 32 units each): one THREAD per window, outputs written coalesced.  The value is
+// bit-identical to k_windows: leaf i is (+0.0 + unit i) for i < cnt and +0.0 beyond, combined in
+// the butterfly's order V(i, s) = V(i, 2s) + V(i + s, 2s), evaluated depth-first so only log2(P2)
+// partials are live.
+template <class Stat, int P2, int S>
+struct SmallTree {
+	static __device__ __forceinline__ typename Stat::Acc eval(const typename Stat::Acc* __restrict__ up, uint32_t i, uint32_t cnt) {
+		typename Stat::Acc a = SmallTree<Stat, P2, S * 2>::eval(up, i, cnt);
+		if (i + S < cnt) Stat::add(a, SmallTree<Stat, P2, S * 2>::eval(up, i + S, cnt));  // adding the +0.0 subtree is the identity
+		return a;
+	}
+};
+template <class Stat, int P2>
+struct SmallTree<Stat, P2, P2> {
+	static __device__ __forceinline__ typename Stat::Acc eval(const typename Stat::Acc* __restrict__ up, uint32_t i, uint32_t cnt) {
+		typename Stat::Acc a = Stat::zero();
+		if (i < cnt) Stat::add(a, up[i]);
+		return a;
+	}
+};
+
+template <class Stat>
+__device__ __forceinline__ void emit_window(const DevPlan& P, const pgt_seg& sg, uint64_t w, uint64_t k, const typename Stat::Acc& acc,
+                                            const uint32_t* __restrict__ pos, const pgt_windows& out, bool have_edges, uint32_t edge_start,
+                                            uint32_t edge_end) {
+	const uint64_t o = w - P.win_lo;
+	uint64_t fs;
+	const uint32_t nsites = pgt_window_sites(P.g, sg, k, &fs);
+	const uint64_t first = sg.site_base + fs, last = first + nsites - 1;
+	const uint32_t label = find_contig(P.off, sg.first_contig, sg.ncontig, last);
+	if (out.label) out.label[o] = label;
+	if (out.nsites) out.nsites[o] = nsites;
+	uint32_t sp = 0, ep = 0;
+	bool have = false;
+	if (P.mode == PGT_MODE_BP) {
+		// dxyWindow.cpp:190 prints the bp position of the first / last buffer entry
+		const uint32_t cf = find_contig(P.off, sg.first_contig, sg.ncontig, first);
+		sp = (uint32_t)(first - P.off[cf]) + 1u;
+		ep = (uint32_t)(last - P.off[label]) + 1u;
+		have = true;
+	} else if (pos) {
+		PGT_CHECK(first >= P.site_origin && last - P.site_origin < P.col_elems);
+		sp = have_edges ? edge_start : __ldg(pos + (first - P.site_origin));  // the caller may have fetched them early
+		ep = have_edges ? edge_end : __ldg(pos + (last - P.site_origin));
+		have = true;
+	}
+	if (have) {
+		if (out.start_pos) out.start_pos[o] = sp;
+		if (out.end_pos) out.end_pos[o] = ep;
+		if (out.mid_pos) out.mid_pos[o] = (sp + ep) / 2u;  // uint32 arithmetic, fstWindow.cpp:73
+	}
+	Stat::emit(out, o, acc);
+}
+
+template <class Stat, int P2>
+__global__ void __launch_bounds__(256) k_windows_small(DevPlan P, const typename Stat::Acc* __restrict__ units, uint64_t units_base,
+                                                        const uint32_t* __restrict__ pos, pgt_windows out) {
+	const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+	uint32_t si = 0xffffffffu;
+	pgt_seg sg;
+	sg.win_base = 0;
+	sg.nwin = 0;
+	for (uint64_t w = P.win_lo + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; w < P.win_hi; w += stride) {
+		if (si == 0xffffffffu || w - sg.win_base >= sg.nwin) {
+			si = find_seg<false>(P, w);
+			sg = P.segs[si];
+		}
+		const uint64_t k = w - sg.win_base;
+		uint64_t fu;
+		const uint32_t cnt = (uint32_t)pgt_window_units(P.g, sg, k, &fu);
+		PGT_CHECK(cnt <= (uint32_t)P2 && sg.unit_base + fu >= P.unit_lo && sg.unit_base + fu + cnt <= P.unit_hi);
+		const typename Stat::Acc acc = SmallTree<Stat, P2, 1>::eval(units + (sg.unit_base + fu - units_base), 0u, cnt);
+		emit_window<Stat>(P, sg, w, k, acc, pos, out);
+	}
+}
+
+// W = S = 1 (the tools' default arguments): every window is one site, so the window table is an
+// elementwise map of the columns; level 1 is skipped and the per-site statistic is evaluated here.
+// Output-bound (36-76 bytes of rows per 1-41 bytes of site): a thread takes four windows per turn and issues
+// their column loads together before the first row is stored; the label comes from a cached contig range
+// instead of a binary search per window.
+template <class Stat>
+__global__ void __launch_bounds__(256) k_windows_persite(DevPlan P, Cols cols, pgt_windows out) {
+	constexpr int U = 4;
+	const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+	uint32_t si = 0xffffffffu;
+	pgt_seg sg;
+	sg.win_base = 0;
+	sg.nwin = 0;
+	uint32_t lc = 0;
+	uint64_t lc_lo = 1, lc_hi = 0;  // sites of contig lc: [lc_lo, lc_hi); empty = nothing cached
+	for (uint64_t w0 = P.win_lo + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; w0 < P.win_hi; w0 += U * stride) {
+		uint64_t site[U];
+		typename Stat::Site v[U];
+		uint32_t ps[U];
+#pragma unroll
+		for (int q = 0; q < U; ++q) {
+			const uint64_t w = w0 + q * stride;
+			site[q] = ~0ull;
+			if (w >= P.win_hi) continue;
+			if (si == 0xffffffffu || w - sg.win_base >= sg.nwin) {
+				si = find_seg<false>(P, w);
+				sg = P.segs[si];
+			}
+			site[q] = sg.site_base + (w - sg.win_base);  // window k of a segment is its site k
+		}
+#pragma unroll
+		for (int q = 0; q < U; ++q) {
+			if (site[q] == ~0ull) continue;
+			PGT_CHECK(site[q] >= P.site_origin && site[q] - P.site_origin < P.col_elems);
+			v[q] = Stat::load(cols, site[q] - P.site_origin);
+			ps[q] = cols.pos ? __ldg(cols.pos + (site[q] - P.site_origin)) : 0u;
+		}
+#pragma unroll
+		for (int q = 0; q < U; ++q) {
+			if (site[q] == ~0ull) continue;
+			const uint64_t o = w0 + q * stride - P.win_lo;
+			if (site[q] < lc_lo || site[q] >= lc_hi) {
+				lc = find_contig(P.off, 0, P.ncontig, site[q]);
+				lc_lo = P.off[lc];
+				lc_hi = P.off[lc + 1];
+			}
+			typename Stat::Acc acc = Stat::zero();
+			Stat::fold(acc, v[q], cols.minind);
+			if (out.label) out.label[o] = lc;
+			if (out.nsites) out.nsites[o] = 1u;
+			if (cols.pos) {
+				if (out.start_pos) out.start_pos[o] = ps[q];
+				if (out.end_pos) out.end_pos[o] = ps[q];
+				if (out.mid_pos) out.mid_pos[o] = (ps[q] + ps[q]) / 2u;  // uint32 arithmetic, fstWindow.cpp:73
+			}
+			Stat::emit(out, o, acc);
+		}
+	}
+}
+
+// ----------------------------------------------------------------------------- level 2, scan mode
+//
+// Fine steps with long windows (e.g. W = 1000, S = 1): summing W/S unit partials per window
+// would cost O(n * W / S^2).  Instead the unit array is cut into blocks of B = wunits units
+// (aligned to the segment's first unit), and an inclusive prefix scan PRE and suffix scan SUF are
+// taken inside every block.  A window covers at most two adjacent blocks, so
+//     window = SUF[first unit] + PRE[last unit]          (van Herk / Gil-Werman)
+// -- two reads per window, only additions of true partial sums (no subtraction, no cancellation).
+// Order inside a block: chunks of 256 units; warp shuffle scan, warp totals, running carry.
+
+template <class Acc>
+__device__ __forceinline__ Acc shfl_up_acc(const Acc& v, unsigned delta) {
+	static_assert(sizeof(Acc) % 4 == 0, "Acc is made of 32-bit words");
+	uint32_t w[sizeof(Acc) / 4];
+	memcpy(w, &v, sizeof(Acc));
+#pragma unroll
+	for (unsigned i = 0; i < sizeof(Acc) / 4; ++i) w[i] = __shfl_up_sync(0xffffffffu, w[i], delta);
+	Acc r;
+	memcpy(&r, w, sizeof(Acc));
+	return r;
+}
+
+// one direction of the block scan: items x0 + i (forward) or x1 - 1 - i (backward), i = 0..n-1
+template <class Stat, bool BACKWARD>
+__device__ __forceinline__ void cta_scan_dir(const typename Stat::Acc* __restrict__ in, typename Stat::Acc* __restrict__ outp, uint64_t x0, uint64_t x1,
+                                             typename Stat::Acc* s_wtot, typename Stat::Acc* s_carry) {
+	typedef typename Stat::Acc Acc;
+	const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+	const uint64_t n = x1 - x0;
+	if (threadIdx.x == 0) *s_carry = Stat::zero();
+	__syncthreads();
+	for (uint64_t base = 0; base < n; base += blockDim.x) {
+		const uint64_t i = base + threadIdx.x;
+		const bool ok = i < n;
+		const uint64_t idx = BACKWARD ? (x1 - 1 - i) : (x0 + i);
+		Acc v = Stat::zero();
+		if (ok) Stat::add(v, in[idx]);
+		// inclusive scan inside the warp
+#pragma unroll
+		for (unsigned d = 1; d < 32; d <<= 1) {
+			Acc o = shfl_up_acc(v, d);
+			if (lane >= d) {
+				Acc t = o;          // earlier items first: t = earlier + v
+				Stat::add(t, v);
+				v = t;
+			}
+		}
+		if (lane == 31) s_wtot[warp] = v;
+		__syncthreads();
+		Acc pre = *s_carry;  // everything before this chunk
+		for (uint32_t w = 0; w < warp; ++w) Stat::add(pre, s_wtot[w]);
+		Stat::add(pre, v);
+		if (ok) outp[idx] = pre;
+		__syncthreads();
+		if (threadIdx.x == blockDim.x - 1) *s_carry = pre;  // inclusive total through this chunk
+		__syncthreads();
+	}
+}
+
+template <class Stat>
+__global__ void __launch_bounds__(256) k_block_scan(DevPlan P, typename Stat::Acc* __restrict__ units, typename Stat::Acc* __restrict__ pre,
+                                                     uint64_t units_base, uint64_t blk_lo, uint64_t blk_hi) {
+	__shared__ typename Stat::Acc s_wtot[8];
+	__shared__ typename Stat::Acc s_carry;
+	const uint64_t B = P.g.wunits;
+	for (uint64_t gb = blk_lo + blockIdx.x; gb < blk_hi; gb += gridDim.x) {
+		const pgt_seg sg = P.segs[find_seg_by_block(P, gb)];
+		const uint64_t lb = gb - sg.blk_base;
+		uint64_t u0 = sg.unit_base + lb * B;
+		uint64_t u1 = sg.unit_base + ((lb + 1) * B < sg.nunits ? (lb + 1) * B : sg.nunits);
+		// clip to the units this scan computed (shards): see DESIGN.md, the clipped values are never used
+		if (u0 < P.unit_lo) u0 = P.unit_lo;
+		if (u1 > P.unit_hi) u1 = P.unit_hi;
+		if (u1 <= u0) continue;
+		PGT_CHECK(u0 >= units_base && u0 >= P.unit_lo && u1 <= P.unit_hi);
+		cta_scan_dir<Stat, false>(units, pre, u0 - units_base, u1 - units_base, s_wtot, &s_carry);  // PRE (reads raw units)
+		cta_scan_dir<Stat, true>(units, units, u0 - units_base, u1 - units_base, s_wtot, &s_carry);  // SUF in place
+	}
+}
+
+template <class Stat>
+__global__ void __launch_bounds__(256) k_windows_hgw(DevPlan P, const typename Stat::Acc* __restrict__ suf, const typename Stat::Acc* __restrict__ pre,
+                                                      uint64_t units_base, const uint32_t* __restrict__ pos, pgt_windows out) {
+	const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+	const uint64_t B = P.g.wunits;
+	uint32_t si = 0xffffffffu;
+	pgt_seg sg;
+	sg.win_base = 0;
+	sg.nwin = 0;
+	for (uint64_t w = P.win_lo + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; w < P.win_hi; w += stride) {
+		if (si == 0xffffffffu || w - sg.win_base >= sg.nwin) {
+			si = find_seg<false>(P, w);
+			sg = P.segs[si];
+		}
+		const uint64_t k = w - sg.win_base;
+		uint64_t fu;
+		const uint64_t cnt = pgt_window_units(P.g, sg, k, &fu);
+		const uint64_t lu = fu + cnt - 1;  // segment-local first / last unit
+		const uint64_t gf = sg.unit_base + fu - units_base, gl = sg.unit_base + lu - units_base;
+		PGT_CHECK(sg.unit_base + fu >= P.unit_lo && sg.unit_base + lu < P.unit_hi);
+		typename Stat::Acc acc = Stat::zero();
+		if (fu / B == lu / B) {
+			// inside one block: block-aligned start (PRE up to the last unit), or it runs to the block /
+			// segment end (SUF from the first unit)
+			if (fu % B == 0) Stat::add(acc, pre[gl]);
+			else Stat::add(acc, suf[gf]);
+		} else {
+			Stat::add(acc, suf[gf]);
+			Stat::add(acc, pre[gl]);
+		}
+		emit_window<Stat>(P, sg, w, k, acc, pos, out);
+	}
+}
+
+#endif  // PGT_LEVEL2_CUH

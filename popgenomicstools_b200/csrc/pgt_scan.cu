@@ -17,6 +17,12 @@
 //                              each unit's site range is found by binary search in `pos` (sparse,
 //                              O(#sites) instead of O(chromosome length)).
 //
+//   (fine)   k_slide<Stat>   : fine steps under long windows (W = 1000, S = 1): windows formed straight
+//                              from the sites in shared memory, no unit array (pgt_slide.cuh).
+//
+// Device code lives in pgt_kernels_common.cuh (plan, statistics), pgt_level1.cuh, pgt_level2.cuh and
+// pgt_slide.cuh, all included below into this one translation unit; this file holds the host side: layout of
+// the caller-owned workspace, kernel selection and launches, host-memory mode, the C ABI entry points.
 // There is no CPU fallback: every entry point fails with PGT_ERR_CUDA when no device is usable.
 #include <cuda_runtime.h>
 
@@ -213,1532 +219,10 @@ static int num_sms() {
 
 static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
-// -DPGT_BOUNDS (make -C csrc bounds -> libpgtscan_bounds.so): every index a kernel forms from the plan is checked
-// against the extent it must stay in -- column slices against the elements the caller's columns hold, positions
-// inside a shared-memory stage against the staged slice, unit / window / block indices against this launch's ranges
-// -- and a violation traps (the launch fails with an error instead of reading or writing out of bounds).  The GPU
-// test-suite is run against this build with PGT_LIB=.../libpgtscan_bounds.so (tools/run_bounds_gpu.sh).
-#ifdef PGT_BOUNDS
-#define PGT_CHECK(cond)                                                                             \
-	do {                                                                                            \
-		if (!(cond)) {                                                                              \
-			printf("PGT_BOUNDS violated at %s:%d: %s\n", __FILE__, __LINE__, #cond);                \
-			__trap();                                                                               \
-		}                                                                                           \
-	} while (0)
-#else
-#define PGT_CHECK(cond) ((void)0)
-#endif
-
-// ----------------------------------------------------------------------------- device plan
-
-struct Cols {
-	const uint32_t* pos;
-	const double* a;
-	const double* b;
-	const int8_t* g;
-	const double* f1;
-	const double* f2;
-	const int32_t* n1;
-	const int32_t* n2;
-	int minind;
-};
-
-struct DevPlan {
-	pgt_geom g;
-	const pgt_seg* segs;
-	const uint64_t* off;       // contig offsets on the plan axis (sites, or bp entries)
-	const uint64_t* site_off;  // bp mode: cumulative site counts per chromosome (global site indices)
-	uint32_t nseg;
-	uint32_t ncontig;
-	uint64_t unit_lo, unit_hi;  // global unit range reduced by this launch
-	uint64_t win_lo, win_hi;    // global window range of this scan
-	uint64_t site_origin;       // global index of element 0 of the columns
-	uint64_t nunits_total;
-	uint64_t col_elems;         // elements the columns hold from element 0 (PGT_BOUNDS checks; ~0 = unknown)
-	int mode;
-};
-
-// last segment with key <= x, key = unit_base (BY_UNIT) or win_base
-template <bool BY_UNIT>
-__device__ __forceinline__ uint32_t find_seg(const DevPlan& P, uint64_t x) {
-	uint32_t lo = 0, hi = P.nseg;
-	while (hi - lo > 1) {
-		uint32_t mid = lo + ((hi - lo) >> 1);
-		uint64_t key = BY_UNIT ? P.segs[mid].unit_base : P.segs[mid].win_base;
-		if (key <= x) lo = mid;
-		else hi = mid;
-	}
-	return lo;
-}
-// last segment with blk_base <= x AND at least one scan block
-__device__ __forceinline__ uint32_t find_seg_by_block(const DevPlan& P, uint64_t x) {
-	uint32_t lo = 0, hi = P.nseg;
-	while (hi - lo > 1) {
-		uint32_t mid = lo + ((hi - lo) >> 1);
-		if (P.segs[mid].blk_base <= x) lo = mid;
-		else hi = mid;
-	}
-	return lo;
-}
-
-// contig c in [c0, c0+nc) with off[c] <= x < off[c+1]
-__device__ __forceinline__ uint32_t find_contig(const uint64_t* off, uint32_t c0, uint32_t nc, uint64_t x) {
-	uint32_t lo = c0, hi = c0 + nc;
-	while (hi - lo > 1) {
-		uint32_t mid = lo + ((hi - lo) >> 1);
-		if (off[mid] <= x) lo = mid;
-		else hi = mid;
-	}
-	return lo;
-}
-
-__device__ __forceinline__ double shfl_xor_f64(double v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }
-__device__ __forceinline__ uint32_t shfl_xor_u32(uint32_t v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }
-
-// ----------------------------------------------------------------------------- statistics
-//
-// A Stat describes: the per-site record loaded from the columns (Site), the unit partial (Acc,
-// stored as-is in the unit array), how one site is folded into a lane's partial (the per-site
-// statistic), the combine used by the butterflies, and the window epilogue.
-
-// --- fstWindow: asum += a; bsum += b (fstWindow.cpp:80-83); fst = bsum != 0 ? asum/bsum : 0 (:85)
-struct FstStat {
-	struct Acc {
-		double a, b;
-	};
-	struct Site {
-		double a, b;
-	};
-	static __device__ __forceinline__ Acc zero() { return Acc{0.0, 0.0}; }
-	static __device__ __forceinline__ Site load(const Cols& c, uint64_t i) { return Site{__ldg(c.a + i), __ldg(c.b + i)}; }
-	// tile columns in staging order (a, b); generic loads: the tile lives in shared memory
-	static __device__ __forceinline__ Site load_tile(const char* const* cp, uint32_t i) {
-		return Site{((const double*)cp[0])[i], ((const double*)cp[1])[i]};
-	}
-	static __device__ __forceinline__ void fold(Acc& acc, const Site& s, int) {
-		acc.a = __dadd_rn(acc.a, s.a);
-		acc.b = __dadd_rn(acc.b, s.b);
-	}
-	static __device__ __forceinline__ void add(Acc& acc, const Acc& o) {
-		acc.a = __dadd_rn(acc.a, o.a);
-		acc.b = __dadd_rn(acc.b, o.b);
-	}
-	static __device__ __forceinline__ Acc shfl_xor(const Acc& v, int m) { return Acc{shfl_xor_f64(v.a, m), shfl_xor_f64(v.b, m)}; }
-	static __device__ __forceinline__ void emit(const pgt_windows& out, uint64_t o, const Acc& acc) {
-		if (out.sum_a) out.sum_a[o] = acc.a;
-		if (out.sum_b) out.sum_b[o] = acc.b;
-		if (out.fst) out.fst[o] = acc.b != 0.0 ? __ddiv_rn(acc.a, acc.b) : 0.0;
-	}
-};
-
-// --- hetWindow: nonmissing += (g >= 0); nhet += (g == 1) (hetWindow.cpp:77-82); h = nhet/nonmissing (:84)
-struct HetStat {
-	struct Acc {
-		uint32_t nonmissing, nhet;
-	};
-	struct Site {
-		int g;
-	};
-	static __device__ __forceinline__ Acc zero() { return Acc{0u, 0u}; }
-	static __device__ __forceinline__ Site load(const Cols& c, uint64_t i) { return Site{(int)__ldg(c.g + i)}; }
-	static __device__ __forceinline__ Site load_tile(const char* const* cp, uint32_t i) { return Site{(int)((const int8_t*)cp[0])[i]}; }
-	static __device__ __forceinline__ void fold(Acc& acc, const Site& s, int) {
-		acc.nonmissing += (s.g >= 0);
-		acc.nhet += (s.g == 1);
-	}
-	static __device__ __forceinline__ void add(Acc& acc, const Acc& o) {
-		acc.nonmissing += o.nonmissing;
-		acc.nhet += o.nhet;
-	}
-	static __device__ __forceinline__ Acc shfl_xor(const Acc& v, int m) { return Acc{shfl_xor_u32(v.nonmissing, m), shfl_xor_u32(v.nhet, m)}; }
-	static __device__ __forceinline__ void emit(const pgt_windows& out, uint64_t o, const Acc& acc) {
-		if (out.nhet) out.nhet[o] = acc.nhet;
-		if (out.nonmissing) out.nonmissing[o] = acc.nonmissing;
-		if (out.het) out.het[o] = acc.nonmissing != 0 ? __ddiv_rn((double)acc.nhet, (double)acc.nonmissing) : 0.0;
-	}
-};
-
-// --- dxyWindow: per-site dxy (dxyWindow.cpp:381) with explicit non-fused IEEE ops so the value is
-// bit-identical to the x86-64 reference (no FMA there); window fold dxyWindow.cpp:179-186:
-// v >= 0 -> dxy += v, ++neffective; v == -9 -> ++nskip.
-__device__ __forceinline__ double dxy_site_value(double f1, double f2, int n1, int n2, int minind) {
-	return (n1 >= minind && n2 >= minind) ? __dadd_rn(__dmul_rn(f1, __dsub_rn(1.0, f2)), __dmul_rn(f2, __dsub_rn(1.0, f1))) : -9.0;
-}
-struct DxyStat {
-	struct Acc {
-		double dxy;
-		uint32_t neff, nskip;
-	};
-	struct Site {
-		double f1, f2;
-		int n1, n2;
-	};
-	static __device__ __forceinline__ Acc zero() { return Acc{0.0, 0u, 0u}; }
-	static __device__ __forceinline__ Site load(const Cols& c, uint64_t i) {
-		return Site{__ldg(c.f1 + i), __ldg(c.f2 + i), __ldg(c.n1 + i), __ldg(c.n2 + i)};
-	}
-	static __device__ __forceinline__ Site load_tile(const char* const* cp, uint32_t i) {
-		return Site{((const double*)cp[0])[i], ((const double*)cp[1])[i], ((const int32_t*)cp[2])[i], ((const int32_t*)cp[3])[i]};
-	}
-	static __device__ __forceinline__ void fold(Acc& acc, const Site& s, int minind) {
-		const double v = dxy_site_value(s.f1, s.f2, s.n1, s.n2, minind);
-		if (v >= 0.0) {
-			acc.dxy = __dadd_rn(acc.dxy, v);
-			++acc.neff;
-		} else if (v == -9.0) {
-			++acc.nskip;
-		}
-	}
-	static __device__ __forceinline__ void add(Acc& acc, const Acc& o) {
-		acc.dxy = __dadd_rn(acc.dxy, o.dxy);
-		acc.neff += o.neff;
-		acc.nskip += o.nskip;
-	}
-	static __device__ __forceinline__ Acc shfl_xor(const Acc& v, int m) {
-		return Acc{shfl_xor_f64(v.dxy, m), shfl_xor_u32(v.neff, m), shfl_xor_u32(v.nskip, m)};
-	}
-	static __device__ __forceinline__ void emit(const pgt_windows& out, uint64_t o, const Acc& acc) {
-		if (out.dxy) out.dxy[o] = acc.dxy;
-		if (out.neffective) out.neffective[o] = acc.neff;
-		if (out.nskip) out.nskip[o] = acc.nskip;
-	}
-};
-
-// --- fused fst + dxy + het over one site axis (BASELINE config 5): one pass, 41 B/site
-struct FusedStat {
-	struct Acc {
-		FstStat::Acc fst;
-		DxyStat::Acc dxy;
-		HetStat::Acc het;
-	};
-	struct Site {
-		FstStat::Site fst;
-		DxyStat::Site dxy;
-		HetStat::Site het;
-	};
-	static __device__ __forceinline__ Acc zero() { return Acc{FstStat::zero(), DxyStat::zero(), HetStat::zero()}; }
-	static __device__ __forceinline__ Site load(const Cols& c, uint64_t i) { return Site{FstStat::load(c, i), DxyStat::load(c, i), HetStat::load(c, i)}; }
-	// staging order: a, b, f1, f2, n1, n2, geno
-	static __device__ __forceinline__ Site load_tile(const char* const* cp, uint32_t i) {
-		return Site{FstStat::load_tile(cp, i), DxyStat::load_tile(cp + 2, i), HetStat::load_tile(cp + 6, i)};
-	}
-	static __device__ __forceinline__ void fold(Acc& acc, const Site& s, int minind) {
-		FstStat::fold(acc.fst, s.fst, minind);
-		DxyStat::fold(acc.dxy, s.dxy, minind);
-		HetStat::fold(acc.het, s.het, minind);
-	}
-	static __device__ __forceinline__ void add(Acc& acc, const Acc& o) {
-		FstStat::add(acc.fst, o.fst);
-		DxyStat::add(acc.dxy, o.dxy);
-		HetStat::add(acc.het, o.het);
-	}
-	static __device__ __forceinline__ Acc shfl_xor(const Acc& v, int m) {
-		return Acc{FstStat::shfl_xor(v.fst, m), DxyStat::shfl_xor(v.dxy, m), HetStat::shfl_xor(v.het, m)};
-	}
-	static __device__ __forceinline__ void emit(const pgt_windows& out, uint64_t o, const Acc& acc) {
-		FstStat::emit(out, o, acc.fst);
-		DxyStat::emit(out, o, acc.dxy);
-		HetStat::emit(out, o, acc.het);
-	}
-};
-
-template <class Stat>
-__device__ __forceinline__ typename Stat::Acc warp_butterfly(typename Stat::Acc acc) {
-#pragma unroll
-	for (int m = 16; m >= 1; m >>= 1) Stat::add(acc, Stat::shfl_xor(acc, m));
-	return acc;
-}
-// butterfly inside aligned groups of G lanes
-template <class Stat, int G>
-__device__ __forceinline__ typename Stat::Acc group_butterfly(typename Stat::Acc acc) {
-#pragma unroll
-	for (int m = G / 2; m >= 1; m >>= 1) Stat::add(acc, Stat::shfl_xor(acc, m));
-	return acc;
-}
-
-// ----------------------------------------------------------------------------- level 1
-
-// One warp per unit, persistent grid-stride over the launch's unit range.  Lane l folds sites
-// l, l+32, l+64, ... of the unit in that order (all loads of a unit are issued before the first
-// fold: UPL independent loads per column per lane in flight), then the butterfly.
-// INDIRECT (bp mode): the unit's site range comes from `bounds` instead of the closed form.
-template <class Stat, int UPL, bool INDIRECT>
-__global__ void __launch_bounds__(256) k_units(DevPlan P, Cols cols, typename Stat::Acc* __restrict__ units, const uint64_t* __restrict__ bounds) {
-	const uint32_t lane = threadIdx.x & 31u;
-	const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-	const uint64_t nwarp = ((uint64_t)gridDim.x * blockDim.x) >> 5;
-	uint32_t si = 0xffffffffu;
-	pgt_seg sg;
-	sg.unit_base = 0;
-	sg.nunits = 0;
-	for (uint64_t j = P.unit_lo + warp; j < P.unit_hi; j += nwarp) {
-		uint64_t i0;
-		uint32_t len;
-		if (INDIRECT) {
-			const uint64_t b0 = bounds[j - P.unit_lo], b1 = bounds[j - P.unit_lo + 1];
-			i0 = b0 + lane;
-			len = (uint32_t)(b1 - b0);
-		} else {
-			if (si == 0xffffffffu || j - sg.unit_base >= sg.nunits) {
-				si = find_seg<true>(P, j);
-				sg = P.segs[si];
-			}
-			uint64_t st;
-			len = pgt_unit_range(P.g, sg.nsites, j - sg.unit_base, &st);
-			i0 = sg.site_base + st - P.site_origin + lane;
-		}
-		PGT_CHECK(len == 0 || (i0 - lane) + len <= P.col_elems);
-		typename Stat::Acc acc = Stat::zero();
-		if (UPL > 0 && len <= 32u * UPL) {
-			typename Stat::Site v[UPL > 0 ? UPL : 1];
-#pragma unroll
-			for (int t = 0; t < UPL; ++t)
-				if (lane + 32u * t < len) v[t] = Stat::load(cols, i0 + 32u * t);
-#pragma unroll
-			for (int t = 0; t < UPL; ++t)
-				if (lane + 32u * t < len) Stat::fold(acc, v[t], cols.minind);
-		} else {
-			for (uint32_t x = lane; x < len; x += 32u) Stat::fold(acc, Stat::load(cols, i0 + (x - lane)), cols.minind);
-		}
-		acc = warp_butterfly<Stat>(acc);
-		if (lane == 0) units[j - P.unit_lo] = acc;
-	}
-}
-
-// ----------------------------------------------------------------------------- level 1, tiled
-//
-// Persistent CTAs (one per SM) walk tiles of `m` consecutive units.  Warp 0 is the producer: it
-// stages the tile's slice of every column in shared memory with 1-D bulk async copies
-// (cp.async.bulk -> UBLKCP, completion on an mbarrier), two stages deep, so the bytes in flight
-// per SM are one whole tile (64-96 KB) and cost no registers.  Warps 1..15 are consumers: groups
-// of G lanes reduce one unit each straight from shared memory (lane g of a group folds sites
-// g, g+G, g+2G, ... in that order, then a log2(G)-level butterfly), so the summation order is the
-// same function of (W, S, u) as in k_units and does not depend on tiles, CTAs or shards.  G is
-// small when units are short (pgt_geom.gw), which keeps all lanes busy for fine windows.
-// Only the 16-byte-aligned interior of a slice is bulk-copied; the <16-byte head and tail are
-// copied by the producer's lanes, so nothing outside [column, column + n) is ever read.
-
-static constexpr int kTileThreads = 512;
-static constexpr int kTileMaxStages = 4;
-static constexpr int kTileConsumerWarps = kTileThreads / 32 - 1;
-static constexpr int kMaxTileCols = 7;  // of a statistic; the sliding tile stages `pos` as one more (kMaxStageCols)
-static constexpr int kMaxStageCols = kMaxTileCols + 1;
-static constexpr uint32_t kTileCtlBytes = 384;  // >= sizeof(TileCtl) = 368
-
-
-// With more segments than this the tiled kernel gets a precomputed tile -> segment table: a CTA's
-// consecutive tiles lie gridDim * m units apart, i.e. in different segments once contigs are shorter
-// than ~1e6 sites, and the producer then paid two binary searches over the segment table per tile
-// (measured: 1e3 contigs 5.5 TB/s, 1e5 contigs 2.6 TB/s, against 7.0 TB/s for 24 contigs).
-static constexpr size_t kTileSegTableMin = 32;
-
-struct TileCfg {
-	const uint32_t* tile_seg;  // [ntiles] segment of each tile's first unit, or NULL (few segments / bp mode)
-	const char* gcol[kMaxStageCols];  // global column pointers (element 0 = site_origin), staging order
-	uint32_t elem[kMaxStageCols];     // bytes per site
-	uint32_t col_off[kMaxStageCols];  // byte offset of the column's region inside a stage
-	uint32_t col_cap[kMaxStageCols];  // capacity of that region in bytes
-	uint32_t ncol;
-	uint32_t m;            // units per tile
-	uint32_t stage_bytes;
-	uint32_t nstages;      // 2..kTileMaxStages
-	int minind;
-	uint64_t valid_elems;  // elements every column holds from element 0 (bounds the aligned superset copies)
-};
-
-struct TileCtl {
-	uint64_t full[kTileMaxStages];
-	uint64_t empty[kTileMaxStages];
-	uint64_t s0[kTileMaxStages];                   // column element index of the tile's first site
-	uint32_t ns[kTileMaxStages];                   // elements staged (PGT_BOUNDS checks)
-	const char* cp[kTileMaxStages][kMaxStageCols];  // where site s0 of each column lives (shared, or global if unstaged)
-};
-static_assert(sizeof(TileCtl) <= kTileCtlBytes, "control block");
-
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-	asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-	asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
-	asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-	asm volatile(
-	    "{\n"
-	    ".reg .pred P1;\n"
-	    "LAB_WAIT:\n"
-	    "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
-	    "@P1 bra DONE;\n"
-	    "bra LAB_WAIT;\n"
-	    "DONE:\n"
-	    "}\n" ::"r"(smem_u32(bar)),
-	    "r"(parity)
-	    : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
-	asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)), "l"(src),
-	             "r"(bytes), "r"(smem_u32(bar))
-	             : "memory");
-}
-
-// Producer side of a stage (all 32 lanes of the producer warp; the caller has waited for the stage to
-// drain): lane c stages elements [s0, s1) of column c.  The bulk copy covers the 16-byte-aligned SUPERSET
-// of the slice whenever that stays inside the column (always, except at the first/last elements of a
-// column that is not 16-byte aligned/padded); only then are head/tail bytes copied by hand, so nothing
-// outside [column, column + valid_elems) is ever read.
-__device__ __forceinline__ void producer_fill_stage(const TileCfg& tc, TileCtl* ctl, unsigned char* stages, uint32_t stg, uint64_t s0,
-                                                    uint64_t s1, uint32_t lane) {
-	PGT_CHECK(s0 <= s1 && s1 <= tc.valid_elems && stg < tc.nstages);
-	// generic-proxy reads of this stage are done; order them before the async-proxy writes
-	asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-	unsigned char* stage = stages + (size_t)stg * tc.stage_bytes;
-	const uint32_t c = lane < tc.ncol ? lane : 0u;
-	const char* A = tc.gcol[c] + s0 * tc.elem[c];
-	const uint64_t nbytes = (s1 - s0) * tc.elem[c];
-	const uint32_t pad = (uint32_t)((uintptr_t)A & 15u);
-	const bool staged = lane < tc.ncol && pad + nbytes + 16u <= tc.col_cap[c];
-	unsigned char* region = stage + tc.col_off[c];
-	const char* col_lo = tc.gcol[c];
-	const char* col_hi = tc.gcol[c] + tc.valid_elems * tc.elem[c];
-	const char* B0 = A - pad;  // aligned superset [B0, B1)
-	const char* B1 = (const char*)(((uintptr_t)(A + nbytes) + 15u) & ~(uintptr_t)15u);
-	uint32_t nh = 0, ntl = 0;
-	if (B0 < col_lo) {  // cannot read before the column: copy the head by hand
-		B0 += 16;
-		nh = 16u - pad;
-		if (nh > nbytes) nh = (uint32_t)nbytes;
-	}
-	if (B1 > col_hi) {  // cannot read past the column: copy the tail by hand
-		B1 -= 16;
-		ntl = (uint32_t)((A + nbytes) - B1);
-		if (B1 < A + nh) ntl = (uint32_t)(nbytes - nh);
-	}
-	uint32_t tx = (staged && B1 > B0) ? (uint32_t)(B1 - B0) : 0u;
-	if (lane < tc.ncol) ctl->cp[stg][c] = staged ? (const char*)(region + pad) : A;
-	uint32_t txsum = tx;
-#pragma unroll
-	for (int m = 16; m >= 1; m >>= 1) txsum += __shfl_xor_sync(0xffffffffu, txsum, m);
-	PGT_CHECK(!tx || (B0 >= col_lo && B1 <= col_hi && (uint32_t)(pad + (B0 - A)) + tx <= tc.col_cap[c] && tc.col_off[c] + tc.col_cap[c] <= tc.stage_bytes));
-	if (lane == 0) {
-		ctl->s0[stg] = s0;
-		ctl->ns[stg] = (uint32_t)(s1 - s0);
-		mbar_arrive_expect_tx(&ctl->full[stg], txsum);
-	}
-	__syncwarp();
-	if (tx) bulk_g2s(region + pad + (B0 - A), B0, tx, &ctl->full[stg]);
-	// rare: hand-copied head / tail bytes
-	const uint32_t any = __ballot_sync(0xffffffffu, staged && (nh | ntl));
-	for (uint32_t cc = 0; cc < tc.ncol; ++cc) {
-		if (!((any >> cc) & 1u)) continue;
-		const uint32_t nh_c = __shfl_sync(0xffffffffu, nh, cc), nt_c = __shfl_sync(0xffffffffu, ntl, cc);
-		const uint32_t pad_c = __shfl_sync(0xffffffffu, pad, cc);
-		const unsigned long long A_c = __shfl_sync(0xffffffffu, (unsigned long long)(uintptr_t)A, cc);
-		const unsigned long long nb_c = __shfl_sync(0xffffffffu, (unsigned long long)nbytes, cc);
-		unsigned char* reg_c = stage + tc.col_off[cc];
-		const unsigned char* Ac = (const unsigned char*)(uintptr_t)A_c;
-		if (lane < nh_c) reg_c[pad_c + lane] = __ldg(Ac + lane);
-		if (lane < nt_c) reg_c[pad_c + (uint32_t)(nb_c - nt_c) + lane] = __ldg(Ac + (nb_c - nt_c) + lane);
-	}
-	__syncwarp();
-	if (lane == 0) mbar_arrive(&ctl->full[stg]);  // control words (and any head/tail bytes) are in place
-}
-
-// global site (entry) index where global unit j starts / ends
-__device__ __forceinline__ uint64_t unit_bounds_global(const DevPlan& P, uint64_t j, uint64_t* end) {
-	const pgt_seg sg = P.segs[find_seg<true>(P, j)];
-	uint64_t st;
-	const uint32_t len = pgt_unit_range(P.g, sg.nsites, j - sg.unit_base, &st);
-	*end = sg.site_base + st + len;
-	return sg.site_base + st;
-}
-
-__global__ void __launch_bounds__(256) k_tile_segs(DevPlan P, uint32_t m, uint64_t ntiles, uint32_t* __restrict__ tile_seg) {
-	const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-	if (t < ntiles) tile_seg[t] = find_seg<true>(P, P.unit_lo + t * m);
-}
-
-// hetWindow's 1-byte genotype column inside the tiled kernel: a warp reduces one unit from the staged tile
-// with 16-byte loads + byte-SIMD compare / popc (the generic per-site loop would need one load per byte).
-// The staged copy keeps the column's alignment modulo 16, so the aligned chunks are the same in shared
-// memory and -- for a slice that was too long to stage -- in global memory (generic loads serve both).
-// Integer counts: independent of the order, identical to the per-site fold.
-// Four genotypes per word.  Both tests end in a word with 0x80 in every byte that counts, and an unsigned
-// dp4a against 0x01010101 adds 128 per such byte: the accumulators hold 128 x count (shifted down once per
-// unit; a lane sees < 2^25 bytes of a unit).  ~7 integer instructions per word and no POPC, which runs at a
-// quarter of the integer rate (the POPC / __vcmpeq4 version needed 13 and was issue-bound at 4.5 TB/s).
-__device__ __forceinline__ void het_count_word(uint32_t w, uint32_t& nonmissing128, uint32_t& nhet128) {
-	nonmissing128 = __dp4a(~w & 0x80808080u, 0x01010101u, nonmissing128);  // g >= 0  (hetWindow.cpp:78): sign bit clear
-	const uint32_t x = w ^ 0x01010101u;                                     // g == 1  (hetWindow.cpp:80): byte of x is zero
-	const uint32_t t = (x & 0x7f7f7f7fu) + 0x7f7f7f7fu;                     // bit 7 of t | x is set iff the byte of x is not zero
-	nhet128 = __dp4a(~(t | x) & 0x80808080u, 0x01010101u, nhet128);
-}
-__device__ __forceinline__ void het_unit_from_tile(HetStat::Acc& acc, const char* col, uint32_t rel, uint32_t len, uint32_t lane) {
-	const int8_t* A = (const int8_t*)col + rel;
-	const int8_t* E = A + len;
-	const int8_t* A0 = (const int8_t*)(((uintptr_t)A + 15u) & ~(uintptr_t)15u);  // first aligned chunk inside
-	const int8_t* A1 = (const int8_t*)((uintptr_t)E & ~(uintptr_t)15u);          // end of the last aligned chunk
-	uint32_t nonmissing = 0, nhet = 0;
-	if (A1 > A0) {
-		const uint32_t nch = (uint32_t)(A1 - A0) >> 4;
-		uint32_t nm128 = 0, h128 = 0;
-		for (uint32_t c = lane; c < nch; c += 32u) {
-			const uint4 v = *(reinterpret_cast<const uint4*>(A0) + c);
-			het_count_word(v.x, nm128, h128);
-			het_count_word(v.y, nm128, h128);
-			het_count_word(v.z, nm128, h128);
-			het_count_word(v.w, nm128, h128);
-		}
-		nonmissing = nm128 >> 7;
-		nhet = h128 >> 7;
-		const uint32_t nh = (uint32_t)(A0 - A), nt = (uint32_t)(E - A1);  // < 16 each
-		if (lane < nh) {
-			const int g = A[lane];
-			nonmissing += (g >= 0);
-			nhet += (g == 1);
-		}
-		if (lane >= 16u && lane - 16u < nt) {
-			const int g = A1[lane - 16u];
-			nonmissing += (g >= 0);
-			nhet += (g == 1);
-		}
-	} else {
-		for (uint32_t x = lane; x < len; x += 32u) {  // < 32 bytes without an aligned chunk
-			const int g = A[x];
-			nonmissing += (g >= 0);
-			nhet += (g == 1);
-		}
-	}
-	acc.nonmissing += nonmissing;
-	acc.nhet += nhet;
-}
-
-template <class Stat, int G, bool INDIRECT>
-__global__ void __launch_bounds__(kTileThreads, 1)
-    k_units_tiled(DevPlan P, TileCfg tc, typename Stat::Acc* __restrict__ units, const uint64_t* __restrict__ bounds) {
-	extern __shared__ __align__(128) unsigned char smem[];
-	TileCtl* ctl = reinterpret_cast<TileCtl*>(smem);
-	unsigned char* stages = smem + kTileCtlBytes;
-	const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
-	const uint64_t nunits = P.unit_hi - P.unit_lo;
-	const uint64_t ntiles = (nunits + tc.m - 1) / tc.m;
-
-	if (threadIdx.x == 0) {
-		for (uint32_t s = 0; s < tc.nstages; ++s) {
-			mbar_init(&ctl->full[s], 2);
-			mbar_init(&ctl->empty[s], kTileConsumerWarps);
-		}
-		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-	}
-	__syncthreads();
-
-	if (warp == 0) {
-		// ------------------------------------------------------------------ producer
-		// lane c stages column c: the bulk copy covers the 16-byte-aligned SUPERSET of the slice
-		// whenever that stays inside the column (always, except at the first/last elements of a
-		// column that is not 16-byte aligned/padded); only then are head/tail bytes copied by hand.
-		uint32_t it = 0;
-		uint32_t psi = 0xffffffffu;  // cached segment of the producer
-		pgt_seg psg;
-		psg.unit_base = 0;
-		psg.nunits = 0;
-		auto unit_span = [&](uint64_t j, uint64_t* end) -> uint64_t {  // global [start, end) of unit j
-			if (psi == 0xffffffffu || j - psg.unit_base >= psg.nunits) {
-				if (tc.tile_seg && psi != 0xffffffffu && j >= psg.unit_base) {
-					do {  // forward from the tile's first segment (set from the table below)
-						++psi;
-						psg = P.segs[psi];
-					} while (j - psg.unit_base >= psg.nunits);
-				} else {
-					psi = find_seg<true>(P, j);
-					psg = P.segs[psi];
-				}
-			}
-			uint64_t st;
-			const uint32_t len = pgt_unit_range(P.g, psg.nsites, j - psg.unit_base, &st);
-			*end = psg.site_base + st + len;
-			return psg.site_base + st;
-		};
-		for (uint64_t t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
-			const uint32_t stg = it % tc.nstages;
-			// the tile's element range is computed BEFORE waiting for the stage to drain
-			const uint64_t j0 = P.unit_lo + t * tc.m;
-			const uint64_t j1 = (P.unit_hi - j0 < tc.m) ? P.unit_hi : j0 + tc.m;
-			uint64_t s0, s1;  // element range of the tile in the columns
-			if (INDIRECT) {
-				s0 = bounds[j0 - P.unit_lo];
-				s1 = bounds[j1 - P.unit_lo];
-			} else {
-				uint64_t e;
-				if (tc.tile_seg) {
-					const uint32_t ts = tc.tile_seg[t];
-					if (ts != psi) {
-						psi = ts;
-						psg = P.segs[psi];
-					}
-				}
-				s0 = unit_span(j0, &e) - P.site_origin;
-				unit_span(j1 - 1, &e);
-				s1 = e - P.site_origin;
-			}
-			if (it >= tc.nstages) mbar_wait(&ctl->empty[stg], ((it / tc.nstages) - 1u) & 1u);
-			producer_fill_stage(tc, ctl, stages, stg, s0, s1, lane);
-		}
-	} else {
-		// ------------------------------------------------------------------ consumers
-		constexpr uint32_t GPW = 32u / G;  // groups per warp
-		const uint32_t gl = lane % G;      // lane inside its group
-		const uint32_t wgroup0 = (warp - 1u) * GPW;
-		constexpr uint32_t NGROUPS = kTileConsumerWarps * GPW;
-		uint32_t si = 0xffffffffu;
-		pgt_seg sg;
-		sg.unit_base = 0;
-		sg.nunits = 0;
-		uint32_t it = 0;
-		for (uint64_t t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
-			const uint32_t stg = it % tc.nstages;
-			mbar_wait(&ctl->full[stg], (it / tc.nstages) & 1u);
-			const uint64_t s0 = ctl->s0[stg];
-			const char* cp[kMaxTileCols];
-#pragma unroll
-			for (int c = 0; c < kMaxTileCols; ++c) cp[c] = ctl->cp[stg][c];
-			const uint64_t j0 = P.unit_lo + t * tc.m;
-			const uint32_t cnt = (uint32_t)((P.unit_hi - j0 < tc.m) ? (P.unit_hi - j0) : tc.m);
-			// Units are dealt to the consumer groups round-robin by GLOBAL unit index, so the group that
-			// gets the extra unit rotates from tile to tile and warps that finish early run ahead
-			// into the next stage: no warp is systematically idle.
-			const uint32_t rot = (uint32_t)((t * tc.m) % NGROUPS);
-			const uint32_t myg = wgroup0 + lane / G;
-			const uint32_t first = myg >= rot ? myg - rot : myg + NGROUPS - rot;
-			for (uint32_t base = 0; base < cnt; base += NGROUPS) {  // warp-uniform trip count
-				const uint32_t ul = base + first;
-				const bool active = ul < cnt;
-				const uint64_t j = j0 + (active ? ul : 0u);
-				uint32_t rel, len;
-				if (INDIRECT) {
-					const uint64_t b0 = bounds[j - P.unit_lo], b1 = bounds[j - P.unit_lo + 1];
-					rel = (uint32_t)(b0 - s0);
-					len = (uint32_t)(b1 - b0);
-				} else {
-					if (si == 0xffffffffu || j - sg.unit_base >= sg.nunits) {
-						if (tc.tile_seg) {  // forward from the tile's first segment
-							if (si == 0xffffffffu || j < sg.unit_base || j - sg.unit_base >= sg.nunits + (uint64_t)tc.m) {
-								si = tc.tile_seg[t];
-								sg = P.segs[si];
-							}
-							while (j - sg.unit_base >= sg.nunits) {
-								++si;
-								sg = P.segs[si];
-							}
-						} else {
-							si = find_seg<true>(P, j);
-							sg = P.segs[si];
-						}
-					}
-					uint64_t st;
-					len = pgt_unit_range(P.g, sg.nsites, j - sg.unit_base, &st);
-					rel = (uint32_t)(sg.site_base + st - P.site_origin - s0);
-				}
-				if (!active) len = 0;
-				PGT_CHECK(len == 0 || (rel + len <= ctl->ns[stg] && j >= P.unit_lo && j < P.unit_hi));
-				typename Stat::Acc acc = Stat::zero();
-				if constexpr (std::is_same<Stat, HetStat>::value && G == 32) {
-					het_unit_from_tile(acc, cp[0], rel, len, lane);
-				} else {
-					for (uint32_t x = gl; x < len; x += G) Stat::fold(acc, Stat::load_tile(cp, rel + x), tc.minind);
-				}
-				acc = group_butterfly<Stat, G>(acc);
-				if (active && gl == 0) units[j - P.unit_lo] = acc;
-			}
-			__syncwarp();
-			if (lane == 0) mbar_arrive(&ctl->empty[stg]);
-		}
-	}
-}
-
-// hetWindow's 1-byte genotype column: a warp per unit, lanes take 16-byte aligned chunks
-// (LDG.128) and count with byte-SIMD + popc; the partial chunks at the two ends of the unit are
-// read byte by byte, so nothing outside [unit start, unit end) is touched.  Integer counts: the
-// result is independent of the order, identical to the generic kernels.
-// volatile asm: the eight loads of a round stay back to back (the compiler otherwise interleaves
-// them with the counting and keeps only ~3 in flight)
-__device__ __forceinline__ uint4 ldg_stream_u4(const uint4* p) {
-	uint4 v;
-	asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
-	return v;
-}
-template <bool INDIRECT>
-__global__ void __launch_bounds__(256, 4) k_units_het_vec(DevPlan P, const int8_t* __restrict__ geno, HetStat::Acc* __restrict__ units,
-                                                        const uint64_t* __restrict__ bounds) {
-	const uint32_t lane = threadIdx.x & 31u;
-	const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-	const uint64_t nwarp = ((uint64_t)gridDim.x * blockDim.x) >> 5;
-	uint32_t si = 0xffffffffu;
-	pgt_seg sg;
-	sg.unit_base = 0;
-	sg.nunits = 0;
-	for (uint64_t j = P.unit_lo + warp; j < P.unit_hi; j += nwarp) {
-		uint64_t i0;
-		uint32_t len;
-		if (INDIRECT) {
-			const uint64_t b0 = bounds[j - P.unit_lo], b1 = bounds[j - P.unit_lo + 1];
-			i0 = b0;
-			len = (uint32_t)(b1 - b0);
-		} else {
-			if (si == 0xffffffffu || j - sg.unit_base >= sg.nunits) {
-				si = find_seg<true>(P, j);
-				sg = P.segs[si];
-			}
-			uint64_t st;
-			len = pgt_unit_range(P.g, sg.nsites, j - sg.unit_base, &st);
-			i0 = sg.site_base + st - P.site_origin;
-		}
-		const int8_t* A = geno + i0;
-		const int8_t* E = A + len;
-		PGT_CHECK(len == 0 || i0 + len <= P.col_elems);
-		const int8_t* A0 = (const int8_t*)(((uintptr_t)A + 15u) & ~(uintptr_t)15u);  // first aligned chunk inside
-		const int8_t* A1 = (const int8_t*)((uintptr_t)E & ~(uintptr_t)15u);          // end of the last aligned chunk
-		uint32_t nonmissing = 0, nhet = 0;
-		if (A1 > A0) {
-			uint32_t nm128 = 0, h128 = 0;
-			const uint32_t nch = (uint32_t)(A1 - A0) >> 4;
-			// 8 x 16 bytes in flight per lane (one 4096-site unit = one round); chunks past the end read
-			// as 0x80 bytes = missing genotypes, which count for nothing
-			const uint4 kMissing = make_uint4(0x80808080u, 0x80808080u, 0x80808080u, 0x80808080u);
-			for (uint32_t c0 = lane; c0 < nch; c0 += 256u) {
-				uint4 v[8];
-#pragma unroll
-				for (int q = 0; q < 8; ++q) {  // unconditional loads (index clamped) so that all 8 are issued back to back
-					const uint32_t c = c0 + 32u * q;
-					v[q] = ldg_stream_u4(reinterpret_cast<const uint4*>(A0) + (c < nch ? c : nch - 1u));
-				}
-#pragma unroll
-				for (int q = 0; q < 8; ++q) {
-					if (c0 + 32u * q >= nch) v[q] = kMissing;
-					het_count_word(v[q].x, nm128, h128);
-					het_count_word(v[q].y, nm128, h128);
-					het_count_word(v[q].z, nm128, h128);
-					het_count_word(v[q].w, nm128, h128);
-				}
-			}
-			nonmissing = nm128 >> 7;
-			nhet = h128 >> 7;
-			const uint32_t nh = (uint32_t)(A0 - A), nt = (uint32_t)(E - A1);  // < 16 each
-			if (lane < nh) {
-				const int g = __ldg(A + lane);
-				nonmissing += (g >= 0);
-				nhet += (g == 1);
-			}
-			if (lane >= 16u && lane - 16u < nt) {
-				const int g = __ldg(A1 + (lane - 16u));
-				nonmissing += (g >= 0);
-				nhet += (g == 1);
-			}
-		} else {
-			for (uint32_t x = lane; x < len; x += 32u) {  // < 32 bytes without an aligned chunk
-				const int g = __ldg(A + x);
-				nonmissing += (g >= 0);
-				nhet += (g == 1);
-			}
-		}
-		HetStat::Acc acc{nonmissing, nhet};
-		acc = warp_butterfly<HetStat>(acc);
-		if (lane == 0) units[j - P.unit_lo] = acc;
-	}
-}
-
-// bp mode: bounds[t] = index (relative to the columns' element 0) of the first site at or after
-// the first bp of unit unit_lo+t, t in [0, unit_hi-unit_lo]; the unit's bp -> (chromosome, pos) is
-// closed form, the site is a lower_bound in that chromosome's slice of `pos`.
-__global__ void __launch_bounds__(256) k_bp_bounds(DevPlan P, const uint32_t* __restrict__ pos, uint64_t ndata, uint64_t* __restrict__ bounds) {
-	const uint64_t nb = P.unit_hi - P.unit_lo + 1;
-	const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-	for (uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; t < nb; t += stride) {
-		const uint64_t j = P.unit_lo + t;
-		uint64_t res;
-		if (j >= P.nunits_total) {
-			res = P.site_off[P.ncontig];
-		} else {
-			const pgt_seg sg = P.segs[find_seg<true>(P, j)];
-			uint64_t st;
-			pgt_unit_range(P.g, sg.nsites, j - sg.unit_base, &st);
-			const uint64_t e = sg.site_base + st;  // global bp entry
-			const uint32_t c = find_contig(P.off, sg.first_contig, sg.ncontig, e);
-			const uint32_t p = (uint32_t)(e - P.off[c]) + 1u;  // 1-based position on chromosome c
-			uint64_t lo = P.site_off[c], hi = P.site_off[c + 1];
-			// clip to the sites this call holds
-			if (lo < P.site_origin) lo = P.site_origin;
-			if (hi > P.site_origin + ndata) hi = P.site_origin + ndata;
-			if (hi < lo) hi = lo;
-			while (lo < hi) {
-				const uint64_t mid = lo + ((hi - lo) >> 1);
-				if (__ldg(pos + (mid - P.site_origin)) < p) lo = mid + 1;
-				else hi = mid;
-			}
-			res = lo;
-		}
-		if (res < P.site_origin) res = P.site_origin;
-		if (res > P.site_origin + ndata) res = P.site_origin + ndata;
-		bounds[t] = res - P.site_origin;
-	}
-}
-
-// ----------------------------------------------------------------------------- level 2
-
-template <class Stat>
-__device__ __forceinline__ void emit_window(const DevPlan& P, const pgt_seg& sg, uint64_t w, uint64_t k, const typename Stat::Acc& acc,
-                                            const uint32_t* __restrict__ pos, const pgt_windows& out, bool have_edges = false,
-                                            uint32_t edge_start = 0, uint32_t edge_end = 0);
-
-// One warp per window: lane l adds unit partials l, l+32, ... (from +0.0, so a window of
-// -0.0 values sums to +0.0 exactly as the reference's `double asum = 0`), then the butterfly.
-// units_base = global index of units[0].
-template <class Stat>
-__global__ void __launch_bounds__(256) k_windows(DevPlan P, const typename Stat::Acc* __restrict__ units, uint64_t units_base,
-                                                  const uint32_t* __restrict__ pos, pgt_windows out) {
-	const uint32_t lane = threadIdx.x & 31u;
-	const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-	const uint64_t nwarp = ((uint64_t)gridDim.x * blockDim.x) >> 5;
-	// The per-window work is a chain of dependent memory round trips; keep it short: the segment is
-	// cached (w only grows, so it changes a few dozen times per warp instead of costing a binary
-	// search in global memory per window), and lane 0 fetches the two edge positions BEFORE the
-	// partials are summed, so that gather overlaps the partial loads instead of following them.
-	// Every warp takes a contiguous run of windows, so the segment only ever moves forward by a step or
-	// two: one binary search per warp, then a walk (genomes of 1e5 contigs with W larger than the contigs
-	// paid a 17-probe search in L2 per window: 0.86 ms for 1e5 windows).
-	uint32_t si = 0xffffffffu;
-	pgt_seg sg;
-	sg.win_base = 0;
-	sg.nwin = 0;
-	const uint64_t nwin_all = P.win_hi - P.win_lo;
-	const uint64_t per = (nwin_all + nwarp - 1) / nwarp;
-	const uint64_t w_begin = P.win_lo + warp * per;
-	const uint64_t w_end = w_begin + per < P.win_hi ? w_begin + per : P.win_hi;
-	for (uint64_t w = w_begin; w < w_end; ++w) {
-		if (si == 0xffffffffu) {
-			si = find_seg<false>(P, w);
-			sg = P.segs[si];
-		}
-		while (w - sg.win_base >= sg.nwin) {  // also skips segments without windows
-			++si;
-			sg = P.segs[si];
-		}
-		const uint64_t k = w - sg.win_base;
-		uint64_t fu;
-		const uint64_t cnt = pgt_window_units(P.g, sg, k, &fu);
-		uint32_t sp = 0, ep = 0;
-		if (lane == 0 && pos && P.mode != PGT_MODE_BP) {
-			uint64_t fs;
-			const uint32_t nsites = pgt_window_sites(P.g, sg, k, &fs);
-			sp = __ldg(pos + (sg.site_base + fs - P.site_origin));
-			ep = __ldg(pos + (sg.site_base + fs + nsites - 1 - P.site_origin));
-		}
-		const typename Stat::Acc* up = units + (sg.unit_base + fu - units_base);
-		PGT_CHECK(sg.unit_base + fu >= P.unit_lo && sg.unit_base + fu + cnt <= P.unit_hi && w >= P.win_lo && w < P.win_hi);
-		typename Stat::Acc acc = Stat::zero();
-		for (uint64_t x = lane; x < cnt; x += 128u) {  // four partials per lane in flight; added in index order
-			typename Stat::Acc v[4];
-#pragma unroll
-			for (int q = 0; q < 4; ++q)
-				if (x + 32u * q < cnt) v[q] = up[x + 32u * q];
-#pragma unroll
-			for (int q = 0; q < 4; ++q)
-				if (x + 32u * q < cnt) Stat::add(acc, v[q]);
-		}
-		acc = warp_butterfly<Stat>(acc);
-		if (lane == 0) emit_window<Stat>(P, sg, w, k, acc, pos, out, true, sp, ep);
-	}
-}
-
-// Fine windows (<= 32 units each): one THREAD per window, outputs written coalesced.  The value is
-// bit-identical to k_windows: leaf i is (+0.0 + unit i) for i < cnt and +0.0 beyond, combined in
-// the butterfly's order V(i, s) = V(i, 2s) + V(i + s, 2s), evaluated depth-first so only log2(P2)
-// partials are live.
-template <class Stat, int P2, int S>
-struct SmallTree {
-	static __device__ __forceinline__ typename Stat::Acc eval(const typename Stat::Acc* __restrict__ up, uint32_t i, uint32_t cnt) {
-		typename Stat::Acc a = SmallTree<Stat, P2, S * 2>::eval(up, i, cnt);
-		if (i + S < cnt) Stat::add(a, SmallTree<Stat, P2, S * 2>::eval(up, i + S, cnt));  // adding the +0.0 subtree is the identity
-		return a;
-	}
-};
-template <class Stat, int P2>
-struct SmallTree<Stat, P2, P2> {
-	static __device__ __forceinline__ typename Stat::Acc eval(const typename Stat::Acc* __restrict__ up, uint32_t i, uint32_t cnt) {
-		typename Stat::Acc a = Stat::zero();
-		if (i < cnt) Stat::add(a, up[i]);
-		return a;
-	}
-};
-
-template <class Stat>
-__device__ __forceinline__ void emit_window(const DevPlan& P, const pgt_seg& sg, uint64_t w, uint64_t k, const typename Stat::Acc& acc,
-                                            const uint32_t* __restrict__ pos, const pgt_windows& out, bool have_edges, uint32_t edge_start,
-                                            uint32_t edge_end) {
-	const uint64_t o = w - P.win_lo;
-	uint64_t fs;
-	const uint32_t nsites = pgt_window_sites(P.g, sg, k, &fs);
-	const uint64_t first = sg.site_base + fs, last = first + nsites - 1;
-	const uint32_t label = find_contig(P.off, sg.first_contig, sg.ncontig, last);
-	if (out.label) out.label[o] = label;
-	if (out.nsites) out.nsites[o] = nsites;
-	uint32_t sp = 0, ep = 0;
-	bool have = false;
-	if (P.mode == PGT_MODE_BP) {
-		// dxyWindow.cpp:190 prints the bp position of the first / last buffer entry
-		const uint32_t cf = find_contig(P.off, sg.first_contig, sg.ncontig, first);
-		sp = (uint32_t)(first - P.off[cf]) + 1u;
-		ep = (uint32_t)(last - P.off[label]) + 1u;
-		have = true;
-	} else if (pos) {
-		PGT_CHECK(first >= P.site_origin && last - P.site_origin < P.col_elems);
-		sp = have_edges ? edge_start : __ldg(pos + (first - P.site_origin));  // the caller may have fetched them early
-		ep = have_edges ? edge_end : __ldg(pos + (last - P.site_origin));
-		have = true;
-	}
-	if (have) {
-		if (out.start_pos) out.start_pos[o] = sp;
-		if (out.end_pos) out.end_pos[o] = ep;
-		if (out.mid_pos) out.mid_pos[o] = (sp + ep) / 2u;  // uint32 arithmetic, fstWindow.cpp:73
-	}
-	Stat::emit(out, o, acc);
-}
-
-template <class Stat, int P2>
-__global__ void __launch_bounds__(256) k_windows_small(DevPlan P, const typename Stat::Acc* __restrict__ units, uint64_t units_base,
-                                                        const uint32_t* __restrict__ pos, pgt_windows out) {
-	const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-	uint32_t si = 0xffffffffu;
-	pgt_seg sg;
-	sg.win_base = 0;
-	sg.nwin = 0;
-	for (uint64_t w = P.win_lo + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; w < P.win_hi; w += stride) {
-		if (si == 0xffffffffu || w - sg.win_base >= sg.nwin) {
-			si = find_seg<false>(P, w);
-			sg = P.segs[si];
-		}
-		const uint64_t k = w - sg.win_base;
-		uint64_t fu;
-		const uint32_t cnt = (uint32_t)pgt_window_units(P.g, sg, k, &fu);
-		PGT_CHECK(cnt <= (uint32_t)P2 && sg.unit_base + fu >= P.unit_lo && sg.unit_base + fu + cnt <= P.unit_hi);
-		const typename Stat::Acc acc = SmallTree<Stat, P2, 1>::eval(units + (sg.unit_base + fu - units_base), 0u, cnt);
-		emit_window<Stat>(P, sg, w, k, acc, pos, out);
-	}
-}
-
-// W = S = 1 (the tools' default arguments): every window is one site, so the window table is an
-// elementwise map of the columns; level 1 is skipped and the per-site statistic is evaluated here.
-// Output-bound (36-76 bytes of rows per 1-41 bytes of site): a thread takes four windows per turn and issues
-// their column loads together before the first row is stored; the label comes from a cached contig range
-// instead of a binary search per window.
-template <class Stat>
-__global__ void __launch_bounds__(256) k_windows_persite(DevPlan P, Cols cols, pgt_windows out) {
-	constexpr int U = 4;
-	const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-	uint32_t si = 0xffffffffu;
-	pgt_seg sg;
-	sg.win_base = 0;
-	sg.nwin = 0;
-	uint32_t lc = 0;
-	uint64_t lc_lo = 1, lc_hi = 0;  // sites of contig lc: [lc_lo, lc_hi); empty = nothing cached
-	for (uint64_t w0 = P.win_lo + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; w0 < P.win_hi; w0 += U * stride) {
-		uint64_t site[U];
-		typename Stat::Site v[U];
-		uint32_t ps[U];
-#pragma unroll
-		for (int q = 0; q < U; ++q) {
-			const uint64_t w = w0 + q * stride;
-			site[q] = ~0ull;
-			if (w >= P.win_hi) continue;
-			if (si == 0xffffffffu || w - sg.win_base >= sg.nwin) {
-				si = find_seg<false>(P, w);
-				sg = P.segs[si];
-			}
-			site[q] = sg.site_base + (w - sg.win_base);  // window k of a segment is its site k
-		}
-#pragma unroll
-		for (int q = 0; q < U; ++q) {
-			if (site[q] == ~0ull) continue;
-			PGT_CHECK(site[q] >= P.site_origin && site[q] - P.site_origin < P.col_elems);
-			v[q] = Stat::load(cols, site[q] - P.site_origin);
-			ps[q] = cols.pos ? __ldg(cols.pos + (site[q] - P.site_origin)) : 0u;
-		}
-#pragma unroll
-		for (int q = 0; q < U; ++q) {
-			if (site[q] == ~0ull) continue;
-			const uint64_t o = w0 + q * stride - P.win_lo;
-			if (site[q] < lc_lo || site[q] >= lc_hi) {
-				lc = find_contig(P.off, 0, P.ncontig, site[q]);
-				lc_lo = P.off[lc];
-				lc_hi = P.off[lc + 1];
-			}
-			typename Stat::Acc acc = Stat::zero();
-			Stat::fold(acc, v[q], cols.minind);
-			if (out.label) out.label[o] = lc;
-			if (out.nsites) out.nsites[o] = 1u;
-			if (cols.pos) {
-				if (out.start_pos) out.start_pos[o] = ps[q];
-				if (out.end_pos) out.end_pos[o] = ps[q];
-				if (out.mid_pos) out.mid_pos[o] = (ps[q] + ps[q]) / 2u;  // uint32 arithmetic, fstWindow.cpp:73
-			}
-			Stat::emit(out, o, acc);
-		}
-	}
-}
-
-// ----------------------------------------------------------------------------- level 2, scan mode
-//
-// Fine steps with long windows (e.g. W = 1000, S = 1): summing W/S unit partials per window
-// would cost O(n * W / S^2).  Instead the unit array is cut into blocks of B = wunits units
-// (aligned to the segment's first unit), and an inclusive prefix scan PRE and suffix scan SUF are
-// taken inside every block.  A window covers at most two adjacent blocks, so
-//     window = SUF[first unit] + PRE[last unit]          (van Herk / Gil-Werman)
-// -- two reads per window, only additions of true partial sums (no subtraction, no cancellation).
-// Order inside a block: chunks of 256 units; warp shuffle scan, warp totals, running carry.
-
-template <class Acc>
-__device__ __forceinline__ Acc shfl_up_acc(const Acc& v, unsigned delta) {
-	static_assert(sizeof(Acc) % 4 == 0, "Acc is made of 32-bit words");
-	uint32_t w[sizeof(Acc) / 4];
-	memcpy(w, &v, sizeof(Acc));
-#pragma unroll
-	for (unsigned i = 0; i < sizeof(Acc) / 4; ++i) w[i] = __shfl_up_sync(0xffffffffu, w[i], delta);
-	Acc r;
-	memcpy(&r, w, sizeof(Acc));
-	return r;
-}
-
-// one direction of the block scan: items x0 + i (forward) or x1 - 1 - i (backward), i = 0..n-1
-template <class Stat, bool BACKWARD>
-__device__ __forceinline__ void cta_scan_dir(const typename Stat::Acc* __restrict__ in, typename Stat::Acc* __restrict__ outp, uint64_t x0, uint64_t x1,
-                                             typename Stat::Acc* s_wtot, typename Stat::Acc* s_carry) {
-	typedef typename Stat::Acc Acc;
-	const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-	const uint64_t n = x1 - x0;
-	if (threadIdx.x == 0) *s_carry = Stat::zero();
-	__syncthreads();
-	for (uint64_t base = 0; base < n; base += blockDim.x) {
-		const uint64_t i = base + threadIdx.x;
-		const bool ok = i < n;
-		const uint64_t idx = BACKWARD ? (x1 - 1 - i) : (x0 + i);
-		Acc v = Stat::zero();
-		if (ok) Stat::add(v, in[idx]);
-		// inclusive scan inside the warp
-#pragma unroll
-		for (unsigned d = 1; d < 32; d <<= 1) {
-			Acc o = shfl_up_acc(v, d);
-			if (lane >= d) {
-				Acc t = o;          // earlier items first: t = earlier + v
-				Stat::add(t, v);
-				v = t;
-			}
-		}
-		if (lane == 31) s_wtot[warp] = v;
-		__syncthreads();
-		Acc pre = *s_carry;  // everything before this chunk
-		for (uint32_t w = 0; w < warp; ++w) Stat::add(pre, s_wtot[w]);
-		Stat::add(pre, v);
-		if (ok) outp[idx] = pre;
-		__syncthreads();
-		if (threadIdx.x == blockDim.x - 1) *s_carry = pre;  // inclusive total through this chunk
-		__syncthreads();
-	}
-}
-
-template <class Stat>
-__global__ void __launch_bounds__(256) k_block_scan(DevPlan P, typename Stat::Acc* __restrict__ units, typename Stat::Acc* __restrict__ pre,
-                                                     uint64_t units_base, uint64_t blk_lo, uint64_t blk_hi) {
-	__shared__ typename Stat::Acc s_wtot[8];
-	__shared__ typename Stat::Acc s_carry;
-	const uint64_t B = P.g.wunits;
-	for (uint64_t gb = blk_lo + blockIdx.x; gb < blk_hi; gb += gridDim.x) {
-		const pgt_seg sg = P.segs[find_seg_by_block(P, gb)];
-		const uint64_t lb = gb - sg.blk_base;
-		uint64_t u0 = sg.unit_base + lb * B;
-		uint64_t u1 = sg.unit_base + ((lb + 1) * B < sg.nunits ? (lb + 1) * B : sg.nunits);
-		// clip to the units this scan computed (shards): see DESIGN.md, the clipped values are never used
-		if (u0 < P.unit_lo) u0 = P.unit_lo;
-		if (u1 > P.unit_hi) u1 = P.unit_hi;
-		if (u1 <= u0) continue;
-		PGT_CHECK(u0 >= units_base && u0 >= P.unit_lo && u1 <= P.unit_hi);
-		cta_scan_dir<Stat, false>(units, pre, u0 - units_base, u1 - units_base, s_wtot, &s_carry);  // PRE (reads raw units)
-		cta_scan_dir<Stat, true>(units, units, u0 - units_base, u1 - units_base, s_wtot, &s_carry);  // SUF in place
-	}
-}
-
-template <class Stat>
-__global__ void __launch_bounds__(256) k_windows_hgw(DevPlan P, const typename Stat::Acc* __restrict__ suf, const typename Stat::Acc* __restrict__ pre,
-                                                      uint64_t units_base, const uint32_t* __restrict__ pos, pgt_windows out) {
-	const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-	const uint64_t B = P.g.wunits;
-	uint32_t si = 0xffffffffu;
-	pgt_seg sg;
-	sg.win_base = 0;
-	sg.nwin = 0;
-	for (uint64_t w = P.win_lo + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; w < P.win_hi; w += stride) {
-		if (si == 0xffffffffu || w - sg.win_base >= sg.nwin) {
-			si = find_seg<false>(P, w);
-			sg = P.segs[si];
-		}
-		const uint64_t k = w - sg.win_base;
-		uint64_t fu;
-		const uint64_t cnt = pgt_window_units(P.g, sg, k, &fu);
-		const uint64_t lu = fu + cnt - 1;  // segment-local first / last unit
-		const uint64_t gf = sg.unit_base + fu - units_base, gl = sg.unit_base + lu - units_base;
-		PGT_CHECK(sg.unit_base + fu >= P.unit_lo && sg.unit_base + lu < P.unit_hi);
-		typename Stat::Acc acc = Stat::zero();
-		if (fu / B == lu / B) {
-			// inside one block: block-aligned start (PRE up to the last unit), or it runs to the block /
-			// segment end (SUF from the first unit)
-			if (fu % B == 0) Stat::add(acc, pre[gl]);
-			else Stat::add(acc, suf[gf]);
-		} else {
-			Stat::add(acc, suf[gf]);
-			Stat::add(acc, pre[gl]);
-		}
-		emit_window<Stat>(P, sg, w, k, acc, pos, out);
-	}
-}
-
-
-// ----------------------------------------------------------------------------- fine steps: sliding tile
-//
-// W = 1000, S = 1 and its kin: steps so short that a "unit" would be a handful of sites (pgt_geom.h:
-// units never span a step), so the two-level scheme degenerates into copying every site into the unit
-// array and scanning that array twice in global memory (~3x the compulsory traffic).  Here the windows
-// are formed straight from the sites, in shared memory, and no unit array exists:
-//
-//   * the site axis of a segment is cut into BLOCKS of W sites from the segment origin; window k
-//     (first site f = k*S, last site l) touches block m = f div W and at most block m + 1, so
-//         window = SUF_m[f mod W] (+ PRE_{m+1}[l mod W] when l is in block m + 1)
-//     with PRE / SUF the inclusive prefix / suffix sums inside a block (van Herk / Gil-Werman): only
-//     additions of true partial sums, no differences, no cancellation;
-//   * persistent CTAs take CHUNKS of consecutive windows; a chunk walks its blocks in order, G blocks per
-//     step: the producer warp stages the step's slice of every column (positions included) with bulk
-//     async copies (the ring of k_units_tiled); every block is scanned by its own team of WPB warps
-//     (thread q of a team owns elements [q*E, (q+1)*E) of its block: forward total, two warp shuffle scans,
-//     the team's warp totals through shared memory, then PRE running forward from the thread's base and
-//     SUF running backward from it); the windows that start in the blocks of the step -- all but its last
-//     block, plus the last block of the step before -- are emitted from SUF and PRE in shared memory with
-//     coalesced row stores.  SUF and the positions are double-buffered by step parity, so a step has two
-//     CTA-wide barriers.  Every site is read once per chunk; neighbouring chunks share W - S sites.
-//     (E, WPB, G) are chosen per W so that a step covers as many sites as the 7 consumer warps can own:
-//     W = 1000: E = 5, one block of 7 warps; W = 256: E = 4, three blocks of 2 warps.
-//
-// Summation order: a pure function of (W, S) and the position of a site inside its block -- not of
-// chunks, CTAs, stages or shards (a chunk that starts or ends inside a block simply has the sites
-// outside its windows absent, and those only ever enter prefix / suffix values no window of the chunk
-// reads), so results are bit-identical for any GPU count.  Reference semantics: fstWindow.cpp:80-99.
-
-static constexpr int kSlideWarps = 7;                          // consumer warps (+ the producer warp = 256 threads: 128 registers each at two CTAs per SM)
-static constexpr int kSlideConsumers = kSlideWarps * 32;
-static constexpr int kSlideThreads = kSlideConsumers + 32;     // + the producer warp (the last one)
-static constexpr uint32_t kSlideMaxE = 6;                      // W <= 1344 (and the fused step must fit shared memory: W <= 1048)
-static constexpr uint32_t kSlideWtBytes = 512;                 // warp totals: 7 x Acc (<= 40 B)
-
-// The team shape for a window size: E elements per thread, WPB warps per block, G = 7 / WPB blocks per step --
-// the (E, WPB) with the most sites per step, the smaller E on ties.  Part of the summation order.
-struct SlideTeam {
-	uint32_t E, wpb, G;
-};
-// (a step holds at most 1024 sites -- G * (W rounded up to 32) -- so that the fused statistic's step fits shared memory)
-__host__ __device__ inline SlideTeam slide_team(uint32_t W) {
-	SlideTeam best{1, kSlideWarps, 0};
-	const uint32_t wp = (W + 31u) / 32u * 32u;
-	for (uint32_t E = 1; E <= kSlideMaxE; ++E) {
-		const uint32_t tpb = (W + E - 1) / E;
-		const uint32_t wpb = (tpb + 31) / 32;
-		if (wpb > (uint32_t)kSlideWarps) continue;
-		uint32_t G = (uint32_t)kSlideWarps / wpb;
-		if (G > 1024u / wp) G = 1024u / wp;
-		if (G < 1) G = 1;
-		if (G > best.G) best = SlideTeam{E, wpb, G};
-	}
-	return best;
-}
-
-struct SlideCfg {
-	uint32_t E, wpb, G;      // slide_team(W)
-	uint32_t wp;             // stride of one block's arrays in shared memory (W rounded up to 32)
-	uint32_t sf_off, pr_off, pos_off, stage_off;  // byte offsets inside the dynamic shared memory
-	uint32_t pos_col;        // staging index of the position column, 0xffffffff = positions not wanted
-	uint64_t chunk_windows;  // windows per chunk
-	uint64_t nchunks;
-};
-
-template <class Acc>
-__device__ __forceinline__ Acc shfl_down_acc(const Acc& v, unsigned delta) {
-	static_assert(sizeof(Acc) % 4 == 0, "Acc is made of 32-bit words");
-	uint32_t w[sizeof(Acc) / 4];
-	memcpy(w, &v, sizeof(Acc));
-#pragma unroll
-	for (unsigned i = 0; i < sizeof(Acc) / 4; ++i) w[i] = __shfl_down_sync(0xffffffffu, w[i], delta);
-	Acc r;
-	memcpy(&r, w, sizeof(Acc));
-	return r;
-}
-
-__device__ __forceinline__ void slide_bar() { asm volatile("bar.sync 1, %0;" ::"n"(kSlideConsumers) : "memory"); }
-
-// the part of a chunk that lies in one segment: windows [ka, kb) of segment `sg` (segment-local), reading
-// the segment-local sites [lo, hi)
-struct SlideRun {
-	pgt_seg sg;
-	uint32_t si;
-	uint64_t ka, kb, lo, hi;
-};
-// first run of the chunk [wa, wb) / the run after `r`; false when the chunk is exhausted
-__device__ __forceinline__ bool slide_run_at(const DevPlan& P, uint64_t w, uint64_t wb, SlideRun& r, bool first) {
-	if (w >= wb) return false;
-	if (first) {
-		r.si = find_seg<false>(P, w);
-		r.sg = P.segs[r.si];
-	}
-	while (w - r.sg.win_base >= r.sg.nwin) {  // also skips segments without windows
-		++r.si;
-		r.sg = P.segs[r.si];
-	}
-	r.ka = w - r.sg.win_base;
-	r.kb = wb - r.sg.win_base < r.sg.nwin ? wb - r.sg.win_base : r.sg.nwin;
-	r.lo = r.ka * P.g.S;
-	const uint64_t e = (r.kb - 1) * P.g.S + P.g.W;
-	r.hi = e < r.sg.nsites ? e : r.sg.nsites;
-	return true;
-}
-
-// (register budget: two CTAs per SM for the narrow statistics -- 128 registers -- and one for the fused
-// scan, whose step fills the shared memory of an SM anyway)
-template <class Stat>
-struct SlideMinBlocks {
-	static constexpr int value = 2;
-};
-template <>
-struct SlideMinBlocks<FusedStat> {
-	static constexpr int value = 1;
-};
-// MULTI = several blocks per step (G > 1, W <= 512); with one block per step the team arithmetic folds away
-template <class Stat, int EMAX, bool MULTI>
-__global__ void __launch_bounds__(kSlideThreads, SlideMinBlocks<Stat>::value) k_slide(DevPlan P, TileCfg tc, SlideCfg sc, pgt_windows out) {
-	typedef typename Stat::Acc Acc;
-	extern __shared__ __align__(128) unsigned char smem[];
-	TileCtl* ctl = reinterpret_cast<TileCtl*>(smem);
-	Acc* wt = reinterpret_cast<Acc*>(smem + kTileCtlBytes);
-	Acc* SfBase = reinterpret_cast<Acc*>(smem + sc.sf_off);           // SUF of the step's blocks: [2][G * wp], by step parity
-	Acc* Pr = reinterpret_cast<Acc*>(smem + sc.pr_off);               // PRE of the step's blocks: [G * wp]
-	uint32_t* PosBase = reinterpret_cast<uint32_t*>(smem + sc.pos_off);  // positions of the step's blocks: [2][G * wp]
-	unsigned char* stages = smem + sc.stage_off;
-	const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
-	const uint64_t W = P.g.W, S = P.g.S;
-	const uint32_t Wu = P.g.W, Su = P.g.S, G = MULTI ? sc.G : 1u, gw = G * sc.wp;
-	const uint32_t wpb = MULTI ? sc.wpb : (uint32_t)kSlideWarps;
-	const bool has_pos = sc.pos_col != 0xffffffffu;
-
-	if (threadIdx.x == 0) {
-		for (uint32_t s = 0; s < tc.nstages; ++s) {
-			mbar_init(&ctl->full[s], 2);
-			mbar_init(&ctl->empty[s], kSlideWarps);
-		}
-		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-	}
-	__syncthreads();
-
-	if (warp == kSlideWarps) {
-		// ------------------------------------------------------------------ producer: one stage per step (G blocks)
-		uint32_t it = 0;
-		for (uint64_t c = blockIdx.x; c < sc.nchunks; c += gridDim.x) {
-			const uint64_t wa = P.win_lo + c * sc.chunk_windows;
-			const uint64_t wb = P.win_hi - wa < sc.chunk_windows ? P.win_hi : wa + sc.chunk_windows;
-			SlideRun r;
-			for (bool ok = slide_run_at(P, wa, wb, r, true); ok; ok = slide_run_at(P, r.sg.win_base + r.kb, wb, r, false)) {
-				for (uint64_t b = r.lo / W; b * W < r.hi; b += G, ++it) {
-					const uint64_t x0 = b * W > r.lo ? b * W : r.lo;
-					const uint64_t x1 = (b + G) * W < r.hi ? (b + G) * W : r.hi;
-					const uint32_t stg = it % tc.nstages;
-					if (it >= tc.nstages) mbar_wait(&ctl->empty[stg], ((it / tc.nstages) - 1u) & 1u);
-					producer_fill_stage(tc, ctl, stages, stg, r.sg.site_base + x0 - P.site_origin, r.sg.site_base + x1 - P.site_origin, lane);
-				}
-			}
-		}
-		return;
-	}
-
-	// ---------------------------------------------------------------------- consumers
-	const uint32_t t = threadIdx.x;
-	const uint32_t team = MULTI ? warp / wpb : 0u;  // which block of a step this thread works on (>= G: none)
-	const uint32_t tw = warp - team * wpb;          // warp inside its team
-	const uint32_t e0 = (tw * 32u + lane) * sc.E;   // first element of the block this thread owns
-	const bool member = MULTI ? team < G : true;
-	uint32_t it = 0, step = 0;  // `step` selects the halves of the double buffers
-	for (uint64_t c = blockIdx.x; c < sc.nchunks; c += gridDim.x) {
-		const uint64_t wa = P.win_lo + c * sc.chunk_windows;
-		const uint64_t wb = P.win_hi - wa < sc.chunk_windows ? P.win_hi : wa + sc.chunk_windows;
-		SlideRun r;
-		for (bool ok = slide_run_at(P, wa, wb, r, true); ok; ok = slide_run_at(P, r.sg.win_base + r.kb, wb, r, false)) {
-			const uint64_t m_first = r.lo / W, m_last = (r.hi - 1) / W;
-			// label = contig of the window's last site: the windows a thread emits go up the axis, so a cursor
-			// that only walks forward replaces a binary search per window
-			uint32_t lc = r.sg.first_contig;
-			uint64_t lc_end = r.sg.ncontig > 1 ? P.off[lc + 1] : ~0ull;  // global site where contig lc ends
-			// kc = ceil(b*W / S): first window that starts at or after block b; kept incrementally
-			uint64_t kq = m_first * W / S;
-			uint32_t krem = (uint32_t)(m_first * W - kq * S);
-			uint64_t kc_from = kq + (krem != 0u);  // first window not yet emitted (by block start)
-			for (uint64_t b = m_first; b <= m_last; b += G, ++step) {
-				// blocks [b, b + gi) arrive; the windows starting in blocks [b - 1, b + gi - 2] leave -- and those of
-				// block b + gi - 1 too when it is the run's last block (they end inside it)
-				const uint32_t gi = (uint32_t)(m_last + 1 - b < G ? m_last + 1 - b : G);
-				Acc* Sf = SfBase + (step & 1u) * gw;
-				const Acc* SfPrev = SfBase + ((step & 1u) ^ 1u) * gw + (G - 1u) * sc.wp;  // SUF of block b - 1
-				uint32_t* Pos = PosBase + (step & 1u) * gw;
-				const uint32_t* PosPrev = PosBase + ((step & 1u) ^ 1u) * gw + (G - 1u) * sc.wp;
-				const uint32_t stg = it % tc.nstages;
-				mbar_wait(&ctl->full[stg], (it / tc.nstages) & 1u);
-				++it;
-				Acc leaf[EMAX];
-				uint32_t pv[EMAX];
-				Acc up = Stat::zero(), dn = Stat::zero();
-				{
-					const char* cp[kMaxTileCols];
-#pragma unroll
-					for (int cc = 0; cc < kMaxTileCols; ++cc) cp[cc] = ctl->cp[stg][cc];
-					const uint32_t* pstage = has_pos ? reinterpret_cast<const uint32_t*>(ctl->cp[stg][sc.pos_col]) : nullptr;
-					const uint64_t x0 = b * W > r.lo ? b * W : r.lo;            // first staged site
-					const uint64_t x1 = (b + gi) * W < r.hi ? (b + gi) * W : r.hi;
-					// sites of a block outside [x0, x1) are absent (other chunk / beyond the segment): +0 leaves
-					const uint32_t s_lo = (uint32_t)(x0 - b * W), s_hi = (uint32_t)(x1 - b * W);  // relative to block b
-					const uint32_t base = team * Wu + e0;                                          // this thread's first element, same frame
-					Acc tot = Stat::zero();
-#pragma unroll
-					for (int e = 0; e < EMAX; ++e) {
-						leaf[e] = Stat::zero();
-						pv[e] = 0u;
-						const uint32_t i = base + (uint32_t)e;
-						if (member && (uint32_t)e < sc.E && e0 + (uint32_t)e < Wu && i >= s_lo && i < s_hi) {
-							PGT_CHECK(i - s_lo < ctl->ns[stg]);
-							Stat::fold(leaf[e], Stat::load_tile(cp, i - s_lo), tc.minind);
-							if (has_pos) pv[e] = pstage[i - s_lo];
-						}
-						Stat::add(tot, leaf[e]);
-					}
-					__syncwarp();
-					if (lane == 0) mbar_arrive(&ctl->empty[stg]);  // the step's sites now live in registers
-					up = tot;
-					dn = tot;
-#pragma unroll
-					for (unsigned d = 1; d < 32; d <<= 1) {
-						Acc o = shfl_up_acc(up, d);
-						if (lane >= d) {  // earlier threads first
-							Stat::add(o, up);
-							up = o;
-						}
-						Acc q = shfl_down_acc(dn, d);
-						if (lane + d < 32u) {  // later threads first
-							Stat::add(q, dn);
-							dn = q;
-						}
-					}
-					if (lane == 31u) wt[warp] = up;  // the warp's total, forward order
-				}
-				slide_bar();  // warp totals visible; every thread has left the emit phase of the step before
-				{
-					Acc bpre = Stat::zero(), bsuf = Stat::zero();
-#pragma unroll
-					for (int w2 = 0; w2 < kSlideWarps - 1; ++w2)  // the team's warps before this one, in order
-						if ((uint32_t)w2 < tw && member) Stat::add(bpre, wt[team * wpb + w2]);
-#pragma unroll
-					for (int w2 = kSlideWarps - 1; w2 > 0; --w2)  // the team's warps after it, last first
-						if ((uint32_t)w2 > tw && (uint32_t)w2 < wpb && member) Stat::add(bsuf, wt[team * wpb + w2]);
-					Acc xu = shfl_up_acc(up, 1), xd = shfl_down_acc(dn, 1);
-					if (lane == 0) xu = Stat::zero();
-					if (lane == 31u) xd = Stat::zero();
-					Stat::add(bpre, xu);
-					Stat::add(bsuf, xd);
-					const uint32_t o0 = team * sc.wp + e0;
-#pragma unroll
-					for (int e = 0; e < EMAX; ++e) {  // PRE: running forward from everything before this thread
-						if (member && (uint32_t)e < sc.E && e0 + (uint32_t)e < Wu) {
-							Stat::add(bpre, leaf[e]);
-							Pr[o0 + e] = bpre;
-							if (has_pos) Pos[o0 + e] = pv[e];
-						}
-					}
-#pragma unroll
-					for (int e = EMAX - 1; e >= 0; --e) {  // SUF: running backward from everything after it
-						if (member && (uint32_t)e < sc.E && e0 + (uint32_t)e < Wu) {
-							Stat::add(bsuf, leaf[e]);
-							Sf[o0 + e] = bsuf;
-						}
-					}
-				}
-				slide_bar();  // PRE, SUF and the positions of the step's blocks complete
-				{
-					// windows that start in blocks [eb_lo, eb_hi]; everything below is relative to the start of block b - 1
-					const uint64_t eb_lo = b > m_first ? b - 1 : b;
-					const uint64_t eb_hi = (b + gi - 1 == m_last) ? m_last : b + gi - 2;  // may be eb_lo - 1: nothing to emit yet
-					// ceil((eb_hi + 1) * W / S): the quotient / remainder of (blocks emitted so far) * W / S stepped forward
-					uint64_t kc_to = kc_from;
-					if (eb_hi + 1 > eb_lo) {
-						const uint32_t nb = (uint32_t)(eb_hi + 1 - eb_lo);
-						kq += (uint64_t)nb * P.g.q;
-						krem += nb * P.g.r;
-						while (krem >= Su) {
-							krem -= Su;
-							++kq;
-						}
-						kc_to = kq + (krem != 0u);
-					}
-					const uint64_t k_lo = kc_from > r.ka ? kc_from : r.ka, k_hi = kc_to < r.kb ? kc_to : r.kb;
-					if (eb_hi + 1 > eb_lo && k_hi > k_lo) {
-						const uint32_t cnt = (uint32_t)(k_hi - k_lo);
-						const uint32_t rel0 = (uint32_t)(k_lo * S + W - b * W);  // first window's start, relative to block b - 1
-						const uint64_t left = r.sg.nsites + W - b * W;            // sites of the segment from block b - 1 on
-						const uint32_t last_rel = (uint32_t)(left < (uint64_t)(G + 2u) * Wu ? left : (uint64_t)(G + 2u) * Wu) - 1u;
-						const uint64_t obase = r.sg.win_base + k_lo - P.win_lo;
-						const uint64_t gbase = r.sg.site_base + b * W - W;  // global site of relative position 0
-						for (uint32_t i = t; i < cnt; i += kSlideConsumers) {
-							const uint32_t rel = rel0 + i * Su;
-							uint32_t blk = 0, brel = 0;  // blk = rel / W; brel = blk * W
-							if (MULTI) {
-								while (rel >= brel + Wu) {  // <= G <= 7 steps
-									brel += Wu;
-									++blk;
-								}
-							} else if (rel >= Wu) {
-								brel = Wu;
-								blk = 1u;
-							}
-							const uint32_t j = rel - brel;  // blk = 0: block b - 1; blk = 1 + g: block g of this step
-							uint32_t lr = rel + Wu - 1u;
-							if (lr > last_rel) lr = last_rel;
-							const bool two = lr >= brel + Wu;  // the window ends in the next block
-							const uint32_t jl = two ? lr - brel - Wu : lr - brel;
-							PGT_CHECK(j < Wu && jl < Wu && blk <= gi && (!two || blk < gi) && obase + i < P.win_hi - P.win_lo);
-							const uint32_t boff = (blk - 1u) * sc.wp;  // (unused when blk == 0)
-							Acc acc = blk == 0u ? SfPrev[j] : Sf[boff + j];
-							if (two) Stat::add(acc, Pr[blk * sc.wp + jl]);
-							const uint64_t o = obase + i;
-							const uint64_t glast = gbase + lr;
-							while (glast >= lc_end) {
-								++lc;
-								lc_end = P.off[lc + 1];
-							}
-							if (out.label) out.label[o] = lc;
-							if (out.nsites) out.nsites[o] = lr - rel + 1u;
-							if (has_pos) {
-								const uint32_t* ps = blk == 0u ? PosPrev : Pos + boff;  // positions of the window's first block
-								const uint32_t sp = ps[j];
-								const uint32_t ep = two ? Pos[blk * sc.wp + jl] : ps[jl];
-								if (out.start_pos) out.start_pos[o] = sp;
-								if (out.end_pos) out.end_pos[o] = ep;
-								if (out.mid_pos) out.mid_pos[o] = (sp + ep) / 2u;  // uint32 arithmetic, fstWindow.cpp:73
-							}
-							Stat::emit(out, o, acc);
-						}
-					}
-					if (eb_hi + 1 > eb_lo) kc_from = kc_to;
-				}
-			}
-		}
-	}
-}
-
-// dxyWindow's global line (dxyWindow.cpp:382-385,429-433) over the unit partials [0, n): one
-// block; thread t adds partials t, t+1024, ...; warp butterflies; counts in 64 bit.
-template <class Stat>
-struct GlobalOf;
-template <>
-struct GlobalOf<DxyStat> {
-	static __device__ __forceinline__ const DxyStat::Acc& get(const DxyStat::Acc& a) { return a; }
-};
-template <>
-struct GlobalOf<FusedStat> {
-	static __device__ __forceinline__ const DxyStat::Acc& get(const FusedStat::Acc& a) { return a.dxy; }
-};
-
-static constexpr int kGlobalBlocks = 256;  // fixed (part of the summation order of the global line)
-
-__device__ __forceinline__ void block_reduce_global(double d, unsigned long long ne, unsigned long long nk, double* __restrict__ out3) {
-	__shared__ double s_d[32];
-	__shared__ unsigned long long s_e[32], s_k[32];
-#pragma unroll
-	for (int m = 16; m >= 1; m >>= 1) {
-		d = __dadd_rn(d, shfl_xor_f64(d, m));
-		ne += __shfl_xor_sync(0xffffffffu, ne, m);
-		nk += __shfl_xor_sync(0xffffffffu, nk, m);
-	}
-	if ((threadIdx.x & 31u) == 0) {
-		s_d[threadIdx.x >> 5] = d;
-		s_e[threadIdx.x >> 5] = ne;
-		s_k[threadIdx.x >> 5] = nk;
-	}
-	__syncthreads();
-	if (threadIdx.x < 32) {
-		const uint32_t nw = blockDim.x >> 5;
-		d = threadIdx.x < nw ? s_d[threadIdx.x] : 0.0;
-		ne = threadIdx.x < nw ? s_e[threadIdx.x] : 0ull;
-		nk = threadIdx.x < nw ? s_k[threadIdx.x] : 0ull;
-#pragma unroll
-		for (int m = 16; m >= 1; m >>= 1) {
-			d = __dadd_rn(d, shfl_xor_f64(d, m));
-			ne += __shfl_xor_sync(0xffffffffu, ne, m);
-			nk += __shfl_xor_sync(0xffffffffu, nk, m);
-		}
-		if (threadIdx.x == 0) {
-			out3[0] = d;
-			out3[1] = (double)ne;
-			out3[2] = (double)nk;
-		}
-	}
-}
-
-// stage 1: block b adds partials b*1024 + t + k*(256*1024) per thread t, then reduces the block
-template <class Stat>
-__global__ void __launch_bounds__(1024) k_global_partial(const typename Stat::Acc* __restrict__ units, uint64_t n, double* __restrict__ partial3) {
-	double d = 0.0;
-	unsigned long long ne = 0, nk = 0;
-	for (uint64_t i = (uint64_t)blockIdx.x * 1024u + threadIdx.x; i < n; i += (uint64_t)kGlobalBlocks * 1024u) {
-		const DxyStat::Acc& a = GlobalOf<Stat>::get(units[i]);
-		d = __dadd_rn(d, a.dxy);
-		ne += a.neff;
-		nk += a.nskip;
-	}
-	block_reduce_global(d, ne, nk, partial3 + 3 * blockIdx.x);
-}
-// stage 2: one block over the 256 block partials
-__global__ void __launch_bounds__(kGlobalBlocks) k_global_final(const double* __restrict__ partial3, double* __restrict__ global3) {
-	block_reduce_global(partial3[3 * threadIdx.x], (unsigned long long)partial3[3 * threadIdx.x + 1],
-	                    (unsigned long long)partial3[3 * threadIdx.x + 2], global3);
-}
-
-// dxyWindow's global line when no unit array exists (sliding-tile and per-site scans): thread t of
-// block b folds sites i0 + b*1024 + t + k*(256*1024) of the owned range [i0, i1) (column element
-// indices) in that order, then the block reductions of k_global_partial.  Classification as
-// DxyStat::fold (dxyWindow.cpp:179-186).
-__global__ void __launch_bounds__(1024) k_global_sites(Cols cols, uint64_t i0, uint64_t i1, double* __restrict__ partial3) {
-	double d = 0.0;
-	unsigned long long ne = 0, nk = 0;
-	constexpr int U = 4;  // four sites' column loads in flight per thread; folded in index order
-	const uint64_t stride = (uint64_t)kGlobalBlocks * 1024u;
-	for (uint64_t i = i0 + (uint64_t)blockIdx.x * 1024u + threadIdx.x; i < i1; i += U * stride) {
-		DxyStat::Site v[U];
-#pragma unroll
-		for (int q = 0; q < U; ++q)
-			if (i + q * stride < i1) v[q] = DxyStat::load(cols, i + q * stride);
-#pragma unroll
-		for (int q = 0; q < U; ++q) {
-			if (i + q * stride >= i1) break;
-			DxyStat::Acc a = DxyStat::zero();
-			DxyStat::fold(a, v[q], cols.minind);
-			d = __dadd_rn(d, a.dxy);
-			ne += a.neff;
-			nk += a.nskip;
-		}
-	}
-	block_reduce_global(d, ne, nk, partial3 + 3 * blockIdx.x);
-}
+#include "pgt_kernels_common.cuh"
+#include "pgt_level1.cuh"
+#include "pgt_level2.cuh"
+#include "pgt_slide.cuh"
 
 // ----------------------------------------------------------------------------- host side of a scan
 

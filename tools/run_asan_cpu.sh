@@ -9,7 +9,7 @@ rm -rf "$OUT"; mkdir -p "$OUT/pkg"
 cd "$ROOT/popgenomicstools_b200/csrc"
 SAN="-fsanitize=address,-fsanitize=undefined,-fno-omit-frame-pointer"
 /usr/local/cuda/bin/nvcc -gencode arch=compute_100a,code=sm_100a -O1 -g -std=c++17 -Xcompiler -fPIC,$SAN -cudart static -shared \
-    pgt_scan.cu pgt_extreme.cu pgt_synth.cu pgt_plan.cpp -o "$OUT/libpgtscan.so"
+    pgt_scan.cu pgt_sharded.cu pgt_upload.cu pgt_extreme.cu pgt_synth.cu pgt_plan.cpp -o "$OUT/libpgtscan.so"
 cp -r "$ROOT/popgenomicstools_b200" "$ROOT/tests" "$ROOT/oracle" "$ROOT/include" "$OUT/pkg/"
 cp "$OUT/libpgtscan.so" "$OUT/pkg/popgenomicstools_b200/libpgtscan.so"
 mkdir -p "$OUT/bin"
