@@ -37,17 +37,24 @@ def write_case(c, d):
 FLOAT_COL = {"fstWindow": {4}, "hetWindow": {4}, "dxyWindow": {3}}
 
 
-def test_golden_transcripts_through_the_clis(golden_cases, tmp_path):
+@pytest.mark.parametrize("mode,stride,env", [
+    ("default", 4, {}),
+    # the streaming-upload path (device-resident columns through the pinned ring, PGT_MEM_DEVICE scan), forced on these tiny inputs
+    ("stream", 11, {"PGT_STREAM_MIN_SITES": "1"}),
+    # one process, three shards (device 0 three times: CUDA_VISIBLE_DEVICES is set, so the list is taken literally)
+    ("devices", 13, {"PGT_DEVICES": "0,0,0", "CUDA_VISIBLE_DEVICES": "0"}),
+])
+def test_golden_transcripts_through_the_clis(golden_cases, tmp_path, mode, stride, env):
     ties = 0
-    # every 4th transcript through a fresh CLI process (each pays 1-3 s of CUDA start-up); ALL
+    # every 4th transcript through a fresh CLI process (each pays 0.3-3 s of CUDA start-up); ALL
     # transcripts go through the library in test_fst_gpu.py / test_stats_gpu.py
     for i, c in enumerate(golden_cases):
-        if i % 4:
+        if i % stride:
             continue
         d = tmp_path / f"c{i}"
         d.mkdir()
         write_case(c, str(d))
-        rc, out, err = U.run(U.ours(c["tool"]), c["argv"], cwd=str(d))
+        rc, out, err = U.run(U.ours(c["tool"]), c["argv"], cwd=str(d), env=env)
         assert rc == c["rc"], (i, c["argv"], err)
         if c["tool"] == "dxyWindow" and c["W"] == 0:
             ties += P.rows_match_modulo_ties(out.splitlines(), c["stdout"].splitlines(), {0})
