@@ -53,6 +53,24 @@ __global__ void __launch_bounds__(256) k_units(DevPlan P, Cols cols, typename St
 	}
 }
 
+// Genomes of many contigs (scaffold-level assemblies: 1e3-1e6 segments, down to a few units each): deriving a
+// unit's site range from its segment costs every consumer group a 72-byte segment record from L2 per unit or two.
+// A one-thread-per-unit kernel writes the unit starts once (8 bytes per unit; units tile the axis, so unit j ends where
+// unit j + 1 starts) and level 1 then runs its INDIRECT variant -- the same kernels bp mode uses -- with identical
+// units, lanes and results.  starts[t] for t in [0, nunits]: column element index of unit unit_lo + t (the last entry:
+// the end of the last unit).
+__global__ void __launch_bounds__(256) k_unit_starts(DevPlan P, uint64_t* __restrict__ starts) {
+	const uint64_t nu = P.unit_hi - P.unit_lo;
+	const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+	for (uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; t <= nu; t += stride) {
+		const uint64_t j = P.unit_lo + (t < nu ? t : nu - 1);
+		const pgt_seg sg = P.segs[find_seg<true>(P, j)];
+		uint64_t st;
+		const uint32_t len = pgt_unit_range(P.g, sg.nsites, j - sg.unit_base, &st);
+		starts[t] = sg.site_base + st + (t < nu ? 0u : len) - P.site_origin;
+	}
+}
+
 // ----------------------------------------------------------------------------- level 1, tiled
 //
 // Persistent CTAs (one per SM) walk tiles of `m` consecutive units.  Warp 0 is the producer: it

@@ -207,6 +207,9 @@ static int g_tune_level2 = 0;
 static int g_tune_stages = 2;      // tiled kernel: shared-memory stages (2..4)
 static int g_tune_stage_kb = 110;  // tiled kernel: KB per stage (stages * stage_kb <= 224)
 extern int g_tune_xgroup;          // extreme scan (pgt_extreme.cu): lanes per unit, 0 = auto
+//   unittable: 0 auto (unit-start table for plans of more than 32 segments, device mode), 1 never, 2 always
+static int g_tune_unittable = 0;
+static constexpr size_t kUnitTableMinSegs = 33;  // measured (profiles/r02o_*): better from 1e3 contigs on, 3.8x at 1e6; few-contig genomes keep the closed form
 //   slide: 0 auto, 1 never use the sliding-tile kernel (k_slide), 2 use it whenever it fits shared memory (any W <= 1048)
 static int g_tune_slide = 0;
 
@@ -268,6 +271,7 @@ struct Layout {
 	size_t segs_off, off_off, siteoff_off, gpart_off, units_off, pre_off, bounds_off, stage_off, outs_off, tileseg_off, total;
 	uint64_t tileseg_cap;   // entries of the tile -> segment table (0 = not used: few segments)
 	bool hgw;               // level 2 in scan mode
+	bool unit_table;        // very many segments: level 1 reads unit starts from a table (k_unit_starts) instead of the segment records
 	bool slide;             // fine steps: windows straight from the sites (k_slide), no unit array
 	bool persite;           // W = S = 1: elementwise (k_windows_persite), no unit array
 	uint32_t slide_stages;
@@ -432,7 +436,9 @@ static int make_layout(const pgt_plan* plan, const pgt_range* range, pgt_stat st
 		L->blk_hi = s1.blk_base + (L->u_hi - 1 - s1.unit_base) / plan->g.wunits + 1;
 	}
 	L->bounds_off = o;
-	if (plan->mode == PGT_MODE_BP) o += align_up((size_t)(nunits + 1) * sizeof(uint64_t), 256);
+	L->unit_table = plan->mode == PGT_MODE_SITES && mem == PGT_MEM_DEVICE && nunits > 0 &&
+	                (g_tune_unittable == 2 || (g_tune_unittable == 0 && plan->segs.size() >= kUnitTableMinSegs));
+	if (plan->mode == PGT_MODE_BP || L->unit_table) o += align_up((size_t)(nunits + 1) * sizeof(uint64_t), 256);
 	L->stage_off = o;
 	L->outs_off = o;
 	if (mem == PGT_MEM_HOST) {
@@ -501,6 +507,7 @@ extern "C" int pgt_tune(const char* key, int value) {
 	if (key && strcmp(key, "level1") == 0) g_tune_level1 = value;
 	else if (key && strcmp(key, "level2") == 0 && value >= 0 && value <= 2) g_tune_level2 = value;
 	else if (key && strcmp(key, "slide") == 0 && value >= 0 && value <= 2) g_tune_slide = value;
+	else if (key && strcmp(key, "unittable") == 0 && value >= 0 && value <= 2) g_tune_unittable = value;
 	else if (key && strcmp(key, "stages") == 0 && value >= 2 && value <= kTileMaxStages) g_tune_stages = value;
 	else if (key && strcmp(key, "stage_kb") == 0 && value >= 8 && value <= 110) g_tune_stage_kb = value;
 	else if (key && strcmp(key, "xgroup") == 0 && (value == 0 || value == 4 || value == 8 || value == 16 || value == 32)) g_tune_xgroup = value;
@@ -903,7 +910,7 @@ static int run_scan(const pgt_plan* plan, const pgt_range* range, pgt_stat stat,
 	P.mode = (int)plan->mode;
 
 	typename Stat::Acc* units = (typename Stat::Acc*)(ws + L.units_off);
-	uint64_t* bounds = bp ? (uint64_t*)(ws + L.bounds_off) : nullptr;
+	uint64_t* bounds = (bp || L.unit_table) ? (uint64_t*)(ws + L.bounds_off) : nullptr;
 	uint64_t ndata = 0;  // bp mode: sites the columns hold
 	if (bp) {
 		if (site_offsets[P.ncontig] < L.origin) return pgt_set_error(PGT_ERR_ARGS, "site_origin beyond the last site");
@@ -950,6 +957,12 @@ static int run_scan(const pgt_plan* plan, const pgt_range* range, pgt_stat stat,
 			return PGT_OK;
 		}
 		if (bp && nunits) PGT_TRY(launch_bounds_kernel(P, cols->pos, ndata, bounds, st));
+		if (L.unit_table) {  // very many segments: unit starts once, then the INDIRECT level-1 kernels
+			const uint64_t want = (nunits + 256) / 256, cap = (uint64_t)num_sms() * 8;
+			k_unit_starts<<<(unsigned)(want < cap ? want : cap), 256, 0, st>>>(P, bounds);
+			g_launches++;
+			PGT_CUDA(cudaGetLastError());
+		}
 		// elements the caller's columns are known to hold: up to the end of the last unit read
 		const uint64_t valid = bp ? ndata : pgt_plan_unit_start(plan, L.u_hi) - L.origin;
 		P.col_elems = valid;

@@ -195,3 +195,41 @@ def test_many_contigs_tile_segment_table(pgt, W, S):
     for k in tiled:
         assert np.concatenate([p[k] for p in parts]).tobytes() == tiled[k].tobytes(), "shards " + k
         assert host[k].tobytes() == tiled[k].tobytes(), "host " + k
+
+
+@pytest.mark.parametrize("W,S,unit", [(1000, 1000, 0), (5000, 1000, 512), (100, 10, 0), (300, 300, 32), (100000, 100000, 4096)])
+def test_unit_start_table_gives_the_same_bits(pgt, W, S, unit):
+    """Plans of more than 32 segments (device mode; pgt_tune unittable = 1 / 2 turns it off / on) let level 1 read unit starts from a table
+    written by k_unit_starts and run the INDIRECT kernels (the ones bp mode uses) instead of deriving every unit from
+    its segment record: same units, same lanes, so every statistic must come out bit for bit, through the tiled and
+    the direct level-1 kernels, unsharded and sharded."""
+    rng = np.random.default_rng(W * 7 + S)
+    lengths = rng.integers(1, 700, size=1500).tolist() + [1, 2, W, W + S, 3 * W + 1]
+    offs = offsets(lengths)
+    n = int(offs[-1])
+    a, b = pgt.synth_fst(9, 0, n)
+    g = pgt.synth_het(9, 0, n)
+    f1, f2, n1, n2 = pgt.synth_dxy(9, 0, n)
+    pos = pgt.synth_pos(9, 0, n, offs, 1)
+    plan = pgt.WindowPlan(offs, W, S, unit_sites=unit)
+    args = (pos, a, b, g, f1, f2, n1, n2)
+    try:
+        for l1 in (0, 1, 2):
+            pgt.tune("level1", l1)
+            pgt.tune("unittable", 1)
+            ref = npy(pgt.fused_window(plan, *args, minind=5))
+            pgt.tune("unittable", 2)
+            tab = npy(pgt.fused_window(plan, *args, minind=5))
+            for k in ref:
+                assert tab[k].tobytes() == ref[k].tobytes(), (l1, k)
+            parts = []
+            for r in range(4):
+                wl, wh, sl, sh = plan.shard(r, 4)
+                if wh > wl:
+                    parts.append(npy(pgt.fused_window(plan, *[x[sl:sh] for x in args], minind=5, window_range=(wl, wh), site_origin=sl)))
+            for k in ref:
+                if k != "dxy_global":
+                    assert np.concatenate([p[k] for p in parts]).tobytes() == ref[k].tobytes(), (l1, "shards", k)
+    finally:
+        pgt.tune("level1", 0)
+        pgt.tune("unittable", 0)
