@@ -778,6 +778,24 @@ static int launch_slide(const pgt_plan* plan, pgt_stat stat, const DevPlan& P, c
 		tc.col_off[c] = sh.col_off[c];
 		tc.col_cap[c] = sh.col_cap[c];
 	}
+	SlideCfg sc;
+	memset(&sc, 0, sizeof(sc));
+	sc.E = sh.E;
+	sc.wpb = sh.wpb;
+	sc.G = sh.G;
+	sc.wp = sh.wp;
+	sc.sf_off = sh.sf_off;
+	sc.pr_off = sh.pr_off;
+	sc.pos_off = sh.pos_off;
+	sc.pos_col = pos ? scol.n : 0xffffffffu;
+	sc.stage_off = sh.stage_off;
+	// chunks: ~4 per resident CTA for balance, but long enough (>= 32 steps of windows) that the W - S sites
+	// shared with the next chunk stay a few percent of what a chunk reads
+	const uint64_t wps = ((uint64_t)sh.G * plan->g.W + plan->g.S - 1) / plan->g.S;  // windows starting in one step
+	auto set_chunks = [&](uint64_t slots) {
+		sc.chunk_windows = std::max<uint64_t>(32 * wps, (nwin + slots * 4 - 1) / (slots * 4));
+		sc.nchunks = (nwin + sc.chunk_windows - 1) / sc.chunk_windows;
+	};
 	void (*kern)(DevPlan, TileCfg, SlideCfg, pgt_windows);
 	if (sh.G > 1) {
 		if (sh.E <= 2) kern = k_slide<Stat, 2, true>;
@@ -793,22 +811,7 @@ static int launch_slide(const pgt_plan* plan, pgt_stat stat, const DevPlan& P, c
 	PGT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kSlideThreads, sh.smem));
 	if (per_sm < 1) per_sm = 1;
 	const uint64_t slots = (uint64_t)num_sms() * per_sm;
-	// chunks: ~4 per resident CTA for balance, but long enough (>= 32 steps of windows) that the W - S sites
-	// shared with the next chunk stay a few percent of what a chunk reads
-	const uint64_t wpb = ((uint64_t)sh.G * plan->g.W + plan->g.S - 1) / plan->g.S;  // windows starting in one step
-	SlideCfg sc;
-	memset(&sc, 0, sizeof(sc));
-	sc.E = sh.E;
-	sc.wpb = sh.wpb;
-	sc.G = sh.G;
-	sc.wp = sh.wp;
-	sc.sf_off = sh.sf_off;
-	sc.pr_off = sh.pr_off;
-	sc.pos_off = sh.pos_off;
-	sc.pos_col = pos ? scol.n : 0xffffffffu;
-	sc.stage_off = sh.stage_off;
-	sc.chunk_windows = std::max<uint64_t>(32 * wpb, (nwin + slots * 4 - 1) / (slots * 4));
-	sc.nchunks = (nwin + sc.chunk_windows - 1) / sc.chunk_windows;
+	set_chunks(slots);
 	const unsigned grid = (unsigned)std::min<uint64_t>(sc.nchunks, slots);
 	{
 		ProfScope prof(0, st);

@@ -81,8 +81,6 @@ __device__ __forceinline__ Acc shfl_down_acc(const Acc& v, unsigned delta) {
 	return r;
 }
 
-__device__ __forceinline__ void slide_bar() { asm volatile("bar.sync 1, %0;" ::"n"(kSlideConsumers) : "memory"); }
-
 // the part of a chunk that lies in one segment: windows [ka, kb) of segment `sg` (segment-local), reading
 // the segment-local sites [lo, hi)
 struct SlideRun {
@@ -119,54 +117,37 @@ template <>
 struct SlideMinBlocks<FusedStat> {
 	static constexpr int value = 1;
 };
-// MULTI = several blocks per step (G > 1, W <= 512); with one block per step the team arithmetic folds away
+// The crew of 7 consumer warps: scans the staged blocks and emits the windows (the whole job of k_slide's consumers).
+// (A variant with THREE crews per CTA for the fused statistic -- fst, dxy and het each with its own arrays and named
+// barrier over the same staged block, 22 warps per SM instead of 8 -- was built and measured: bit-identical, but at 80
+// registers per thread it spills ~420 bytes and came out +7 % at S = 1 and -13 % at S = 7: dropped)
+struct SlideCrew {
+	uint32_t t;          // thread inside the crew (0..223)
+	uint32_t warp;       // warp inside the crew (0..6)
+	uint32_t bar_id;     // named barrier of the crew
+	uint32_t col_shift;  // first staged column of the crew's statistic
+	bool common;         // the crew writes what all statistics share: label, positions, nsites
+	void* wt;            // shared memory: warp totals, SUF [2][G * wp], PRE [G * wp], positions [2][G * wp]
+	void* sf;
+	void* pr;
+	uint32_t* pos;
+};
+
+__device__ __forceinline__ void slide_bar(uint32_t id) { asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(kSlideConsumers) : "memory"); }
+
 template <class Stat, int EMAX, bool MULTI>
-__global__ void __launch_bounds__(kSlideThreads, SlideMinBlocks<Stat>::value) k_slide(DevPlan P, TileCfg tc, SlideCfg sc, pgt_windows out) {
+__device__ __forceinline__ void slide_consume(const DevPlan& P, const TileCfg& tc, const SlideCfg& sc, const pgt_windows& out, TileCtl* ctl,
+                                              const SlideCrew& crew) {
 	typedef typename Stat::Acc Acc;
-	extern __shared__ __align__(128) unsigned char smem[];
-	TileCtl* ctl = reinterpret_cast<TileCtl*>(smem);
-	Acc* wt = reinterpret_cast<Acc*>(smem + kTileCtlBytes);
-	Acc* SfBase = reinterpret_cast<Acc*>(smem + sc.sf_off);           // SUF of the step's blocks: [2][G * wp], by step parity
-	Acc* Pr = reinterpret_cast<Acc*>(smem + sc.pr_off);               // PRE of the step's blocks: [G * wp]
-	uint32_t* PosBase = reinterpret_cast<uint32_t*>(smem + sc.pos_off);  // positions of the step's blocks: [2][G * wp]
-	unsigned char* stages = smem + sc.stage_off;
-	const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+	Acc* wt = reinterpret_cast<Acc*>(crew.wt);
+	Acc* SfBase = reinterpret_cast<Acc*>(crew.sf);
+	Acc* Pr = reinterpret_cast<Acc*>(crew.pr);
+	uint32_t* PosBase = crew.pos;
 	const uint64_t W = P.g.W, S = P.g.S;
 	const uint32_t Wu = P.g.W, Su = P.g.S, G = MULTI ? sc.G : 1u, gw = G * sc.wp;
 	const uint32_t wpb = MULTI ? sc.wpb : (uint32_t)kSlideWarps;
-	const bool has_pos = sc.pos_col != 0xffffffffu;
-
-	if (threadIdx.x == 0) {
-		for (uint32_t s = 0; s < tc.nstages; ++s) {
-			mbar_init(&ctl->full[s], 2);
-			mbar_init(&ctl->empty[s], kSlideWarps);
-		}
-		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-	}
-	__syncthreads();
-
-	if (warp == kSlideWarps) {
-		// ------------------------------------------------------------------ producer: one stage per step (G blocks)
-		uint32_t it = 0;
-		for (uint64_t c = blockIdx.x; c < sc.nchunks; c += gridDim.x) {
-			const uint64_t wa = P.win_lo + c * sc.chunk_windows;
-			const uint64_t wb = P.win_hi - wa < sc.chunk_windows ? P.win_hi : wa + sc.chunk_windows;
-			SlideRun r;
-			for (bool ok = slide_run_at(P, wa, wb, r, true); ok; ok = slide_run_at(P, r.sg.win_base + r.kb, wb, r, false)) {
-				for (uint64_t b = r.lo / W; b * W < r.hi; b += G, ++it) {
-					const uint64_t x0 = b * W > r.lo ? b * W : r.lo;
-					const uint64_t x1 = (b + G) * W < r.hi ? (b + G) * W : r.hi;
-					const uint32_t stg = it % tc.nstages;
-					if (it >= tc.nstages) mbar_wait(&ctl->empty[stg], ((it / tc.nstages) - 1u) & 1u);
-					producer_fill_stage(tc, ctl, stages, stg, r.sg.site_base + x0 - P.site_origin, r.sg.site_base + x1 - P.site_origin, lane);
-				}
-			}
-		}
-		return;
-	}
-
-	// ---------------------------------------------------------------------- consumers
-	const uint32_t t = threadIdx.x;
+	const bool has_pos = crew.common && sc.pos_col != 0xffffffffu;
+	const uint32_t t = crew.t, warp = crew.warp, lane = crew.t & 31u;
 	const uint32_t team = MULTI ? warp / wpb : 0u;  // which block of a step this thread works on (>= G: none)
 	const uint32_t tw = warp - team * wpb;          // warp inside its team
 	const uint32_t e0 = (tw * 32u + lane) * sc.E;   // first element of the block this thread owns
@@ -203,7 +184,7 @@ __global__ void __launch_bounds__(kSlideThreads, SlideMinBlocks<Stat>::value) k_
 				{
 					const char* cp[kMaxTileCols];
 #pragma unroll
-					for (int cc = 0; cc < kMaxTileCols; ++cc) cp[cc] = ctl->cp[stg][cc];
+					for (int cc = 0; cc < kMaxTileCols; ++cc) cp[cc] = cc + (int)crew.col_shift < kMaxStageCols ? ctl->cp[stg][cc + crew.col_shift] : nullptr;
 					const uint32_t* pstage = has_pos ? reinterpret_cast<const uint32_t*>(ctl->cp[stg][sc.pos_col]) : nullptr;
 					const uint64_t x0 = b * W > r.lo ? b * W : r.lo;            // first staged site
 					const uint64_t x1 = (b + gi) * W < r.hi ? (b + gi) * W : r.hi;
@@ -242,7 +223,7 @@ __global__ void __launch_bounds__(kSlideThreads, SlideMinBlocks<Stat>::value) k_
 					}
 					if (lane == 31u) wt[warp] = up;  // the warp's total, forward order
 				}
-				slide_bar();  // warp totals visible; every thread has left the emit phase of the step before
+				slide_bar(crew.bar_id);  // warp totals visible; every thread has left the emit phase of the step before
 				{
 					Acc bpre = Stat::zero(), bsuf = Stat::zero();
 #pragma unroll
@@ -273,7 +254,7 @@ __global__ void __launch_bounds__(kSlideThreads, SlideMinBlocks<Stat>::value) k_
 						}
 					}
 				}
-				slide_bar();  // PRE, SUF and the positions of the step's blocks complete
+				slide_bar(crew.bar_id);  // PRE, SUF and the positions of the step's blocks complete
 				{
 					// windows that start in blocks [eb_lo, eb_hi]; everything below is relative to the start of block b - 1
 					const uint64_t eb_lo = b > m_first ? b - 1 : b;
@@ -325,8 +306,8 @@ __global__ void __launch_bounds__(kSlideThreads, SlideMinBlocks<Stat>::value) k_
 								++lc;
 								lc_end = P.off[lc + 1];
 							}
-							if (out.label) out.label[o] = lc;
-							if (out.nsites) out.nsites[o] = lr - rel + 1u;
+							if (crew.common && out.label) out.label[o] = lc;
+							if (crew.common && out.nsites) out.nsites[o] = lr - rel + 1u;
 							if (has_pos) {
 								const uint32_t* ps = blk == 0u ? PosPrev : Pos + boff;  // positions of the window's first block
 								const uint32_t sp = ps[j];
@@ -343,6 +324,58 @@ __global__ void __launch_bounds__(kSlideThreads, SlideMinBlocks<Stat>::value) k_
 			}
 		}
 	}
+}
+
+// The producer warp of a sliding-tile CTA: one stage per step (G blocks) of every chunk this CTA walks.
+__device__ __forceinline__ void slide_produce(const DevPlan& P, const TileCfg& tc, const SlideCfg& sc, TileCtl* ctl, unsigned char* stages,
+                                              uint32_t G, uint32_t lane) {
+	const uint64_t W = P.g.W;
+	uint32_t it = 0;
+	for (uint64_t c = blockIdx.x; c < sc.nchunks; c += gridDim.x) {
+		const uint64_t wa = P.win_lo + c * sc.chunk_windows;
+		const uint64_t wb = P.win_hi - wa < sc.chunk_windows ? P.win_hi : wa + sc.chunk_windows;
+		SlideRun r;
+		for (bool ok = slide_run_at(P, wa, wb, r, true); ok; ok = slide_run_at(P, r.sg.win_base + r.kb, wb, r, false)) {
+			for (uint64_t b = r.lo / W; b * W < r.hi; b += G, ++it) {
+				const uint64_t x0 = b * W > r.lo ? b * W : r.lo;
+				const uint64_t x1 = (b + G) * W < r.hi ? (b + G) * W : r.hi;
+				const uint32_t stg = it % tc.nstages;
+				if (it >= tc.nstages) mbar_wait(&ctl->empty[stg], ((it / tc.nstages) - 1u) & 1u);
+				producer_fill_stage(tc, ctl, stages, stg, r.sg.site_base + x0 - P.site_origin, r.sg.site_base + x1 - P.site_origin, lane);
+			}
+		}
+	}
+}
+
+// MULTI = several blocks per step (G > 1, W <= 512); with one block per step the team arithmetic folds away
+template <class Stat, int EMAX, bool MULTI>
+__global__ void __launch_bounds__(kSlideThreads, SlideMinBlocks<Stat>::value) k_slide(DevPlan P, TileCfg tc, SlideCfg sc, pgt_windows out) {
+	extern __shared__ __align__(128) unsigned char smem[];
+	TileCtl* ctl = reinterpret_cast<TileCtl*>(smem);
+	const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+	if (threadIdx.x == 0) {
+		for (uint32_t s = 0; s < tc.nstages; ++s) {
+			mbar_init(&ctl->full[s], 2);
+			mbar_init(&ctl->empty[s], kSlideWarps);
+		}
+		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+	}
+	__syncthreads();
+	if (warp == kSlideWarps) {
+		slide_produce(P, tc, sc, ctl, smem + sc.stage_off, MULTI ? sc.G : 1u, lane);
+		return;
+	}
+	SlideCrew crew;
+	crew.t = threadIdx.x;
+	crew.warp = warp;
+	crew.bar_id = 1;
+	crew.col_shift = 0;
+	crew.common = true;
+	crew.wt = smem + kTileCtlBytes;
+	crew.sf = smem + sc.sf_off;    // SUF of the step's blocks: [2][G * wp], by step parity
+	crew.pr = smem + sc.pr_off;    // PRE of the step's blocks: [G * wp]
+	crew.pos = reinterpret_cast<uint32_t*>(smem + sc.pos_off);  // positions of the step's blocks: [2][G * wp]
+	slide_consume<Stat, EMAX, MULTI>(P, tc, sc, out, ctl, crew);
 }
 
 // dxyWindow's global line (dxyWindow.cpp:382-385,429-433) over the unit partials [0, n): one
