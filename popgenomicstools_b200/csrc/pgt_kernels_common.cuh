@@ -234,6 +234,35 @@ struct FusedStat {
 	}
 };
 
+// --- fst + het together: what one of the two crews of the fused sliding tile computes (pgt_slide.cuh); every
+// component is folded, combined and emitted exactly as by FstStat / HetStat alone.  Staged columns as FusedStat.
+struct FstHetStat {
+	struct Acc {
+		FstStat::Acc fst;
+		HetStat::Acc het;
+	};
+	struct Site {
+		FstStat::Site fst;
+		HetStat::Site het;
+	};
+	static __device__ __forceinline__ Acc zero() { return Acc{FstStat::zero(), HetStat::zero()}; }
+	static __device__ __forceinline__ Site load_tile(const char* const* cp, uint32_t i) {
+		return Site{FstStat::load_tile(cp, i), HetStat::load_tile(cp + 6, i)};
+	}
+	static __device__ __forceinline__ void fold(Acc& acc, const Site& s, int minind) {
+		FstStat::fold(acc.fst, s.fst, minind);
+		HetStat::fold(acc.het, s.het, minind);
+	}
+	static __device__ __forceinline__ void add(Acc& acc, const Acc& o) {
+		FstStat::add(acc.fst, o.fst);
+		HetStat::add(acc.het, o.het);
+	}
+	static __device__ __forceinline__ void emit(const pgt_windows& out, uint64_t o, const Acc& acc) {
+		FstStat::emit(out, o, acc.fst);
+		HetStat::emit(out, o, acc.het);
+	}
+};
+
 template <class Stat>
 __device__ __forceinline__ typename Stat::Acc warp_butterfly(typename Stat::Acc acc) {
 #pragma unroll

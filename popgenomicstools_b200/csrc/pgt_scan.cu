@@ -210,6 +210,8 @@ extern int g_tune_xgroup;          // extreme scan (pgt_extreme.cu): lanes per u
 //   unittable: 0 auto (unit-start table for plans of more than 32 segments, device mode), 1 never, 2 always
 static int g_tune_unittable = 0;
 static constexpr size_t kUnitTableMinSegs = 33;  // measured (profiles/r02o_*): better from 1e3 contigs on, 3.8x at 1e6; few-contig genomes keep the closed form
+//   fused2: 0 auto (fused sliding tile with one block per step: two crews, k_slide_fused2), 1 the single-crew k_slide<FusedStat>
+static int g_tune_fused2 = 0;
 //   slide: 0 auto, 1 never use the sliding-tile kernel (k_slide), 2 use it whenever it fits shared memory (any W <= 1048)
 static int g_tune_slide = 0;
 
@@ -507,6 +509,7 @@ extern "C" int pgt_tune(const char* key, int value) {
 	if (key && strcmp(key, "level1") == 0) g_tune_level1 = value;
 	else if (key && strcmp(key, "level2") == 0 && value >= 0 && value <= 2) g_tune_level2 = value;
 	else if (key && strcmp(key, "slide") == 0 && value >= 0 && value <= 2) g_tune_slide = value;
+	else if (key && strcmp(key, "fused2") == 0 && value >= 0 && value <= 1) g_tune_fused2 = value;
 	else if (key && strcmp(key, "unittable") == 0 && value >= 0 && value <= 2) g_tune_unittable = value;
 	else if (key && strcmp(key, "stages") == 0 && value >= 2 && value <= kTileMaxStages) g_tune_stages = value;
 	else if (key && strcmp(key, "stage_kb") == 0 && value >= 8 && value <= 110) g_tune_stage_kb = value;
@@ -796,6 +799,33 @@ static int launch_slide(const pgt_plan* plan, pgt_stat stat, const DevPlan& P, c
 		sc.chunk_windows = std::max<uint64_t>(32 * wps, (nwin + slots * 4 - 1) / (slots * 4));
 		sc.nchunks = (nwin + sc.chunk_windows - 1) / sc.chunk_windows;
 	};
+	if constexpr (std::is_same<Stat, FusedStat>::value) {
+		if (sh.G == 1 && g_tune_fused2 != 1) {
+			// two crews (fst + het, dxy) share the staged block; their SUF / PRE arrays partition the fused ones
+			SlideCfg2 s2;
+			const uint32_t part[2] = {24u, 16u};  // accumulator bytes per site: FstHetStat, DxyStat
+			uint32_t so = sh.sf_off, po = sh.pr_off;
+			for (int c = 0; c < 2; ++c) {
+				s2.wt_off[c] = kTileCtlBytes + 256u * c;
+				s2.sf_off[c] = so;
+				s2.pr_off[c] = po;
+				so += 2u * sh.wp * part[c];
+				po += sh.wp * part[c];
+			}
+			void (*k2)(DevPlan, TileCfg, SlideCfg, SlideCfg2, pgt_windows) =
+			    sh.E <= 4 ? k_slide_fused2<4> : (sh.E == 5 ? k_slide_fused2<5> : k_slide_fused2<6>);
+			PGT_CUDA(cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh.smem));
+			const uint64_t slots = (uint64_t)num_sms();
+			set_chunks(slots);
+			{
+				ProfScope prof(0, st);
+				k2<<<(unsigned)std::min<uint64_t>(sc.nchunks, slots), kSlide2Threads, sh.smem, st>>>(P, tc, sc, s2, out);
+			}
+			g_launches++;
+			PGT_CUDA(cudaGetLastError());
+			return PGT_OK;
+		}
+	}
 	void (*kern)(DevPlan, TileCfg, SlideCfg, pgt_windows);
 	if (sh.G > 1) {
 		if (sh.E <= 2) kern = k_slide<Stat, 2, true>;

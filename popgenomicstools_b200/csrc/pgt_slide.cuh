@@ -117,10 +117,9 @@ template <>
 struct SlideMinBlocks<FusedStat> {
 	static constexpr int value = 1;
 };
-// The crew of 7 consumer warps: scans the staged blocks and emits the windows (the whole job of k_slide's consumers).
-// (A variant with THREE crews per CTA for the fused statistic -- fst, dxy and het each with its own arrays and named
-// barrier over the same staged block, 22 warps per SM instead of 8 -- was built and measured: bit-identical, but at 80
-// registers per thread it spills ~420 bytes and came out +7 % at S = 1 and -13 % at S = 7: dropped)
+// A crew of 7 consumer warps: scans the staged blocks and emits the windows of ONE statistic (the whole job of
+// k_slide's consumers).  The fused scan with one block per step runs TWO crews per CTA over the same staged block
+// (k_slide_fused2: fst + het, and dxy), each with its own shared-memory arrays and named barrier.
 struct SlideCrew {
 	uint32_t t;          // thread inside the crew (0..223)
 	uint32_t warp;       // warp inside the crew (0..6)
@@ -376,6 +375,53 @@ __global__ void __launch_bounds__(kSlideThreads, SlideMinBlocks<Stat>::value) k_
 	crew.pr = smem + sc.pr_off;    // PRE of the step's blocks: [G * wp]
 	crew.pos = reinterpret_cast<uint32_t*>(smem + sc.pos_off);  // positions of the step's blocks: [2][G * wp]
 	slide_consume<Stat, EMAX, MULTI>(P, tc, sc, out, ctl, crew);
+}
+
+// The fused statistic with one block per step (W > 512) as two crews of 7 warps: crew 0 scans fst + het (staged columns
+// a, b, geno: 24-byte accumulators) and also writes label, positions and nsites; crew 1 scans dxy (f1, f2, n1, n2: 16
+// bytes).  They read the same staged block and keep their own SUF / PRE arrays (24 + 16 = the 40 bytes per site of the
+// fused accumulator), named barriers 1 and 2.  16 warps per SM instead of 8 at 128 registers per thread instead of 190,
+// and every column of the table holds exactly the bits of its single-statistic scan.  A stage drains when all 14
+// consumer warps have taken their sites into registers.  (Three crews -- fst, dxy, het: 22 warps, 80 registers -- spilled
+// ~420 bytes per thread and gained nothing: DESIGN.md section 12.)
+struct SlideCfg2 {
+	uint32_t wt_off[2], sf_off[2], pr_off[2];
+};
+static constexpr int kSlide2Threads = 2 * kSlideConsumers + 32;
+template <int EMAX>
+__global__ void __launch_bounds__(kSlide2Threads, 1) k_slide_fused2(DevPlan P, TileCfg tc, SlideCfg sc, SlideCfg2 s2, pgt_windows out) {
+	extern __shared__ __align__(128) unsigned char smem[];
+	TileCtl* ctl = reinterpret_cast<TileCtl*>(smem);
+	const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+	if (threadIdx.x == 0) {
+		for (uint32_t s = 0; s < tc.nstages; ++s) {
+			mbar_init(&ctl->full[s], 2);
+			mbar_init(&ctl->empty[s], 2 * kSlideWarps);
+		}
+		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+	}
+	__syncthreads();
+	if (warp == 2 * kSlideWarps) {
+		slide_produce(P, tc, sc, ctl, smem + sc.stage_off, 1u, lane);
+		return;
+	}
+	const uint32_t ci = warp / kSlideWarps;  // 0: fst + het, 1: dxy
+	SlideCrew crew;
+	crew.t = threadIdx.x - ci * kSlideConsumers;
+	crew.warp = warp - ci * kSlideWarps;
+	crew.col_shift = ci == 0 ? 0u : 2u;
+	crew.common = ci == 0;
+	crew.wt = smem + s2.wt_off[ci];
+	crew.sf = smem + s2.sf_off[ci];
+	crew.pr = smem + s2.pr_off[ci];
+	crew.pos = reinterpret_cast<uint32_t*>(smem + sc.pos_off);
+	if (ci == 0) {
+		crew.bar_id = 1;
+		slide_consume<FstHetStat, EMAX, false>(P, tc, sc, out, ctl, crew);
+	} else {
+		crew.bar_id = 2;
+		slide_consume<DxyStat, EMAX, false>(P, tc, sc, out, ctl, crew);
+	}
 }
 
 // dxyWindow's global line (dxyWindow.cpp:382-385,429-433) over the unit partials [0, n): one
