@@ -146,7 +146,10 @@ struct HetStat {
 	static __device__ __forceinline__ void emit(const pgt_windows& out, uint64_t o, const Acc& acc) {
 		if (out.nhet) out.nhet[o] = acc.nhet;
 		if (out.nonmissing) out.nonmissing[o] = acc.nonmissing;
-		if (out.het) out.het[o] = acc.nonmissing != 0 ? __ddiv_rn((double)acc.nhet, (double)acc.nonmissing) : 0.0;
+		// (one non-missing site -- every window of the tools' default W = S = 1 -- divides by 1: the ~40-instruction IEEE
+		// division is skipped, the value is the same)
+		if (out.het)
+			out.het[o] = acc.nonmissing > 1u ? __ddiv_rn((double)acc.nhet, (double)acc.nonmissing) : (acc.nonmissing ? (double)acc.nhet : 0.0);
 	}
 };
 

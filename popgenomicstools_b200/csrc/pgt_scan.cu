@@ -212,6 +212,8 @@ static int g_tune_unittable = 0;
 static constexpr size_t kUnitTableMinSegs = 33;  // measured (profiles/r02o_*): better from 1e3 contigs on, 3.8x at 1e6; few-contig genomes keep the closed form
 //   fused2: 0 auto (fused sliding tile with one block per step: two crews, k_slide_fused2), 1 the single-crew k_slide<FusedStat>
 static int g_tune_fused2 = 0;
+//   persite: 0 auto (W = S = 1: four windows per thread with 128-bit accesses when everything is aligned), 1 always the scalar kernel
+static int g_tune_persite = 0;
 //   slide: 0 auto, 1 never use the sliding-tile kernel (k_slide), 2 use it whenever it fits shared memory (any W <= 1048)
 static int g_tune_slide = 0;
 
@@ -223,6 +225,17 @@ static int num_sms() {
 }
 
 static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+// Grid of a grid-stride kernel: the blocks that are resident at once (one wave), or fewer when the work is small.
+// (A fixed cap of 8 blocks per SM launched the per-site kernel -- 6 resident blocks at 40 registers -- as one full wave
+// plus a third of one: ncu "waves per SM 1.33", profiles/r02h_persite_ncu_details.txt.)
+template <class K>
+static unsigned one_wave_grid(K kern, int threads, uint64_t want_blocks) {
+	int per_sm = 0;
+	if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, 0) != cudaSuccess || per_sm < 1) per_sm = 1;
+	const uint64_t cap = (uint64_t)num_sms() * per_sm;
+	return (unsigned)(want_blocks < cap ? (want_blocks ? want_blocks : 1) : cap);
+}
 
 #include "pgt_kernels_common.cuh"
 #include "pgt_level1.cuh"
@@ -510,6 +523,7 @@ extern "C" int pgt_tune(const char* key, int value) {
 	else if (key && strcmp(key, "level2") == 0 && value >= 0 && value <= 2) g_tune_level2 = value;
 	else if (key && strcmp(key, "slide") == 0 && value >= 0 && value <= 2) g_tune_slide = value;
 	else if (key && strcmp(key, "fused2") == 0 && value >= 0 && value <= 1) g_tune_fused2 = value;
+	else if (key && strcmp(key, "persite") == 0 && value >= 0 && value <= 1) g_tune_persite = value;
 	else if (key && strcmp(key, "unittable") == 0 && value >= 0 && value <= 2) g_tune_unittable = value;
 	else if (key && strcmp(key, "stages") == 0 && value >= 2 && value <= kTileMaxStages) g_tune_stages = value;
 	else if (key && strcmp(key, "stage_kb") == 0 && value >= 8 && value <= 110) g_tune_stage_kb = value;
@@ -852,6 +866,47 @@ static int launch_slide(const pgt_plan* plan, pgt_stat stat, const DevPlan& P, c
 	return PGT_OK;
 }
 
+// W = S = 1: the vectorised kernel when its preconditions hold (one segment; every used column and output pointer
+// 16-byte aligned at the scan's first window -- 4-byte aligned for the genotype column), else the scalar one.
+template <class Stat>
+static int launch_persite(const pgt_plan* plan, pgt_stat stat, const DevPlan& P, const Cols& C, const pgt_windows& out, cudaStream_t st) {
+	const uint64_t nwin = P.win_hi - P.win_lo;
+	if (nwin == 0) return PGT_OK;
+	bool vec = g_tune_persite != 1 && plan->segs.size() == 1 && nwin >= 4;
+	uint64_t site0 = 0;
+	if (vec) {
+		site0 = plan->segs[0].site_base + (P.win_lo - plan->segs[0].win_base) - P.site_origin;
+		auto ok = [&](const void* p, size_t elem, size_t align) { return !p || (((uintptr_t)p + site0 * elem) & (align - 1)) == 0; };
+		ColDesc d[8];
+		pgt_columns pc;
+		memset(&pc, 0, sizeof(pc));
+		pc.a = C.a;
+		pc.b = C.b;
+		pc.geno = C.g;
+		pc.f1 = C.f1;
+		pc.f2 = C.f2;
+		pc.n1 = C.n1;
+		pc.n2 = C.n2;
+		const int nc = stat_columns(stat, PGT_MODE_SITES, &pc, d);
+		for (int i = 0; i < nc; ++i) vec = vec && d[i].ptr && ok(d[i].ptr, d[i].elem, d[i].elem == 1 ? 4 : 16);
+		vec = vec && ok(C.pos, 4, 16);
+		const void* outs[14] = {out.label, out.start_pos, out.end_pos, out.mid_pos, out.nsites, out.sum_a, out.sum_b, out.fst,
+		                        out.nhet, out.nonmissing, out.het, out.dxy, out.neffective, out.nskip};
+		for (const void* p : outs) vec = vec && (((uintptr_t)p) & 15) == 0;
+	}
+	ProfScope prof(1, st);
+	if (vec) {
+		const unsigned grid = one_wave_grid(k_windows_persite4<Stat>, 256, (nwin + 1023) / 1024);
+		k_windows_persite4<Stat><<<grid, 256, 0, st>>>(P, C, out, site0);
+	} else {
+		const unsigned grid = one_wave_grid(k_windows_persite<Stat>, 256, (nwin + 1023) / 1024);  // four windows per thread and turn
+		k_windows_persite<Stat><<<grid, 256, 0, st>>>(P, C, out);
+	}
+	g_launches++;
+	PGT_CUDA(cudaGetLastError());
+	return PGT_OK;
+}
+
 // dxyWindow's global line straight from the columns (scans without a unit array)
 static int launch_global_sites(const Cols& cols, uint64_t i0, uint64_t i1, double* scratch, double* g3, cudaStream_t st) {
 	k_global_sites<<<kGlobalBlocks, 1024, 0, st>>>(cols, i0, i1, scratch);
@@ -973,11 +1028,7 @@ static int run_scan(const pgt_plan* plan, const pgt_range* range, pgt_stat stat,
 				P.col_elems = last_site + 1 - L.origin;
 			}
 			if (nwin && L.persite) {
-				const uint64_t want = (nwin + 255) / 256, cap = (uint64_t)num_sms() * 8;
-				ProfScope prof(1, st);
-				k_windows_persite<Stat><<<(unsigned)(want < cap ? want : cap), 256, 0, st>>>(P, C, *out);
-				g_launches++;
-				PGT_CUDA(cudaGetLastError());
+				PGT_TRY(launch_persite<Stat>(plan, stat, P, C, *out, st));
 			} else if (nwin) {
 				uint64_t last;
 				pgt_plan_window(plan, L.w_hi - 1, nullptr, &last, nullptr);
@@ -1183,11 +1234,7 @@ static int run_scan(const pgt_plan* plan, const pgt_range* range, pgt_stat stat,
 			Ps.col_elems = ns;
 			const pgt_windows o = device_table(slot);  // rewritten two slabs later, after this slab's copy-back (order of `st`)
 			if (L.persite) {
-				const uint64_t want = (wb - w + 255) / 256, cap = (uint64_t)num_sms() * 8;
-				ProfScope prof(1, st);
-				k_windows_persite<Stat><<<(unsigned)(want < cap ? want : cap), 256, 0, st>>>(Ps, C, o);
-				g_launches++;
-				PGT_CUDA(cudaGetLastError());
+				PGT_TRY(launch_persite<Stat>(plan, stat, Ps, C, o, st));
 			} else {
 				PGT_TRY(launch_slide<Stat>(plan, stat, Ps, C, ns, nullptr, o, st));
 			}
