@@ -300,6 +300,7 @@ int pgt_profile_read(double* units_ms, uint64_t* units_launches, double* windows
  *   "unittable": 0 auto (plans of more than 32 segments in device mode: level 1 reads unit starts from a table) | 1 never | 2 always
  *   "slide": 0 auto | 1 never use the sliding-tile kernel for fine steps | 2 use it for every site-mode geometry whose block fits shared memory (W <= 1048)
  *   "stages", "stage_kb": shared-memory ring of the tiled kernel
+ *   "xsmall": extreme scan, 0 auto (short windows: a thread per window over a shared-memory tile) | 1 never | 2 whenever the longest window is <= 2048 sites
  *   "xgroup": lanes per unit of the extreme scan's level 1 (pgt_extreme.h), 0 auto | 4 | 8 | 16 | 32 */
 int pgt_tune(const char* key, int value);
 

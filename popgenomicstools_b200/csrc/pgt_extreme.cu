@@ -54,12 +54,14 @@ static const uint32_t kDefaultUnit = 2048;
 
 // pgt_tune("xgroup", G): force the lanes-per-unit of the extreme scan's level 1 (0 = auto; 4, 8, 16, 32)
 int g_tune_xgroup = 0;
+int g_tune_xsmall = 0;  // 0 auto, 1 never the small-window kernel (k_xsmall), 2 whenever the longest window allows it
 
 // ----------------------------------------------------------------------------- host plan
 
 struct pgt_xplan {
 	uint32_t W = 0, U = 0;
 	uint64_t nsites = 0, nwin = 0, nunits = 0;
+	uint64_t max_window_sites = 0;            // longest window (chooses the small-window kernel)
 	std::vector<uint32_t> label, start, end;  // per window
 	std::vector<uint64_t> xoff;               // nwin+1: window w holds sites [xoff[w], xoff[w+1])
 	std::vector<uint64_t> unit0;              // nwin+1: first unit of window w
@@ -195,6 +197,7 @@ extern "C" int pgt_xplan_create(pgt_xplan** out, const uint32_t* pos, const uint
 		for (uint64_t w = 0; w < nwin; ++w) {
 			P->unit0[w] = u;
 			u += (P->xoff[w + 1] - P->xoff[w] + P->U - 1) / P->U;
+			P->max_window_sites = std::max(P->max_window_sites, P->xoff[w + 1] - P->xoff[w]);
 		}
 		P->unit0[nwin] = u;
 		P->nunits = u;
@@ -464,6 +467,87 @@ __global__ void __launch_bounds__(256) k_xwindows(XDev P, const uint32_t* __rest
 	}
 }
 
+// Short windows (tens of sites: dense windows over sparse SNP sets): the two-level scheme pays a unit partial, a second
+// read of the window table and a butterfly per 33-site window (r01: 3.3 ms per 1e9 sites at 33 sites per window).  Here a
+// CTA stages a tile of consecutive sites in shared memory with coalesced loads -- batch t = the windows whose first site
+// lies in [site_lo + t*kXTileStep, +kXTileStep), found by two binary searches in xoff; their sites span less than
+// kXTileStep + kXMaxSmallWindow <= kXTileSites -- and ONE THREAD walks each window in file order: the reference's own
+// loop (first site taken unconditionally, then strictly-greater comparisons, ihsWindow.cpp:159-173), so NaN handling
+// needs no special case, and the finished row is written straight to the output columns (no partials, no level 2).
+static constexpr uint32_t kXTileSites = 12288;        // 96 KB of scores per CTA: two CTAs per SM
+static constexpr uint32_t kXMaxSmallWindow = 2048;    // plans whose longest window exceeds this keep the two-level scheme
+static constexpr uint32_t kXTileStep = kXTileSites - kXMaxSmallWindow;
+
+// first window w in [0, nw] with xoff[w] >= s (nw if none)
+__device__ __forceinline__ uint64_t x_lower_window(const XDev& P, uint64_t s) {
+	uint64_t lo = 0, hi = P.nw;
+	while (lo < hi) {
+		const uint64_t mid = lo + ((hi - lo) >> 1);
+		if (P.xoff[mid] < s) lo = mid + 1;
+		else hi = mid;
+	}
+	return lo;
+}
+
+// batch -> first window, one thread per batch (a binary search over millions of windows is ~25 dependent trips to L2 /
+// HBM: done per tile inside k_xsmall it cost more than the tile itself).  bw[nbatches] = nw: the last batch also takes
+// the windows that start at site_hi (trailing empty windows).
+__global__ void __launch_bounds__(256) k_xbatches(XDev P, uint64_t nbatches, uint64_t* __restrict__ bw) {
+	const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (t < nbatches) bw[t] = x_lower_window(P, P.site_lo + t * kXTileStep);
+	else if (t == nbatches) bw[t] = P.nw;
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(256) k_xsmall(XDev P, uint64_t nbatches, const uint64_t* __restrict__ bw, const double* __restrict__ score,
+                                                 const uint32_t* __restrict__ pos, pgt_xwindows out) {
+	extern __shared__ __align__(16) double x_tile[];
+	for (uint64_t t = blockIdx.x; t < nbatches; t += gridDim.x) {
+		const uint64_t w_lo = bw[t], w_hi = bw[t + 1];
+		if (w_hi > w_lo) {
+			const uint64_t s_lo = P.xoff[w_lo], s_hi = P.xoff[w_hi];
+			const uint32_t n = (uint32_t)(s_hi - s_lo);  // < kXTileStep + kXMaxSmallWindow
+			const double* __restrict__ src = score + (s_lo - P.origin);
+			// the whole tile in flight at once and at no register cost: 8-byte asynchronous copies straight into shared
+			// memory (with register-staged loads, 16 KB in flight per CTA, the kernel ran at 1.6 TB/s)
+			const uint32_t tile_addr = (uint32_t)__cvta_generic_to_shared(x_tile);
+			for (uint32_t i = threadIdx.x; i < n; i += 256u)
+				asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(tile_addr + i * 8u), "l"(src + i) : "memory");
+			asm volatile("cp.async.wait_all;" ::: "memory");
+			__syncthreads();
+			for (uint64_t w = w_lo + threadIdx.x; w < w_hi; w += 256u) {
+				const uint64_t a = P.xoff[w], b = P.xoff[w + 1];
+				const uint32_t len = (uint32_t)(b - a);
+				if (len == 0) {  // the reference's "NA NA NA 0" row (ihsWindow.cpp:82)
+					if (out.ext_value) out.ext_value[w] = CUDART_NAN;
+					if (out.ext_pos) out.ext_pos[w] = 0u;
+					if (out.ext_site) out.ext_site[w] = ~0ull;
+					if (out.nbig) out.nbig[w] = 0u;
+					if (out.nsites) out.nsites[w] = 0u;
+					if (out.prop) out.prop[w] = CUDART_NAN;
+					continue;
+				}
+				const double* __restrict__ p = x_tile + (a - s_lo);
+				double best = p[0];
+				double bkey = MODE == XMODE_ABS ? fabs(best) : (MODE == XMODE_MAX ? best : -best);  // NaN stays NaN: nothing beats it
+				uint32_t bi = 0, nbig = x_big<MODE>(best, P.cutoff) ? 1u : 0u;
+				for (uint32_t j = 1; j < len; ++j) {
+					const double v = p[j];
+					const double k = MODE == XMODE_ABS ? fabs(v) : (MODE == XMODE_MAX ? v : -v);
+					if (k > bkey) {  // strictly greater: the first extreme stays on ties; false for NaN on either side
+						bkey = k;
+						best = v;
+						bi = j;
+					}
+					nbig += x_big<MODE>(v, P.cutoff) ? 1u : 0u;
+				}
+				x_emit(w, best, a + bi, nbig, len, P.origin, pos, out);
+			}
+		}
+		__syncthreads();  // the tile is reused by the next batch
+	}
+}
+
 __global__ void k_synth_score(uint64_t seed, uint64_t site0, uint64_t n, double* __restrict__ score) {
 	const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
 	for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) score[i] = pgt_synth_score(seed, site0 + i);
@@ -587,7 +671,24 @@ void x_launch_units(const XDev& P, uint64_t nsite, const double* score, const XP
 
 template <int MODE>
 int x_run(const XDev& P, uint64_t nsite, uint64_t nunit, const double* score, const uint32_t* pos, const XPartials& part,
-          const pgt_xwindows& out, cudaStream_t st) {
+          const pgt_xwindows& out, bool small, cudaStream_t st) {
+	if (small && P.nw) {
+		// short windows: tile of sites in shared memory, a thread per window, rows written directly (k_xsmall)
+		const uint64_t nbatches = (P.site_hi - P.site_lo) / kXTileStep + 1;
+		const size_t smem = (size_t)kXTileSites * sizeof(double);
+		PGT_CUDA(cudaFuncSetAttribute(k_xsmall<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+		int per_sm = 0;
+		if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_xsmall<MODE>, 256, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
+		const uint64_t cap = (uint64_t)x_num_sms() * per_sm;
+		XProf prof(2, st);
+		uint64_t* bw = part.idx;  // the partials are not used on this path: >= nw entries, and nw >= nbatches + 1 (checked by the caller)
+		k_xbatches<<<(unsigned)((nbatches + 256) / 256), 256, 0, st>>>(P, nbatches, bw);
+		pgt_count_launch();
+		k_xsmall<MODE><<<(unsigned)(nbatches < cap ? nbatches : cap), 256, smem, st>>>(P, nbatches, bw, score, pos, out);
+		pgt_count_launch();
+		PGT_CUDA(cudaGetLastError());
+		return PGT_OK;
+	}
 	if (nsite) {
 		XProf prof(2, st);
 		// lanes per unit from the mean unit length: short windows get narrow groups, so that every
@@ -710,10 +811,17 @@ extern "C" int pgt_scan_extreme(const pgt_xplan* plan, const pgt_range* range, p
 		if (out->nbig) dout.nbig = (uint32_t*)(ws + L.o_nbig);
 		if (out->nsites) dout.nsites = (uint32_t*)(ws + L.o_nsites);
 	}
+	// short windows (a function of the plan only: longest window <= 2048 sites, fewer than 160 sites per unit on average)
+	// Measured (1e9 sites, profiles/r02z_extreme_small_windows.txt): 33 sites per window 2.79 ms against 3.32 ms for
+	// the two-level scheme, 100 sites per window 2.31 against 2.08 ms (a thread per window leaves most of a CTA idle once
+	// windows are long): chosen below 48 sites per window.  (The batch table lives in the unit-partial area, one entry
+	// per batch + 1: tiny scans keep the two-level scheme.)
+	const bool small = g_tune_xsmall != 1 && plan->max_window_sites <= kXMaxSmallWindow && plan->nunits > 0 &&
+	                   (g_tune_xsmall == 2 || plan->nsites / plan->nunits < 48) && L.nunit >= L.nsite / kXTileStep + 2;
 	switch (mode) {
-		case XMODE_ABS: rc = x_run<XMODE_ABS>(P, L.nsite, L.nunit, d_score, d_pos, part, dout, st); break;
-		case XMODE_MAX: rc = x_run<XMODE_MAX>(P, L.nsite, L.nunit, d_score, d_pos, part, dout, st); break;
-		default: rc = x_run<XMODE_MIN>(P, L.nsite, L.nunit, d_score, d_pos, part, dout, st); break;
+		case XMODE_ABS: rc = x_run<XMODE_ABS>(P, L.nsite, L.nunit, d_score, d_pos, part, dout, small, st); break;
+		case XMODE_MAX: rc = x_run<XMODE_MAX>(P, L.nsite, L.nunit, d_score, d_pos, part, dout, small, st); break;
+		default: rc = x_run<XMODE_MIN>(P, L.nsite, L.nunit, d_score, d_pos, part, dout, small, st); break;
 	}
 	if (rc != PGT_OK) return rc;
 	if (mem == PGT_MEM_HOST) {

@@ -207,6 +207,7 @@ static int g_tune_level2 = 0;
 static int g_tune_stages = 2;      // tiled kernel: shared-memory stages (2..4)
 static int g_tune_stage_kb = 110;  // tiled kernel: KB per stage (stages * stage_kb <= 224)
 extern int g_tune_xgroup;          // extreme scan (pgt_extreme.cu): lanes per unit, 0 = auto
+extern int g_tune_xsmall;          // extreme scan: 0 auto, 1 never / 2 always (if the longest window fits) the small-window kernel
 //   unittable: 0 auto (unit-start table for plans of more than 32 segments, device mode), 1 never, 2 always
 static int g_tune_unittable = 0;
 static constexpr size_t kUnitTableMinSegs = 33;  // measured (profiles/r02o_*): better from 1e3 contigs on, 3.8x at 1e6; few-contig genomes keep the closed form
@@ -527,6 +528,7 @@ extern "C" int pgt_tune(const char* key, int value) {
 	else if (key && strcmp(key, "unittable") == 0 && value >= 0 && value <= 2) g_tune_unittable = value;
 	else if (key && strcmp(key, "stages") == 0 && value >= 2 && value <= kTileMaxStages) g_tune_stages = value;
 	else if (key && strcmp(key, "stage_kb") == 0 && value >= 8 && value <= 110) g_tune_stage_kb = value;
+	else if (key && strcmp(key, "xsmall") == 0 && value >= 0 && value <= 2) g_tune_xsmall = value;
 	else if (key && strcmp(key, "xgroup") == 0 && (value == 0 || value == 4 || value == 8 || value == 16 || value == 32)) g_tune_xgroup = value;
 	else return pgt_set_error(PGT_ERR_ARGS, "pgt_tune: unknown key");
 	return PGT_OK;

@@ -60,8 +60,18 @@ def gpu_rows(plan, out, names):
     return O.extreme_rows(res, names)
 
 
+@pytest.fixture(params=[1, 2], ids=["two-level", "small-window-kernel"])
+def xsmall(request):
+    """Both kernels of the extreme scan: the two-level scheme (unit partials + window combine) and k_xsmall (a thread
+    per window over a shared-memory tile, chosen for short windows; forced here whenever the longest window fits)."""
+    pgt = _pgt()
+    pgt.tune("xsmall", request.param)
+    yield request.param
+    pgt.tune("xsmall", 0)
+
+
 @pytest.mark.parametrize("host", [False, True])
-def test_golden_transcripts(golden_extreme_cases, host):
+def test_golden_transcripts(golden_extreme_cases, host, xsmall):
     for i, c in enumerate(golden_extreme_cases):
         chr_id, pos, val = case_columns(c)
         lengths = list(c["lengths"])
@@ -73,7 +83,7 @@ def test_golden_transcripts(golden_extreme_cases, host):
 
 
 @pytest.mark.parametrize("unit_sites", [0, 1, 3, 64])
-def test_random_vs_oracle(unit_sites):
+def test_random_vs_oracle(unit_sites, xsmall):
     rng = np.random.default_rng(100 + unit_sites)
     for it in range(40):
         mode = "ihs" if it % 2 == 0 else "xpehh"
@@ -172,3 +182,41 @@ def test_errors():
         pgt.scan_extreme(plan, 0, 2.0, pos, np.zeros(100), window_range=(5, 200))
     with pytest.raises(TypeError):
         pgt.ihs_window(plan, pos, np.zeros(100, np.float32))
+
+
+def test_short_windows_many_batches():
+    """3e6 sites in windows of ~33 sites (1e5 windows, hundreds of shared-memory tiles per scan, empty windows inside and
+    at the chromosome ends, ties, NaN on first sites): the small-window kernel is chosen automatically, equals the oracle
+    and the two-level scheme bit for bit, whole, sharded and from host memory."""
+    import torch
+    pgt = _pgt()
+    rng = np.random.default_rng(21)
+    lengths = [1_700_000, 900_000, 400_003]
+    pos = np.concatenate([np.cumsum(rng.integers(1, 6, size=L)) for L in lengths])  # ~3 bp per site
+    n = len(pos)
+    val = np.round(rng.normal(size=n), 1)  # ties
+    val[rng.integers(0, n, size=2000)] = np.nan
+    chrlen = [int(pos[sum(lengths[:c + 1]) - 1]) + 1000 for c in range(3)]  # padded: empty windows at the ends
+    W = 100
+    ref = O.extreme("ihs", T.expand_chr(lengths), pos, val, W, 1.0, chrlen)
+    try:
+        pgt.tune("xsmall", 0)
+        plan, out = run_gpu("ihs", pos, lengths, val, W, 1.0, chrlen)
+        assert plan.num_windows == len(ref["n"]) > 90000
+        assert_equal_to_oracle(out, ref)
+        pgt.tune("xsmall", 1)
+        _, two = run_gpu("ihs", pos, lengths, val, W, 1.0, chrlen)
+        for k in out:
+            assert np.asarray(out[k]).tobytes() == np.asarray(two[k]).tobytes(), k
+        pgt.tune("xsmall", 0)
+        _, hst = run_gpu("ihs", pos, lengths, val, W, 1.0, chrlen, host=True)
+        assert_equal_to_oracle(hst, ref)
+        for r in range(3):
+            w_lo, w_hi, s_lo, s_hi = plan.shard(r, 3)
+            _, part = run_gpu("ihs", pos, lengths, val, W, 1.0, chrlen, window_range=(w_lo, w_hi))
+            assert_equal_to_oracle(part, ref, slice(w_lo, w_hi))
+        ref2 = O.extreme("xpehh", T.expand_chr(lengths), pos, val, W, -0.5, chrlen)
+        _, x2 = run_gpu("xpehh", pos, lengths, val, W, -0.5, chrlen)
+        assert_equal_to_oracle(x2, ref2)
+    finally:
+        pgt.tune("xsmall", 0)
