@@ -82,7 +82,30 @@ def test_scan_fails_loudly_without_device():
     rc = lib.pgt_scan_extreme(xh, None, 0, 2.0, pos.ctypes.data, a.ctypes.data, C.byref(xo), ws.ctypes.data, ws.nbytes,
                               _cabi.PGT_MEM_HOST, None)
     assert rc == _cabi.PGT_ERR_CUDA
+    # the round-2 entry points: one-process multi-GPU scan, streaming uploader, IPC export -- none has a CPU path
+    dev = (C.c_int * 2)(0, 1)
+    xo2 = _cabi.PgtXWindows()
+    xo2.ext_value = val.ctypes.data
+    assert lib.pgt_scan_extreme_sharded(xh, 0, 2.0, pos.ctypes.data, a.ctypes.data, C.byref(xo2), dev, 2) == _cabi.PGT_ERR_CUDA
     lib.pgt_xplan_destroy(xh)
+    h2 = C.c_void_p()
+    assert lib.pgt_plan_create(C.byref(h2), 0, off.ctypes.data, 1, 10, 5, 0) == 0
+    so, sb = np.zeros(19), np.zeros(19)
+    out2 = _cabi.PgtWindows()
+    out2.sum_a, out2.sum_b = so.ctypes.data, sb.ctypes.data
+    rc = lib.pgt_scan_sharded(h2, _cabi.PGT_STAT_FST, C.byref(cols), 1, None, C.byref(out2), dev, 2, None, None)
+    assert rc == _cabi.PGT_ERR_CUDA and b"no CPU fallback" in lib.pgt_last_error()
+    assert lib.pgt_scan_sharded(h2, _cabi.PGT_STAT_FST, C.byref(cols), 1, None, C.byref(out2), None, 0, None, None) == _cabi.PGT_ERR_ARGS
+    assert lib.pgt_plan_scan_path(h2, _cabi.PGT_STAT_FST) == 0 and lib.pgt_plan_scan_path(h2, 9) == _cabi.PGT_ERR_ARGS
+    lib.pgt_plan_destroy(h2)
+    up = C.c_void_p()
+    assert lib.pgt_uploader_create(C.byref(up), None, 0, 4, 1 << 20, 2) == _cabi.PGT_ERR_CUDA and not up.value
+    assert lib.pgt_uploader_create(C.byref(up), None, 0, 0, 1 << 20, 2) == _cabi.PGT_ERR_ARGS
+    handle = (C.c_ubyte * 64)()
+    assert lib.pgt_ipc_export(ws.ctypes.data, handle, 64) == _cabi.PGT_ERR_CUDA
+    assert lib.pgt_ipc_export(ws.ctypes.data, handle, 8) == _cabi.PGT_ERR_ARGS
+    fb, tb = C.c_size_t(), C.c_size_t()
+    assert lib.pgt_device_mem_info(C.byref(fb), C.byref(tb)) == _cabi.PGT_ERR_CUDA
 
 
 def test_tune_knobs_and_the_env_hook():
@@ -93,12 +116,14 @@ def test_tune_knobs_and_the_env_hook():
     from popgenomicstools_b200 import _cabi
     lib = _cabi.load()
     for key, good, bad in ((b"level1", 2, None), (b"level2", 2, 3), (b"slide", 2, 3), (b"stages", 3, 9),
-                           (b"stage_kb", 64, 500), (b"xgroup", 8, 5)):
+                           (b"stage_kb", 64, 500), (b"xgroup", 8, 5), (b"xsmall", 2, 3), (b"persite", 1, 2), (b"fused2", 1, 2),
+                           (b"unittable", 2, 3)):
         assert lib.pgt_tune(key, good) == 0, key
         if bad is not None:
             assert lib.pgt_tune(key, bad) == _cabi.PGT_ERR_ARGS, key
     assert lib.pgt_tune(b"nonsense", 1) == _cabi.PGT_ERR_ARGS
-    for key, dflt in ((b"level1", 0), (b"level2", 0), (b"slide", 0), (b"stages", 2), (b"stage_kb", 110), (b"xgroup", 0)):
+    for key, dflt in ((b"level1", 0), (b"level2", 0), (b"slide", 0), (b"stages", 2), (b"stage_kb", 110), (b"xgroup", 0), (b"xsmall", 0),
+                      (b"persite", 0), (b"fused2", 0), (b"unittable", 0)):
         assert lib.pgt_tune(key, dflt) == 0
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     run = lambda v: subprocess.run([sys.executable, "-c", "import popgenomicstools_b200"], cwd=root,
