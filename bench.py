@@ -20,7 +20,8 @@ region, against MEASURED_PEAKS.json; `configs` = the other BASELINE.json configu
 per-site / 100 kb, C5 and its S = 1 stress variant), each sharded over the same N ranks: value, kernel time,
 algorithmic bytes (columns in + window rows out, SURVEY 8d), fraction of the HBM peak and the table checksum;
 `cpu_baseline` = the unmodified reference binary (oracle/_ref, g++ -O3) timed on this box's host cores on a
-bounded text sample.
+bounded text sample; its `compute_only` = the window arithmetic alone (oracle/pgt_oracle.c on pre-parsed arrays, one
+core and all cores -- SURVEY 8d's second CPU figure: the reference itself cannot separate parsing from arithmetic).
 
 --impl reference runs only that CPU arm (the reference's own implementation of the path); it never imports the
 product package or loads libpgtscan.so.
@@ -161,6 +162,43 @@ def cli_arm(tmp, jobs, W, S):
     return best
 
 
+def _port_contig(job):
+    import numpy as np
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_lib as O
+    lo, hi, seed, W, S = job
+    a, b = O.synth_fst(seed, lo, hi - lo)
+    pos = np.arange(1, hi - lo + 1, dtype=np.uint32)
+    chr_id = np.zeros(hi - lo, np.uint32)
+    best = None
+    for _ in range(2):
+        t0 = time.perf_counter()
+        O.fst(chr_id, pos, a, b, W, S, count_only=True)
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+    return best
+
+
+def compute_only_port(offs, seed, W, S, nproc):
+    """SURVEY 8(d) CPU timing (2): the window arithmetic alone -- oracle/pgt_oracle.c, the restatement of
+    fstWindow.cpp:69-107 (re-sum of every window, no parsing, no printing) over pre-parsed arrays; one contig
+    per process.  One core = the sum of the per-contig times; all cores = the contigs spread over nproc processes."""
+    import multiprocessing as mp
+    n = int(offs[-1])
+    jobs = sorted(((int(offs[i]), int(offs[i + 1]), seed, W, S) for i in range(len(offs) - 1)), key=lambda j: j[0] - j[1])
+    with mp.get_context("fork").Pool(nproc) as pool:
+        t0 = time.perf_counter()
+        secs = pool.map(_port_contig, jobs, chunksize=1)
+        wall = time.perf_counter() - t0
+    # greedy longest-first schedule of the measured compute times over nproc cores (generation excluded)
+    load = [0.0] * nproc
+    for t in secs:
+        load[load.index(min(load))] += t
+    return {"kind": "port", "what": "oracle/pgt_oracle.c window arithmetic only (pre-parsed arrays, no text, no output)",
+            "sites": n, "one_core_sites_per_s": round(n / sum(secs), 1), "cores": nproc,
+            "all_cores_sites_per_s": round(n / max(load), 1), "pool_wall_s_incl_generation": round(wall, 2)}
+
+
 def reference_arm(wl, sample_sites, steps, warmup, with_cli=False):
     """Times the unmodified reference fstWindow (oracle/_ref, built from /root/reference with
     g++ -O3 -Wall) end to end -- text parsing is inseparable from its window arithmetic -- on a
@@ -207,7 +245,13 @@ def reference_arm(wl, sample_sites, steps, warmup, with_cli=False):
         sec = sum(times) / len(times)
         tb = sum(os.path.getsize(j[0]) for j in jobs)
         cli = cli_arm(tmp, jobs, W, S) if with_cli else None
-        return dict(value=n / sec, unit=UNIT, cores=nproc, kind="reference", **({"our_cli_same_text": cli} if cli else {}),
+        extra = {"our_cli_same_text": cli} if cli else {}
+        if with_cli:
+            try:
+                extra["compute_only"] = compute_only_port(offs, wl["seed"], W, S, nproc)
+            except Exception as ex:
+                extra["compute_only"] = {"error": repr(ex)[:200]}
+        return dict(value=n / sec, unit=UNIT, cores=nproc, kind="reference", **extra,
                     sample=(f"unmodified reference fstWindow (g++ -O3 -Wall) end to end incl. text parsing: scaled twin "
                             f"{n} sites / 24 contig files ({tb / 1e9:.2f} GB text), {W}/{S}, one process per contig, "
                             f"{nproc} at a time on {cores} host cores")), sec
