@@ -491,15 +491,18 @@ def run_config(cfg, R, pgt, steps, peak):
             if density:  # bp axis: the sites are those of the bp range; a shard reads its share of them
                 sites_l = int(round(sites_l / density))
         in_b = IN_BYTES[cfg["stat"]] + (4 if density else 0)
-        algo = in_b * sites_l + OUT_BYTES[cfg["stat"]] * nwin_l
+        # positions: compulsory only where a window row prints them -- its first and its last site, so 8 B per window
+        # and never more than the whole column (S = 1: every site starts a window); the bp axis streams them (in_b)
+        pos_b = 0 if density else min(4 * sites_l, 8 * nwin_l)
+        algo = in_b * sites_l + pos_b + OUT_BYTES[cfg["stat"]] * nwin_l
         k_ms = (prof["units_ms"] + prof["windows_ms"]) / steps
         ach = algo / (k_ms * 1e-3) / 1e9 if k_ms > 0 else 0.0
-        tot = R.reduce([algo, ach, k_ms, prof["units_ms"] / steps, prof["windows_ms"] / steps], "sum")
+        tot = R.reduce([algo, ach, k_ms, prof["units_ms"] / steps, prof["windows_ms"] / steps, pos_b], "sum")
         res = dict(name=cfg["name"], desc=cfg["desc"], path=path, n_sites=n, windows=plan.num_windows, value=n / (ms_step * 1e-3),
                    unit=UNIT, ms_per_step=round(ms_step, 4), steps=steps,
                    kernel_ms=round(tot[2] / R.world, 4), level1_ms=round(tot[3] / R.world, 4), level2_ms=round(tot[4] / R.world, 4),
                    algorithmic_bytes=int(tot[0]), achieved_gbs=round(tot[1] / R.world, 1), frac=round(tot[1] / R.world / peak, 4),
-                   bytes_per_site_in=in_b, bytes_per_window_out=OUT_BYTES[cfg["stat"]])
+                   bytes_per_site_in=in_b, bytes_per_window_out=OUT_BYTES[cfg["stat"]], window_edge_position_bytes=int(tot[5]))
         R.barrier()
         res["table"] = ("one table in rank 0's HBM, rows written in place by every rank" if tab.placement == "rank0"
                         else "sharded: every rank keeps its rows in its own HBM (table above 256 MB)")

@@ -8,23 +8,33 @@
 
 template <class Stat>
 __device__ __forceinline__ void emit_window(const DevPlan& P, const pgt_seg& sg, uint64_t w, uint64_t k, const typename Stat::Acc& acc,
-                                            const uint32_t* __restrict__ pos, const pgt_windows& out, bool have_edges = false,
+                                            const uint32_t* __restrict__ pos, const pgt_windows& out, uint64_t o, bool have_edges = false,
                                             uint32_t edge_start = 0, uint32_t edge_end = 0);
+
+// two batches of 32 rows of every output column, staged in shared memory so that a block writes its rows with
+// full-width stores (double-buffered: one barrier per batch)
+struct RowStage {
+	uint32_t u[9][64];  // label, start_pos, end_pos, mid_pos, nsites, nhet, nonmissing, neffective, nskip
+	double d[5][64];    // sum_a, sum_b, fst, het, dxy
+};
 
 // One warp per window: lane l adds unit partials l, l+32, ... (from +0.0, so a window of
 // -0.0 values sums to +0.0 exactly as the reference's `double asum = 0`), then the butterfly.
 // units_base = global index of units[0].
+// A block owns a contiguous run of windows and walks it 32 rows at a time: warp i computes rows i, i+8, i+16, i+24 of
+// the batch into shared memory, then the block stores the batch column by column, 128 / 256 bytes per store -- one row
+// at a time from lane 0 was eight 4- or 8-byte stores per window, which is what a shard pays for when its rows live in
+// another GPU's HBM (one NVLink packet per store).
 template <class Stat>
 __global__ void __launch_bounds__(256) k_windows(DevPlan P, const typename Stat::Acc* __restrict__ units, uint64_t units_base,
                                                   const uint32_t* __restrict__ pos, pgt_windows out) {
-	const uint32_t lane = threadIdx.x & 31u;
-	const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-	const uint64_t nwarp = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+	__shared__ RowStage rows;
+	const uint32_t lane = threadIdx.x & 31u, wi = threadIdx.x >> 5;
 	// The per-window work is a chain of dependent memory round trips; keep it short: the segment is
 	// cached (w only grows, so it changes a few dozen times per warp instead of costing a binary
 	// search in global memory per window), and lane 0 fetches the two edge positions BEFORE the
 	// partials are summed, so that gather overlaps the partial loads instead of following them.
-	// Every warp takes a contiguous run of windows, so the segment only ever moves forward by a step or
+	// Every block takes a contiguous run of windows, so the segment only ever moves forward by a step or
 	// two: one binary search per warp, then a walk (genomes of 1e5 contigs with W larger than the contigs
 	// paid a 17-probe search in L2 per window: 0.86 ms for 1e5 windows).
 	uint32_t si = 0xffffffffu;
@@ -32,42 +42,74 @@ __global__ void __launch_bounds__(256) k_windows(DevPlan P, const typename Stat:
 	sg.win_base = 0;
 	sg.nwin = 0;
 	const uint64_t nwin_all = P.win_hi - P.win_lo;
-	const uint64_t per = (nwin_all + nwarp - 1) / nwarp;
-	const uint64_t w_begin = P.win_lo + warp * per;
+	const uint64_t per = (nwin_all + gridDim.x - 1) / gridDim.x;
+	const uint64_t w_begin = P.win_lo + (uint64_t)blockIdx.x * per;
 	const uint64_t w_end = w_begin + per < P.win_hi ? w_begin + per : P.win_hi;
-	for (uint64_t w = w_begin; w < w_end; ++w) {
-		if (si == 0xffffffffu) {
-			si = find_seg<false>(P, w);
-			sg = P.segs[si];
-		}
-		while (w - sg.win_base >= sg.nwin) {  // also skips segments without windows
-			++si;
-			sg = P.segs[si];
-		}
-		const uint64_t k = w - sg.win_base;
-		uint64_t fu;
-		const uint64_t cnt = pgt_window_units(P.g, sg, k, &fu);
-		uint32_t sp = 0, ep = 0;
-		if (lane == 0 && pos && P.mode != PGT_MODE_BP) {
-			uint64_t fs;
-			const uint32_t nsites = pgt_window_sites(P.g, sg, k, &fs);
-			sp = __ldg(pos + (sg.site_base + fs - P.site_origin));
-			ep = __ldg(pos + (sg.site_base + fs + nsites - 1 - P.site_origin));
-		}
-		const typename Stat::Acc* up = units + (sg.unit_base + fu - units_base);
-		PGT_CHECK(sg.unit_base + fu >= P.unit_lo && sg.unit_base + fu + cnt <= P.unit_hi && w >= P.win_lo && w < P.win_hi);
-		typename Stat::Acc acc = Stat::zero();
-		for (uint64_t x = lane; x < cnt; x += 128u) {  // four partials per lane in flight; added in index order
-			typename Stat::Acc v[4];
+	pgt_windows staged;  // the same columns as `out`, 32 rows each, in shared memory
+	staged.label = out.label ? rows.u[0] : nullptr;
+	staged.start_pos = out.start_pos ? rows.u[1] : nullptr;
+	staged.end_pos = out.end_pos ? rows.u[2] : nullptr;
+	staged.mid_pos = out.mid_pos ? rows.u[3] : nullptr;
+	staged.nsites = out.nsites ? rows.u[4] : nullptr;
+	staged.nhet = out.nhet ? rows.u[5] : nullptr;
+	staged.nonmissing = out.nonmissing ? rows.u[6] : nullptr;
+	staged.neffective = out.neffective ? rows.u[7] : nullptr;
+	staged.nskip = out.nskip ? rows.u[8] : nullptr;
+	staged.sum_a = out.sum_a ? rows.d[0] : nullptr;
+	staged.sum_b = out.sum_b ? rows.d[1] : nullptr;
+	staged.fst = out.fst ? rows.d[2] : nullptr;
+	staged.het = out.het ? rows.d[3] : nullptr;
+	staged.dxy = out.dxy ? rows.d[4] : nullptr;
+	staged.dxy_global = nullptr;
+	uint32_t half = 0;  // which 32 rows of the stage this batch uses
+	for (uint64_t b0 = w_begin; b0 < w_end; b0 += 32u, half ^= 32u) {  // block-uniform
+		const uint32_t nrows = (uint32_t)(w_end - b0 < 32u ? w_end - b0 : 32u);
+		for (uint32_t r = wi; r < nrows; r += 8u) {
+			const uint64_t w = b0 + r;
+			if (si == 0xffffffffu) {
+				si = find_seg<false>(P, w);
+				sg = P.segs[si];
+			}
+			while (w - sg.win_base >= sg.nwin) {  // also skips segments without windows
+				++si;
+				sg = P.segs[si];
+			}
+			const uint64_t k = w - sg.win_base;
+			uint64_t fu;
+			const uint64_t cnt = pgt_window_units(P.g, sg, k, &fu);
+			uint32_t sp = 0, ep = 0;
+			if (lane == 0 && pos && P.mode != PGT_MODE_BP) {
+				uint64_t fs;
+				const uint32_t nsites = pgt_window_sites(P.g, sg, k, &fs);
+				sp = __ldg(pos + (sg.site_base + fs - P.site_origin));
+				ep = __ldg(pos + (sg.site_base + fs + nsites - 1 - P.site_origin));
+			}
+			const typename Stat::Acc* up = units + (sg.unit_base + fu - units_base);
+			PGT_CHECK(sg.unit_base + fu >= P.unit_lo && sg.unit_base + fu + cnt <= P.unit_hi && w >= P.win_lo && w < P.win_hi);
+			typename Stat::Acc acc = Stat::zero();
+			for (uint64_t x = lane; x < cnt; x += 128u) {  // four partials per lane in flight; added in index order
+				typename Stat::Acc v[4];
 #pragma unroll
-			for (int q = 0; q < 4; ++q)
-				if (x + 32u * q < cnt) v[q] = up[x + 32u * q];
+				for (int q = 0; q < 4; ++q)
+					if (x + 32u * q < cnt) v[q] = up[x + 32u * q];
 #pragma unroll
-			for (int q = 0; q < 4; ++q)
-				if (x + 32u * q < cnt) Stat::add(acc, v[q]);
+				for (int q = 0; q < 4; ++q)
+					if (x + 32u * q < cnt) Stat::add(acc, v[q]);
+			}
+			acc = warp_butterfly<Stat>(acc);
+			if (lane == 0) emit_window<Stat>(P, sg, w, k, acc, pos, staged, half + r, true, sp, ep);
 		}
-		acc = warp_butterfly<Stat>(acc);
-		if (lane == 0) emit_window<Stat>(P, sg, w, k, acc, pos, out, true, sp, ep);
+		__syncthreads();
+		const uint64_t o = b0 - P.win_lo + lane;
+		uint32_t* const gu[9] = {out.label, out.start_pos, out.end_pos, out.mid_pos, out.nsites, out.nhet, out.nonmissing, out.neffective, out.nskip};
+		double* const gd[5] = {out.sum_a, out.sum_b, out.fst, out.het, out.dxy};
+#pragma unroll
+		for (int f = 0; f < 9; ++f)
+			if ((f & 7) == (int)wi && gu[f] && lane < nrows) gu[f][o] = rows.u[f][half + lane];
+#pragma unroll
+		for (int f = 0; f < 5; ++f)
+			if (((f + 9) & 7) == (int)wi && gd[f] && lane < nrows) gd[f][o] = rows.d[f][half + lane];
+		// no second barrier: the next batch fills the other half, and the barrier after it orders this store before the refill
 	}
 }
 
@@ -94,9 +136,8 @@ struct SmallTree<Stat, P2, P2> {
 
 template <class Stat>
 __device__ __forceinline__ void emit_window(const DevPlan& P, const pgt_seg& sg, uint64_t w, uint64_t k, const typename Stat::Acc& acc,
-                                            const uint32_t* __restrict__ pos, const pgt_windows& out, bool have_edges, uint32_t edge_start,
-                                            uint32_t edge_end) {
-	const uint64_t o = w - P.win_lo;
+                                            const uint32_t* __restrict__ pos, const pgt_windows& out, uint64_t o, bool have_edges,
+                                            uint32_t edge_start, uint32_t edge_end) {
 	uint64_t fs;
 	const uint32_t nsites = pgt_window_sites(P.g, sg, k, &fs);
 	const uint64_t first = sg.site_base + fs, last = first + nsites - 1;
@@ -143,7 +184,7 @@ __global__ void __launch_bounds__(256) k_windows_small(DevPlan P, const typename
 		const uint32_t cnt = (uint32_t)pgt_window_units(P.g, sg, k, &fu);
 		PGT_CHECK(cnt <= (uint32_t)P2 && sg.unit_base + fu >= P.unit_lo && sg.unit_base + fu + cnt <= P.unit_hi);
 		const typename Stat::Acc acc = SmallTree<Stat, P2, 1>::eval(units + (sg.unit_base + fu - units_base), 0u, cnt);
-		emit_window<Stat>(P, sg, w, k, acc, pos, out);
+		emit_window<Stat>(P, sg, w, k, acc, pos, out, w - P.win_lo);
 	}
 }
 
@@ -495,7 +536,7 @@ __global__ void __launch_bounds__(256) k_windows_hgw(DevPlan P, const typename S
 			Stat::add(acc, suf[gf]);
 			Stat::add(acc, pre[gl]);
 		}
-		emit_window<Stat>(P, sg, w, k, acc, pos, out);
+		emit_window<Stat>(P, sg, w, k, acc, pos, out, w - P.win_lo);
 	}
 }
 
