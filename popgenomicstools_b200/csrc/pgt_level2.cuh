@@ -254,7 +254,14 @@ __global__ void __launch_bounds__(256) k_windows_persite(DevPlan P, Cols cols, p
 // scan's windows lie in ONE segment (always so for W = S = 1: the reference's buffer is exactly full at every contig
 // change, so all contigs chain up), and every column / output pointer is 16-byte aligned at the scan's first window.
 // site0 = column element index of window win_lo.
+// Four doubles are one 256-bit access (LDG/STG.E.ENL2.256, sm_100) when the address allows it: a warp then covers 1 KB of
+// full 32-byte sectors per instruction.  As two 128-bit halves each instruction touched every other half-sector
+// (ncu: 26 of 32 bytes per sector used by the stores of the per-site kernel).
 __device__ __forceinline__ void ld4(const double* p, double* v) {
+	if ((reinterpret_cast<uintptr_t>(p) & 31u) == 0) {
+		asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(v[0]), "=d"(v[1]), "=d"(v[2]), "=d"(v[3]) : "l"(p));
+		return;
+	}
 	const double2 a = __ldg(reinterpret_cast<const double2*>(p)), b = __ldg(reinterpret_cast<const double2*>(p) + 1);
 	v[0] = a.x;
 	v[1] = a.y;
@@ -286,10 +293,13 @@ __device__ __forceinline__ void st4(uint32_t* p, uint32_t a, uint32_t b, uint32_
 	if (p) *reinterpret_cast<uint4*>(p) = make_uint4(a, b, c, d);
 }
 __device__ __forceinline__ void st4(double* p, double a, double b, double c, double d) {
-	if (p) {
-		reinterpret_cast<double2*>(p)[0] = make_double2(a, b);
-		reinterpret_cast<double2*>(p)[1] = make_double2(c, d);
+	if (!p) return;
+	if ((reinterpret_cast<uintptr_t>(p) & 31u) == 0) {
+		asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(p), "d"(a), "d"(b), "d"(c), "d"(d) : "memory");
+		return;
 	}
+	reinterpret_cast<double2*>(p)[0] = make_double2(a, b);
+	reinterpret_cast<double2*>(p)[1] = make_double2(c, d);
 }
 // sites i .. i+3 of the statistic's columns
 __device__ __forceinline__ void load4(const Cols& c, uint64_t i, FstStat::Site* s) {
@@ -373,14 +383,31 @@ __global__ void __launch_bounds__(256) k_windows_persite4(DevPlan P, Cols cols, 
 	const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
 	uint32_t lc = 0;
 	uint64_t lc_lo = 1, lc_hi = 0;  // global sites of contig lc: [lc_lo, lc_hi); empty = nothing cached
+	// The loads of a thread's NEXT turn are issued before the rows of this turn are stored, so a warp always has column
+	// loads in flight behind its store burst (the rows are 36-76 bytes per 1-41 bytes read: without this a warp sat out a
+	// full DRAM round trip per turn with nothing outstanding).
+	typename Stat::Site v[4];
+	uint32_t ps[4] = {0u, 0u, 0u, 0u};
+	{
+		const uint64_t g0 = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+		if (g0 < ngroups && nwin - 4 * g0 >= 4) {
+			PGT_CHECK(site0 + 4 * g0 + 4 <= P.col_elems);
+			load4(cols, site0 + 4 * g0, v);
+			if (cols.pos) ld4(cols.pos + site0 + 4 * g0, ps);
+		}
+	}
 	for (uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; g < ngroups; g += stride) {
 		const uint64_t o = 4 * g, i = site0 + o, gs = P.site_origin + i;
 		if (nwin - o >= 4) {
-			PGT_CHECK(i + 4 <= P.col_elems);
-			typename Stat::Site v[4];
-			uint32_t ps[4] = {0u, 0u, 0u, 0u};
-			load4(cols, i, v);
-			if (cols.pos) ld4(cols.pos + i, ps);
+			typename Stat::Site vn[4];
+			uint32_t pn[4] = {0u, 0u, 0u, 0u};
+			const uint64_t gn = g + stride;
+			const bool more = gn < ngroups && nwin - 4 * gn >= 4;
+			if (more) {
+				PGT_CHECK(site0 + 4 * gn + 4 <= P.col_elems);
+				load4(cols, site0 + 4 * gn, vn);
+				if (cols.pos) ld4(cols.pos + site0 + 4 * gn, pn);
+			}
 			uint32_t lab[4];
 #pragma unroll
 			for (int q = 0; q < 4; ++q) {
@@ -406,6 +433,13 @@ __global__ void __launch_bounds__(256) k_windows_persite4(DevPlan P, Cols cols, 
 				st4(out.mid_pos ? out.mid_pos + o : nullptr, (ps[0] + ps[0]) / 2u, (ps[1] + ps[1]) / 2u, (ps[2] + ps[2]) / 2u, (ps[3] + ps[3]) / 2u);
 			}
 			emit4(out, o, acc);
+			if (more) {
+#pragma unroll
+				for (int q = 0; q < 4; ++q) {
+					v[q] = vn[q];
+					ps[q] = pn[q];
+				}
+			}
 		} else {
 			for (uint64_t q = 0; o + q < nwin; ++q) {  // the last one to three windows of the scan
 				PGT_CHECK(i + q < P.col_elems);

@@ -745,7 +745,7 @@ static int launch_windows(const DevPlan& P, typename Stat::Acc* units, uint64_t 
 		const uint64_t want = (nwin + 255) / 256;
 		kern<<<(unsigned)(want < cap ? want : cap), 256, 0, st>>>(P, units, units_base, pos, out);
 	} else {
-		const uint64_t want = (nwin + 31) / 32;  // a block stores its rows 32 at a time
+		const uint64_t want = (nwin + 7) / 8;  // few windows: a warp each; many: runs per block, stored 32 rows at a time
 		k_windows<Stat><<<(unsigned)(want < cap ? want : cap), 256, 0, st>>>(P, units, units_base, pos, out);
 	}
 	g_launches++;

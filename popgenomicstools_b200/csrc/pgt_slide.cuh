@@ -378,9 +378,10 @@ __global__ void __launch_bounds__(kSlideThreads, SlideMinBlocks<Stat>::value) k_
 }
 
 // The fused statistic with one block per step (W > 512) as two crews of 7 warps: crew 0 scans fst + het (staged columns
-// a, b, geno: 24-byte accumulators) and also writes label, positions and nsites; crew 1 scans dxy (f1, f2, n1, n2: 16
-// bytes).  They read the same staged block and keep their own SUF / PRE arrays (24 + 16 = the 40 bytes per site of the
-// fused accumulator), named barriers 1 and 2.  16 warps per SM instead of 8 at 128 registers per thread instead of 190,
+// a, b, geno: 24-byte accumulators); crew 1 scans dxy (f1, f2, n1, n2: 16 bytes) and also writes label, positions and
+// nsites (with those on crew 0 the dxy crew spent 40 % of its time waiting for the next block, ncu r03g: 3.34 -> 3.23 ms
+// per 1e8 sites).  They read the same staged block and keep their own SUF / PRE arrays (24 + 16 = the 40 bytes per site
+// of the fused accumulator), named barriers 1 and 2.  16 warps per SM instead of 8 at 128 registers per thread instead of 190,
 // and every column of the table holds exactly the bits of its single-statistic scan.  A stage drains when all 14
 // consumer warps have taken their sites into registers.  (Three crews -- fst, dxy, het: 22 warps, 80 registers -- spilled
 // ~420 bytes per thread and gained nothing: DESIGN.md section 12.)
@@ -410,7 +411,7 @@ __global__ void __launch_bounds__(kSlide2Threads, 1) k_slide_fused2(DevPlan P, T
 	crew.t = threadIdx.x - ci * kSlideConsumers;
 	crew.warp = warp - ci * kSlideWarps;
 	crew.col_shift = ci == 0 ? 0u : 2u;
-	crew.common = ci == 0;
+	crew.common = ci == 1;  // dxy has the lighter rows (16 of the 56 statistic bytes): it also writes the 20 shared ones
 	crew.wt = smem + s2.wt_off[ci];
 	crew.sf = smem + s2.sf_off[ci];
 	crew.pr = smem + s2.pr_off[ci];
