@@ -149,8 +149,8 @@ static bool fast_maf_line(const char* p, const char* le, const char** name_b, co
 	return true;
 }
 
-static int load_maf(const char* path, Maf* m, const char* which, Input* keep) {
-	const int rc = read_input(path, keep, true);
+// read_input's verdict on one MAF file, worded as the reference words it
+static int report_maf(int rc, const char* path, const char* which) {
 	if (rc == -2) {  // the reference dies here with boost's gzip_error (dxyWindow.cpp:256-278): never print partial rows
 		fprintf(stderr, "Corrupt or truncated gzip stream in %s MAF file: %s\n", which, path);
 		return -1;
@@ -282,8 +282,16 @@ int main(int argc, char** argv) {
 	// files are opened before the options are looked at (dxyWindow.cpp:73-95)
 	Input in1, in2;
 	Maf m1, m2;
-	if (load_maf(argv[argc - 2], &m1, "Pop1", &in1) != 0) return -1;
-	if (load_maf(argv[argc - 1], &m2, "Pop2", &in2) != 0) return -1;
+	{
+		// both files are read (and inflated) at the same time; Pop1's verdict is reported first, as the reference
+		// opens Pop1 first (dxyWindow.cpp:73-95)
+		int rc2 = 0;
+		std::thread second([&]() { rc2 = read_input(argv[argc - 1], &in2, true); });
+		const int rc1 = read_input(argv[argc - 2], &in1, true);
+		second.join();
+		if (report_maf(rc1, argv[argc - 2], "Pop1") != 0) return -1;
+		if (report_maf(rc2, argv[argc - 1], "Pop2") != 0) return -1;
+	}
 	const char* sizefname = nullptr;
 	bool have_sizefile = false;
 	Input sizein;

@@ -45,10 +45,99 @@ struct Input {
 	void* map = nullptr;
 	size_t map_size = 0;
 	std::vector<char> owned;
+	char* heap = nullptr;  // inflated BGZF input (malloc: a vector would zero gigabytes on one thread first)
 	~Input() {
 		if (map) munmap(map, map_size);
+		free(heap);
 	}
 };
+
+inline unsigned parse_threads() {
+	const char* env = getenv("PGT_THREADS");
+	unsigned n = env ? (unsigned)atoi(env) : std::thread::hardware_concurrency();
+	if (n < 1) n = 1;
+	if (n > 64) n = 64;
+	return n;
+}
+
+// BGZF (bgzip / htslib -- what ANGSD writes its .mafs.gz with): a series of independent gzip members of at most
+// 64 KB, each carrying its own compressed size in a 'BC' extra subfield (SAM spec 4.1) and its uncompressed size in
+// the trailer.  That makes the output offset of every member known up front, so members inflate in parallel.
+struct BgzfBlock {
+	size_t in_off;     // first byte of the raw deflate data
+	uint32_t in_len;   // bytes of deflate data
+	uint32_t out_len;  // ISIZE
+	uint32_t crc;      // CRC32 of the uncompressed bytes
+	size_t out_off;
+};
+// true when [d, d + n) is nothing but well-formed BGZF members
+inline bool bgzf_index(const unsigned char* d, size_t n, std::vector<BgzfBlock>* blocks, size_t* total) {
+	auto u16 = [&](size_t o) { return (uint32_t)d[o] | ((uint32_t)d[o + 1] << 8); };
+	auto u32 = [&](size_t o) { return u16(o) | (u16(o + 2) << 16); };
+	size_t o = 0, out = 0;
+	while (o < n) {
+		if (n - o < 18 + 8 || d[o] != 0x1f || d[o + 1] != 0x8b || d[o + 2] != 8 || d[o + 3] != 4) return false;  // FEXTRA only
+		const size_t xlen = u16(o + 10);
+		if (n - o < 12 + xlen + 8) return false;
+		size_t bsize = 0;
+		for (size_t x = o + 12; x + 4 <= o + 12 + xlen;) {
+			const size_t slen = u16(x + 2);
+			if (d[x] == 'B' && d[x + 1] == 'C' && slen == 2 && x + 6 <= o + 12 + xlen) bsize = (size_t)u16(x + 4) + 1;
+			x += 4 + slen;
+		}
+		if (bsize < 12 + xlen + 8 || bsize > n - o) return false;
+		BgzfBlock b;
+		b.in_off = o + 12 + xlen;
+		b.in_len = (uint32_t)(bsize - 12 - xlen - 8);
+		b.crc = u32(o + bsize - 8);
+		b.out_len = u32(o + bsize - 4);
+		if (b.out_len > (1u << 16)) return false;
+		b.out_off = out;
+		out += b.out_len;
+		blocks->push_back(b);
+		o += bsize;
+	}
+	*total = out;
+	return true;
+}
+// 0 ok, -2 a member does not inflate to its declared size / checksum, -1 out of memory
+inline int bgzf_inflate_parallel(const unsigned char* d, const std::vector<BgzfBlock>& blocks, char* out, unsigned nt) {
+	std::atomic<size_t> next{0};
+	std::atomic<int> status{0};
+	auto work = [&]() {
+		z_stream zs;
+		memset(&zs, 0, sizeof(zs));
+		if (inflateInit2(&zs, -15) != Z_OK) {
+			status = -1;
+			return;
+		}
+		for (;;) {
+			const size_t b0 = next.fetch_add(64);  // 64 members (<= 4 MB of text) per grab
+			if (b0 >= blocks.size() || status.load() != 0) break;
+			const size_t b1 = std::min(blocks.size(), b0 + 64);
+			for (size_t i = b0; i < b1; ++i) {
+				const BgzfBlock& b = blocks[i];
+				inflateReset(&zs);
+				zs.next_in = (Bytef*)(d + b.in_off);
+				zs.avail_in = b.in_len;
+				zs.next_out = (Bytef*)(out + b.out_off);
+				zs.avail_out = b.out_len;
+				const int rc = inflate(&zs, Z_FINISH);
+				if (rc != Z_STREAM_END || zs.avail_out != 0 || zs.avail_in != 0 ||
+				    (uint32_t)crc32(crc32(0L, Z_NULL, 0), (const Bytef*)(out + b.out_off), b.out_len) != b.crc) {
+					status = -2;
+					break;
+				}
+			}
+		}
+		inflateEnd(&zs);
+	};
+	std::vector<std::thread> th;
+	for (unsigned t = 1; t < nt; ++t) th.emplace_back(work);
+	work();
+	for (auto& t : th) t.join();
+	return status.load();
+}
 
 // 0 ok, -1 cannot open, -2 corrupt or truncated gzip stream (the reference aborts there with boost's
 // gzip_error, dxyWindow.cpp:256-278; partial rows must never be presented as a complete result)
@@ -84,6 +173,28 @@ inline int read_input(const char* path, Input* in, bool allow_gzip) {
 	}
 	// gzip magic sniff as the reference does (dxyWindow.cpp:82-83)
 	if (allow_gzip && in->size >= 2 && (unsigned char)in->data[0] == 0x1f && (unsigned char)in->data[1] == 0x8b) {
+		{
+			std::vector<BgzfBlock> blocks;
+			size_t total = 0;
+			const unsigned nt = parse_threads();
+			const char* off = getenv("PGT_BGZF_PARALLEL");  // "0": always the serial zlib stream
+			if (!(off && off[0] == '0') && bgzf_index((const unsigned char*)in->data, in->size, &blocks, &total) && blocks.size() >= 2) {
+				char* out = (char*)malloc(std::max<size_t>(total, 1));
+				if (!out) return -1;
+				const int rc = bgzf_inflate_parallel((const unsigned char*)in->data, blocks, out, std::min<size_t>(nt, (blocks.size() + 63) / 64));
+				if (rc != 0) {
+					free(out);
+					return rc;
+				}
+				if (in->map) munmap(in->map, in->map_size);
+				in->map = nullptr;
+				std::vector<char>().swap(in->owned);
+				in->heap = out;
+				in->data = out;
+				in->size = total;
+				return 0;
+			}
+		}
 		std::vector<char> out;
 		out.resize(std::max<size_t>(in->size * 4, 1 << 16));
 		z_stream zs;
@@ -289,14 +400,6 @@ struct ContigRun {
 	std::string name;
 	uint64_t count;
 };
-
-inline unsigned parse_threads() {
-	const char* env = getenv("PGT_THREADS");
-	unsigned n = env ? (unsigned)atoi(env) : std::thread::hardware_concurrency();
-	if (n < 1) n = 1;
-	if (n > 64) n = 64;
-	return n;
-}
 
 // inputs smaller than this are parsed on one thread (PGT_PARALLEL_MIN_BYTES overrides: the tests
 // use 1 to push tiny fuzzed files through the multi-chunk path)

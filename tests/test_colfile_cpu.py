@@ -155,6 +155,62 @@ def test_truncated_or_corrupt_gzip_is_an_error_not_a_short_result(tmp_path):
     assert (rc, se) == (0, "") and colfile.read(tmp_path / "t2.pgtc")["columns"]["pos"].tolist() == [5]
 
 
+def test_bgzf_members_inflate_in_parallel_to_the_same_columns(tmp_path):
+    """ANGSD writes .mafs.gz through htslib's BGZF: independent <= 64 KB gzip members that carry their own sizes,
+    inflated here by several threads straight to their final offsets.  Same columns as the plain file for one
+    and many threads and for the serial zlib stream; a damaged member is an error (CRC / size checked per member),
+    a file that only looks like BGZF falls back to the serial stream."""
+    import gzip as gz
+    import struct
+    names, lengths = ["chr1", "chr2", "scaf_3"], [150000, 90000, 7]
+    n = sum(lengths)
+    rng = np.random.default_rng(11)
+    pos = np.concatenate([np.cumsum(rng.integers(1, 9, size=L)) for L in lengths])
+    f, nn = rng.integers(0, 1000001, size=n), rng.integers(0, 30, size=n)
+    text = T.maf_text(names, lengths, pos, f, nn).encode()
+    (tmp_path / "p.mafs").write_bytes(text)
+    blob = T.bgzf_bytes(text, rng)
+    assert gz.decompress(blob) == text and blob.count(b"BC\x02\x00") > 50
+    (tmp_path / "p.mafs.gz").write_bytes(blob)
+    (tmp_path / "full.mafs.gz").write_bytes(T.bgzf_bytes(text))  # full 65280-byte members, as bgzip writes them
+    args = ["-winsize", 10, "-stepsize", 5, "-fixedsite", 1]
+    want = None
+    for name, env in (("p.mafs", {}), ("p.mafs.gz", {"PGT_THREADS": "1"}), ("p.mafs.gz", {"PGT_THREADS": "7"}),
+                      ("full.mafs.gz", {"PGT_THREADS": "3"}), ("p.mafs.gz", {"PGT_BGZF_PARALLEL": "0"})):
+        out = tmp_path / "o2.pgtc"
+        rc, so, se = U.run(U.ours("dxyWindow"), args + ["p.mafs", name], cwd=str(tmp_path),
+                           env=dict(env, PGT_PACK=str(tmp_path / "o1.pgtc"), PGT_PACK2=str(out)))
+        assert (rc, se) == (0, ""), (name, env, rc, se)
+        got = out.read_bytes()
+        want = want or got
+        assert got == want, (name, env)
+        out.unlink()
+    r = colfile.read(tmp_path / "o1.pgtc")
+    assert np.array_equal(r["columns"]["pos"], pos) and np.array_equal(r["columns"]["nind"], nn)
+    # damage: a flipped byte inside a member's deflate data, a wrong ISIZE, a file cut inside a member
+    members = [m.start() for m in __import__("re").finditer(b"\x1f\x8b\x08\x04\0\0\0\0\x00\xff\x06\x00BC\x02\x00", blob)]
+    mid = members[len(members) // 2]
+    bad = bytearray(blob)
+    bad[mid + 18 + 5] ^= 0x55
+    (tmp_path / "flip.mafs.gz").write_bytes(bytes(bad))
+    bad = bytearray(blob)
+    nxt = members[len(members) // 2 + 1]
+    bad[nxt - 4:nxt] = struct.pack("<I", struct.unpack("<I", blob[nxt - 4:nxt])[0] + 1)
+    (tmp_path / "isize.mafs.gz").write_bytes(bytes(bad))
+    (tmp_path / "cut.mafs.gz").write_bytes(blob[:mid + 40])
+    for name in ("flip.mafs.gz", "isize.mafs.gz", "cut.mafs.gz"):
+        rc, so, se = U.run(U.ours("dxyWindow"), args + ["p.mafs", name], cwd=str(tmp_path),
+                           env={"PGT_THREADS": "4", "PGT_PACK": str(tmp_path / "a.pgtc"), "PGT_PACK2": str(tmp_path / "bad.pgtc")})
+        assert rc == 255 and so == "" and "gzip" in se and not (tmp_path / "bad.pgtc").exists(), (name, rc, se)
+    # a 'BC' subfield that lies about the member size: not BGZF after all, the serial stream still reads it
+    lie = bytearray(blob)
+    lie[members[3] + 16:members[3] + 18] = struct.pack("<H", 17)
+    (tmp_path / "lie.mafs.gz").write_bytes(bytes(lie))
+    rc, so, se = U.run(U.ours("dxyWindow"), args + ["p.mafs", "lie.mafs.gz"], cwd=str(tmp_path),
+                       env={"PGT_PACK": str(tmp_path / "a.pgtc"), "PGT_PACK2": str(tmp_path / "l2.pgtc")})
+    assert (rc, se) == (0, "") and (tmp_path / "l2.pgtc").read_bytes() == want
+
+
 def test_hostile_pgtc_headers_are_refused(tmp_path):
     """64-bit header fields that wrap when multiplied (nsites ~ 2^61, huge run counts / name blocks) must be
     rejected by the C++ view and by the Python reader, not turned into out-of-bounds column pointers."""

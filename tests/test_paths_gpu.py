@@ -123,6 +123,48 @@ def test_site_mode_all_paths(pgt, W, S, u):
             assert hres[k].tobytes() == full[k].tobytes(), "host vs device " + k
 
 
+def test_warp_per_window_rows_staged_over_many_batches(pgt):
+    """k_windows stores its rows 32 at a time from a double-buffered shared-memory stage.  Here every block walks
+    several batches (1e5 windows of 80 units over 1184 blocks: 32 + 32 + a ragged rest), contig ends fall inside
+    batches, and the device table is compared with the oracle row by row; a shard's table (its first row at an
+    odd offset of the block runs) must hold the same bits."""
+    lengths = [1_700_003, 2560 + 31, 900_000, 5, 700_017]
+    offs = offsets(lengths)
+    n = int(offs[-1])
+    W, S = 2560, 32
+    chr_id = T.expand_chr(lengths)
+    a, b = pgt.synth_fst(7, 0, n)
+    g = pgt.synth_het(7, 0, n)
+    f1, f2, n1, n2 = pgt.synth_dxy(7, 0, n)
+    pos = pgt.synth_pos(7, 0, n, offs, 1)
+    h = {k: v.cpu().numpy() for k, v in dict(pos=pos, a=a, b=b, g=g, f1=f1, f2=f2, n1=n1, n2=n2).items()}
+    rf = O.fst(chr_id, h["pos"], h["a"], h["b"], W, S)
+    ra = O.fst(chr_id, h["pos"], np.abs(h["a"]), np.abs(h["b"]), W, S)
+    rh = O.het(chr_id, h["pos"], h["g"], W, S)
+    rd = O.dxy(chr_id, h["pos"], h["f1"], h["f2"], h["n1"], h["n2"], 5, W, S, 1)
+    plan = pgt.WindowPlan(offs, W, S, unit_sites=32)
+    assert plan.num_windows > 1184 * 64 and plan.scan_path(pgt._cabi.PGT_STAT_FUSED) == "units"
+    pgt.tune("level2", 1)  # warp per window
+    try:
+        res = npy(pgt.fused_window(plan, pos, a, b, g, f1, f2, n1, n2, minind=5))
+        wl, wh, sl, sh = plan.shard(1, 3)
+        part = npy(pgt.fused_window(plan, pos[sl:sh], a[sl:sh], b[sl:sh], g[sl:sh], f1[sl:sh], f2[sl:sh], n1[sl:sh], n2[sl:sh],
+                                    minind=5, window_range=(wl, wh), site_origin=sl))
+    finally:
+        pgt.tune("level2", 0)
+    assert len(res["label"]) == len(rf["label"]) == plan.num_windows
+    for k, want in (("label", rf["label"]), ("start_pos", rf["start"]), ("end_pos", rf["end"]), ("mid_pos", rf["mid"]), ("nsites", rf["n"]),
+                    ("nhet", rh["nhet"]), ("nonmissing", rh["nonmissing"]), ("het", rh["h"]), ("neffective", rd["neff"]),
+                    ("nskip", rd["nskip"])):
+        P.assert_exact(res[k], want, k)
+    P.assert_sum_close(res["sum_a"], rf["asum"], ra["asum"], "sum_a")
+    P.assert_sum_close(res["sum_b"], rf["bsum"], ra["bsum"], "sum_b")
+    P.assert_sum_close(res["dxy"], rd["dxy"], rd["dxy"], "dxy")
+    for k in res:
+        if k != "dxy_global":
+            assert part[k].tobytes() == res[k][wl:wh].tobytes(), k
+
+
 @pytest.mark.parametrize("density", [10, 1])
 @pytest.mark.parametrize("W,S", [(2000, 500), (100, 100), (1, 1), (777, 10)])
 def test_bp_mode_all_paths(pgt, density, W, S):

@@ -58,3 +58,24 @@ def xpehh_text(names, lengths, pos, v_micro):
     head = "id\tpos\tgpos\tp1\tihh1\tp2\tihh2\txpehh\tnormxpehh\tcrit\n"
     return head + "".join(f"{names[c]}_{p}\t{p}\t{p / 1e6:.6f}\t0.5\t0.1\t0.25\t0.2\t{micro_str(v // 2)}\t{micro_str(v)}\t0\n"
                           for c, p, v in zip(chr_id, pos, v_micro))
+
+
+def bgzf_bytes(data, rng=None, level=6):
+    """`data` as a BGZF file (bgzip / htslib, SAM spec 4.1): gzip members of at most 64 KB with a 'BC' extra
+    subfield holding the member's size, then the empty end-of-file member.  rng: ragged member sizes."""
+    import struct
+    import zlib
+
+    def member(chunk):
+        co = zlib.compressobj(level, zlib.DEFLATED, -15)
+        cd = co.compress(chunk) + co.flush()
+        head = b"\x1f\x8b\x08\x04" + b"\0\0\0\0" + b"\x00\xff" + struct.pack("<H", 6) + b"BC" + struct.pack("<HH", 2, len(cd) + 25)
+        return head + cd + struct.pack("<II", zlib.crc32(chunk), len(chunk))
+
+    out, o = [], 0
+    while o < len(data):
+        k = 65280 if rng is None else int(rng.integers(1, 65281))
+        out.append(member(data[o:o + k]))
+        o += k
+    out.append(member(b""))
+    return b"".join(out)
