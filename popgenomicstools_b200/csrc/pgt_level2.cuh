@@ -188,14 +188,82 @@ __global__ void __launch_bounds__(256) k_windows_small(DevPlan P, const typename
 	}
 }
 
+// ----------------------------------------------------------------------------- dxyWindow's global line
+//
+// Block partial triples {sum of dxy, neffective, nskip} (counts carried as doubles: exact below 2^53), reduced by
+// k_global_final (pgt_slide.cuh).  The per-site kernels below add their own sites' values on the way -- their windows ARE
+// the sites -- so the dxy columns are read once; scans with a unit array reduce the unit partials, the sliding tile takes a
+// pass over the columns (k_global_partial / k_global_sites).
+static constexpr int kGlobalBlocks = 256;  // fixed (part of the summation order of the global line)
+static constexpr int kGlobalMaxPartials = 4096;  // block partial triples the workspace holds (per-site kernels: one per block)
+
+__device__ __forceinline__ void block_reduce_global(double d, unsigned long long ne, unsigned long long nk, double* __restrict__ out3) {
+	__shared__ double s_d[32];
+	__shared__ unsigned long long s_e[32], s_k[32];
+#pragma unroll
+	for (int m = 16; m >= 1; m >>= 1) {
+		d = __dadd_rn(d, shfl_xor_f64(d, m));
+		ne += __shfl_xor_sync(0xffffffffu, ne, m);
+		nk += __shfl_xor_sync(0xffffffffu, nk, m);
+	}
+	if ((threadIdx.x & 31u) == 0) {
+		s_d[threadIdx.x >> 5] = d;
+		s_e[threadIdx.x >> 5] = ne;
+		s_k[threadIdx.x >> 5] = nk;
+	}
+	__syncthreads();
+	if (threadIdx.x < 32) {
+		const uint32_t nw = blockDim.x >> 5;
+		d = threadIdx.x < nw ? s_d[threadIdx.x] : 0.0;
+		ne = threadIdx.x < nw ? s_e[threadIdx.x] : 0ull;
+		nk = threadIdx.x < nw ? s_k[threadIdx.x] : 0ull;
+#pragma unroll
+		for (int m = 16; m >= 1; m >>= 1) {
+			d = __dadd_rn(d, shfl_xor_f64(d, m));
+			ne += __shfl_xor_sync(0xffffffffu, ne, m);
+			nk += __shfl_xor_sync(0xffffffffu, nk, m);
+		}
+		if (threadIdx.x == 0) {
+			out3[0] = d;
+			out3[1] = (double)ne;
+			out3[2] = (double)nk;
+		}
+	}
+}
+
+// what a window accumulator contributes to the global line (nothing for fst / het)
+template <class Stat>
+struct GlobalTerm {
+	static constexpr bool has = false;
+	static __device__ __forceinline__ void add(const typename Stat::Acc&, double&, unsigned long long&, unsigned long long&) {}
+};
+template <>
+struct GlobalTerm<DxyStat> {
+	static constexpr bool has = true;
+	static __device__ __forceinline__ void add(const DxyStat::Acc& a, double& d, unsigned long long& ne, unsigned long long& nk) {
+		d = __dadd_rn(d, a.dxy);
+		ne += a.neff;
+		nk += a.nskip;
+	}
+};
+template <>
+struct GlobalTerm<FusedStat> {
+	static constexpr bool has = true;
+	static __device__ __forceinline__ void add(const FusedStat::Acc& a, double& d, unsigned long long& ne, unsigned long long& nk) {
+		GlobalTerm<DxyStat>::add(a.dxy, d, ne, nk);
+	}
+};
+
 // W = S = 1 (the tools' default arguments): every window is one site, so the window table is an
 // elementwise map of the columns; level 1 is skipped and the per-site statistic is evaluated here.
 // Output-bound (36-76 bytes of rows per 1-41 bytes of site): a thread takes four windows per turn and issues
 // their column loads together before the first row is stored; the label comes from a cached contig range
 // instead of a binary search per window.
 template <class Stat>
-__global__ void __launch_bounds__(256) k_windows_persite(DevPlan P, Cols cols, pgt_windows out) {
+__global__ void __launch_bounds__(256) k_windows_persite(DevPlan P, Cols cols, pgt_windows out, double* __restrict__ gpart) {
 	constexpr int U = 4;
+	double gd = 0.0;  // this thread's share of the global line (gpart != NULL: one partial triple per block)
+	unsigned long long gne = 0, gnk = 0;
 	const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
 	uint32_t si = 0xffffffffu;
 	pgt_seg sg;
@@ -236,6 +304,7 @@ __global__ void __launch_bounds__(256) k_windows_persite(DevPlan P, Cols cols, p
 			}
 			typename Stat::Acc acc = Stat::zero();
 			Stat::fold(acc, v[q], cols.minind);
+			if (GlobalTerm<Stat>::has && gpart) GlobalTerm<Stat>::add(acc, gd, gne, gnk);
 			if (out.label) out.label[o] = lc;
 			if (out.nsites) out.nsites[o] = 1u;
 			if (cols.pos) {
@@ -246,6 +315,7 @@ __global__ void __launch_bounds__(256) k_windows_persite(DevPlan P, Cols cols, p
 			Stat::emit(out, o, acc);
 		}
 	}
+	if (GlobalTerm<Stat>::has && gpart) block_reduce_global(gd, gne, gnk, gpart + 3 * blockIdx.x);  // gpart is grid-uniform
 }
 
 // The same map with FOUR CONSECUTIVE windows per thread and 128-bit loads and stores: the scalar kernel above spends ~130
@@ -377,7 +447,9 @@ __device__ __forceinline__ void emit4(const pgt_windows& out, uint64_t o, const 
 }
 
 template <class Stat>
-__global__ void __launch_bounds__(256) k_windows_persite4(DevPlan P, Cols cols, pgt_windows out, uint64_t site0) {
+__global__ void __launch_bounds__(256) k_windows_persite4(DevPlan P, Cols cols, pgt_windows out, uint64_t site0, double* __restrict__ gpart) {
+	double gd = 0.0;  // this thread's share of the global line (gpart != NULL: one partial triple per block)
+	unsigned long long gne = 0, gnk = 0;
 	const uint64_t nwin = P.win_hi - P.win_lo;
 	const uint64_t ngroups = (nwin + 3) / 4;
 	const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
@@ -423,6 +495,7 @@ __global__ void __launch_bounds__(256) k_windows_persite4(DevPlan P, Cols cols, 
 			for (int q = 0; q < 4; ++q) {
 				acc[q] = Stat::zero();
 				Stat::fold(acc[q], v[q], cols.minind);
+				if (GlobalTerm<Stat>::has && gpart) GlobalTerm<Stat>::add(acc[q], gd, gne, gnk);
 			}
 			st4(out.label ? out.label + o : nullptr, lab[0], lab[1], lab[2], lab[3]);
 			st4(out.nsites ? out.nsites + o : nullptr, 1u, 1u, 1u, 1u);
@@ -445,6 +518,7 @@ __global__ void __launch_bounds__(256) k_windows_persite4(DevPlan P, Cols cols, 
 				PGT_CHECK(i + q < P.col_elems);
 				typename Stat::Acc acc = Stat::zero();
 				Stat::fold(acc, Stat::load(cols, i + q), cols.minind);
+				if (GlobalTerm<Stat>::has && gpart) GlobalTerm<Stat>::add(acc, gd, gne, gnk);
 				const uint32_t ps = cols.pos ? __ldg(cols.pos + i + q) : 0u;
 				lc = find_contig(P.off, 0, P.ncontig, gs + q);
 				if (out.label) out.label[o + q] = lc;
@@ -458,6 +532,7 @@ __global__ void __launch_bounds__(256) k_windows_persite4(DevPlan P, Cols cols, 
 			}
 		}
 	}
+	if (GlobalTerm<Stat>::has && gpart) block_reduce_global(gd, gne, gnk, gpart + 3 * blockIdx.x);  // gpart is grid-uniform
 }
 
 // ----------------------------------------------------------------------------- level 2, scan mode

@@ -424,7 +424,7 @@ static int make_layout(const pgt_plan* plan, const pgt_range* range, pgt_stat st
 	L->siteoff_off = o;
 	if (plan->mode == PGT_MODE_BP) o += align_up(plan->off.size() * sizeof(uint64_t), 256);
 	L->gpart_off = o;
-	o += align_up((size_t)kGlobalBlocks * 3 * sizeof(double), 256);
+	o += align_up((size_t)kGlobalMaxPartials * 3 * sizeof(double), 256);
 	L->units_off = o;
 	o += align_up((size_t)nunits * acc_bytes(stat) + 8, 256);
 	// level 2 in scan mode when summing wunits partials per window would dominate (fine steps, long windows)
@@ -760,7 +760,7 @@ static int launch_global(const typename Stat::Acc*, uint64_t, double*, double*, 
 template <>
 int launch_global<DxyStat>(const DxyStat::Acc* units, uint64_t n, double* scratch, double* g3, cudaStream_t st) {
 	k_global_partial<DxyStat><<<kGlobalBlocks, 1024, 0, st>>>(units, n, scratch);
-	k_global_final<<<1, kGlobalBlocks, 0, st>>>(scratch, g3);
+	k_global_final<<<1, kGlobalBlocks, 0, st>>>(scratch, kGlobalBlocks, g3);
 	g_launches += 2;
 	PGT_CUDA(cudaGetLastError());
 	return PGT_OK;
@@ -768,7 +768,7 @@ int launch_global<DxyStat>(const DxyStat::Acc* units, uint64_t n, double* scratc
 template <>
 int launch_global<FusedStat>(const FusedStat::Acc* units, uint64_t n, double* scratch, double* g3, cudaStream_t st) {
 	k_global_partial<FusedStat><<<kGlobalBlocks, 1024, 0, st>>>(units, n, scratch);
-	k_global_final<<<1, kGlobalBlocks, 0, st>>>(scratch, g3);
+	k_global_final<<<1, kGlobalBlocks, 0, st>>>(scratch, kGlobalBlocks, g3);
 	g_launches += 2;
 	PGT_CUDA(cudaGetLastError());
 	return PGT_OK;
@@ -871,7 +871,8 @@ static int launch_slide(const pgt_plan* plan, pgt_stat stat, const DevPlan& P, c
 // W = S = 1: the vectorised kernel when its preconditions hold (one segment; every used column and output pointer
 // 16-byte aligned at the scan's first window -- 4-byte aligned for the genotype column), else the scalar one.
 template <class Stat>
-static int launch_persite(const pgt_plan* plan, pgt_stat stat, const DevPlan& P, const Cols& C, const pgt_windows& out, cudaStream_t st) {
+static int launch_persite(const pgt_plan* plan, pgt_stat stat, const DevPlan& P, const Cols& C, const pgt_windows& out, double* gpart,
+                          double* g3, cudaStream_t st) {
 	const uint64_t nwin = P.win_hi - P.win_lo;
 	if (nwin == 0) return PGT_OK;
 	bool vec = g_tune_persite != 1 && plan->segs.size() == 1 && nwin >= 4;
@@ -897,22 +898,28 @@ static int launch_persite(const pgt_plan* plan, pgt_stat stat, const DevPlan& P,
 		for (const void* p : outs) vec = vec && (((uintptr_t)p) & 15) == 0;
 	}
 	ProfScope prof(1, st);
+	unsigned grid;
 	if (vec) {
-		const unsigned grid = one_wave_grid(k_windows_persite4<Stat>, 256, (nwin + 1023) / 1024);
-		k_windows_persite4<Stat><<<grid, 256, 0, st>>>(P, C, out, site0);
+		grid = std::min<unsigned>(one_wave_grid(k_windows_persite4<Stat>, 256, (nwin + 1023) / 1024), kGlobalMaxPartials);
+		k_windows_persite4<Stat><<<grid, 256, 0, st>>>(P, C, out, site0, gpart);
 	} else {
-		const unsigned grid = one_wave_grid(k_windows_persite<Stat>, 256, (nwin + 1023) / 1024);  // four windows per thread and turn
-		k_windows_persite<Stat><<<grid, 256, 0, st>>>(P, C, out);
+		grid = std::min<unsigned>(one_wave_grid(k_windows_persite<Stat>, 256, (nwin + 1023) / 1024), kGlobalMaxPartials);  // four windows per thread and turn
+		k_windows_persite<Stat><<<grid, 256, 0, st>>>(P, C, out, gpart);
 	}
 	g_launches++;
 	PGT_CUDA(cudaGetLastError());
+	if (gpart) {  // the global line over exactly these windows' sites: one partial triple per block
+		k_global_final<<<1, kGlobalBlocks, 0, st>>>(gpart, grid, g3);
+		g_launches++;
+		PGT_CUDA(cudaGetLastError());
+	}
 	return PGT_OK;
 }
 
 // dxyWindow's global line straight from the columns (scans without a unit array)
 static int launch_global_sites(const Cols& cols, uint64_t i0, uint64_t i1, double* scratch, double* g3, cudaStream_t st) {
 	k_global_sites<<<kGlobalBlocks, 1024, 0, st>>>(cols, i0, i1, scratch);
-	k_global_final<<<1, kGlobalBlocks, 0, st>>>(scratch, g3);
+	k_global_final<<<1, kGlobalBlocks, 0, st>>>(scratch, kGlobalBlocks, g3);
 	g_launches += 2;
 	PGT_CUDA(cudaGetLastError());
 	return PGT_OK;
@@ -1029,14 +1036,21 @@ static int run_scan(const pgt_plan* plan, const pgt_range* range, pgt_stat stat,
 				pgt_plan_window(plan, L.w_hi - 1, nullptr, &last_site, nullptr);
 				P.col_elems = last_site + 1 - L.origin;
 			}
+			bool global_done = false;
 			if (nwin && L.persite) {
-				PGT_TRY(launch_persite<Stat>(plan, stat, P, C, *out, st));
+				// the windows ARE the sites: when the owned range of the global line is exactly their span (always, unless the
+				// scan owns sites outside any window) the kernel adds its sites up on the way and the dxy columns are read once
+				uint64_t first_site, last_site;
+				pgt_plan_window(plan, L.w_lo, &first_site, nullptr, nullptr);
+				pgt_plan_window(plan, L.w_hi - 1, nullptr, &last_site, nullptr);
+				global_done = want_global && GlobalTerm<Stat>::has && L.gsite_lo == first_site && L.gsite_hi == last_site + 1;
+				PGT_TRY(launch_persite<Stat>(plan, stat, P, C, *out, global_done ? (double*)(ws + L.gpart_off) : nullptr, out->dxy_global, st));
 			} else if (nwin) {
 				uint64_t last;
 				pgt_plan_window(plan, L.w_hi - 1, nullptr, &last, nullptr);
 				PGT_TRY(launch_slide<Stat>(plan, stat, P, C, last + 1 - L.origin, cols->pos, *out, st));
 			}
-			if (want_global) {
+			if (want_global && !global_done) {
 				if (L.gsite_lo < L.origin) return pgt_set_error(PGT_ERR_ARGS, "site_origin lies after the first site this scan must read");
 				PGT_TRY(launch_global_sites(C, L.gsite_lo - L.origin, L.gsite_hi - L.origin, (double*)(ws + L.gpart_off), out->dxy_global, st));
 			}
@@ -1236,7 +1250,7 @@ static int run_scan(const pgt_plan* plan, const pgt_range* range, pgt_stat stat,
 			Ps.col_elems = ns;
 			const pgt_windows o = device_table(slot);  // rewritten two slabs later, after this slab's copy-back (order of `st`)
 			if (L.persite) {
-				PGT_TRY(launch_persite<Stat>(plan, stat, Ps, C, o, st));
+				PGT_TRY(launch_persite<Stat>(plan, stat, Ps, C, o, nullptr, nullptr, st));  // (global line: fold_global below)
 			} else {
 				PGT_TRY(launch_slide<Stat>(plan, stat, Ps, C, ns, nullptr, o, st));
 			}

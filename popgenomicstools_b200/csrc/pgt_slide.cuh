@@ -438,42 +438,6 @@ struct GlobalOf<FusedStat> {
 	static __device__ __forceinline__ const DxyStat::Acc& get(const FusedStat::Acc& a) { return a.dxy; }
 };
 
-static constexpr int kGlobalBlocks = 256;  // fixed (part of the summation order of the global line)
-
-__device__ __forceinline__ void block_reduce_global(double d, unsigned long long ne, unsigned long long nk, double* __restrict__ out3) {
-	__shared__ double s_d[32];
-	__shared__ unsigned long long s_e[32], s_k[32];
-#pragma unroll
-	for (int m = 16; m >= 1; m >>= 1) {
-		d = __dadd_rn(d, shfl_xor_f64(d, m));
-		ne += __shfl_xor_sync(0xffffffffu, ne, m);
-		nk += __shfl_xor_sync(0xffffffffu, nk, m);
-	}
-	if ((threadIdx.x & 31u) == 0) {
-		s_d[threadIdx.x >> 5] = d;
-		s_e[threadIdx.x >> 5] = ne;
-		s_k[threadIdx.x >> 5] = nk;
-	}
-	__syncthreads();
-	if (threadIdx.x < 32) {
-		const uint32_t nw = blockDim.x >> 5;
-		d = threadIdx.x < nw ? s_d[threadIdx.x] : 0.0;
-		ne = threadIdx.x < nw ? s_e[threadIdx.x] : 0ull;
-		nk = threadIdx.x < nw ? s_k[threadIdx.x] : 0ull;
-#pragma unroll
-		for (int m = 16; m >= 1; m >>= 1) {
-			d = __dadd_rn(d, shfl_xor_f64(d, m));
-			ne += __shfl_xor_sync(0xffffffffu, ne, m);
-			nk += __shfl_xor_sync(0xffffffffu, nk, m);
-		}
-		if (threadIdx.x == 0) {
-			out3[0] = d;
-			out3[1] = (double)ne;
-			out3[2] = (double)nk;
-		}
-	}
-}
-
 // stage 1: block b adds partials b*1024 + t + k*(256*1024) per thread t, then reduces the block
 template <class Stat>
 __global__ void __launch_bounds__(1024) k_global_partial(const typename Stat::Acc* __restrict__ units, uint64_t n, double* __restrict__ partial3) {
@@ -487,10 +451,16 @@ __global__ void __launch_bounds__(1024) k_global_partial(const typename Stat::Ac
 	}
 	block_reduce_global(d, ne, nk, partial3 + 3 * blockIdx.x);
 }
-// stage 2: one block over the 256 block partials
-__global__ void __launch_bounds__(kGlobalBlocks) k_global_final(const double* __restrict__ partial3, double* __restrict__ global3) {
-	block_reduce_global(partial3[3 * threadIdx.x], (unsigned long long)partial3[3 * threadIdx.x + 1],
-	                    (unsigned long long)partial3[3 * threadIdx.x + 2], global3);
+// stage 2: one block over the n block partials (thread t adds partials t, t + 256, ... in that order; n = 256: one each)
+__global__ void __launch_bounds__(kGlobalBlocks) k_global_final(const double* __restrict__ partial3, uint32_t n, double* __restrict__ global3) {
+	double d = 0.0;
+	unsigned long long ne = 0, nk = 0;
+	for (uint32_t i = threadIdx.x; i < n; i += kGlobalBlocks) {
+		d = __dadd_rn(d, partial3[3 * i]);
+		ne += (unsigned long long)partial3[3 * i + 1];
+		nk += (unsigned long long)partial3[3 * i + 2];
+	}
+	block_reduce_global(d, ne, nk, global3);
 }
 
 // dxyWindow's global line when no unit array exists (sliding-tile and per-site scans): thread t of

@@ -112,7 +112,11 @@ def test_no_read_outside_the_columns(env, name, W, S, unit, knobs, n_extra):
                 res = pgt.scan(plan, stat, {k: gc[k] for k in need}, minind=5)
                 torch.cuda.synchronize()  # an out-of-bounds access surfaces here as an illegal-address error
                 for k, v in res.items():
-                    assert v.cpu().numpy().tobytes() == ref[k].cpu().numpy().tobytes(), (name, at_end, stat, k)
+                    got, want = v.cpu().numpy(), ref[k].cpu().numpy()
+                    if k == "dxy_global":  # the one output whose summation order may follow the kernel: counts exact
+                        assert got[1] == want[1] and got[2] == want[2] and abs(got[0] - want[0]) <= 1e-12 * abs(want[0]), (name, at_end, stat)
+                    else:
+                        assert got.tobytes() == want.tobytes(), (name, at_end, stat, k)
             del gc
             for gbuf in keep:
                 gbuf.free()
