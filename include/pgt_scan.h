@@ -296,6 +296,7 @@ int pgt_profile_read(double* units_ms, uint64_t* units_launches, double* windows
  *   "level1": 0 auto | 1 direct warp-per-unit kernel (long units only) | 2 tiled TMA-staged kernel
  *   "level2": 0 auto | 1 always warp-per-window | 2 always scan mode (block prefix/suffix scans)
  *   "fused2": 0 auto (fused sliding tile, W > 512: two crews of warps -- fst + het, dxy -- over one staged block) | 1 one crew with the fused accumulator
+ *   "slideglobal": 0 auto (the sliding tile adds up dxyWindow's global line on the way when its runs own exactly the line's sites) | 1 always a separate pass over the dxy columns
  *   "persite": 0 auto | 1 always the scalar per-site kernel (W = S = 1)
  *   "unittable": 0 auto (plans of more than 32 segments in device mode: level 1 reads unit starts from a table) | 1 never | 2 always
  *   "slide": 0 auto | 1 never use the sliding-tile kernel for fine steps | 2 use it for every site-mode geometry whose block fits shared memory (W <= 1048)

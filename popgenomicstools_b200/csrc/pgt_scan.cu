@@ -217,6 +217,8 @@ static int g_tune_fused2 = 0;
 static int g_tune_persite = 0;
 //   slide: 0 auto, 1 never use the sliding-tile kernel (k_slide), 2 use it whenever it fits shared memory (any W <= 1048)
 static int g_tune_slide = 0;
+// 0: the sliding tile also takes dxyWindow's global line when its runs own exactly the line's sites; 1: always a separate pass
+static int g_tune_slideglobal = 0;
 
 static int num_sms() {
 	int dev = 0, n = 0;
@@ -524,6 +526,7 @@ extern "C" int pgt_tune(const char* key, int value) {
 	else if (key && strcmp(key, "level2") == 0 && value >= 0 && value <= 2) g_tune_level2 = value;
 	else if (key && strcmp(key, "slide") == 0 && value >= 0 && value <= 2) g_tune_slide = value;
 	else if (key && strcmp(key, "fused2") == 0 && value >= 0 && value <= 1) g_tune_fused2 = value;
+	else if (key && strcmp(key, "slideglobal") == 0 && value >= 0 && value <= 1) g_tune_slideglobal = value;
 	else if (key && strcmp(key, "persite") == 0 && value >= 0 && value <= 1) g_tune_persite = value;
 	else if (key && strcmp(key, "unittable") == 0 && value >= 0 && value <= 2) g_tune_unittable = value;
 	else if (key && strcmp(key, "stages") == 0 && value >= 2 && value <= kTileMaxStages) g_tune_stages = value;
@@ -778,7 +781,7 @@ int launch_global<FusedStat>(const FusedStat::Acc* units, uint64_t n, double* sc
 // they hold `valid_elems` elements.  `pos` may be NULL (host mode gathers positions on the host).
 template <class Stat>
 static int launch_slide(const pgt_plan* plan, pgt_stat stat, const DevPlan& P, const Cols& cols, uint64_t valid_elems, const uint32_t* pos,
-                        const pgt_windows& out, cudaStream_t st) {
+                        const pgt_windows& out, double* gpart, double* g3, cudaStream_t st) {
 	const uint64_t nwin = P.win_hi - P.win_lo;
 	if (nwin == 0) return PGT_OK;
 	SlideShape sh;
@@ -808,6 +811,14 @@ static int launch_slide(const pgt_plan* plan, pgt_stat stat, const DevPlan& P, c
 	sc.pos_off = sh.pos_off;
 	sc.pos_col = pos ? scol.n : 0xffffffffu;
 	sc.stage_off = sh.stage_off;
+	sc.gpart = gpart;
+	auto finish_global = [&](unsigned grid) -> int {  // one partial triple per CTA -> the line
+		if (!gpart) return PGT_OK;
+		k_global_final<<<1, kGlobalBlocks, 0, st>>>(gpart, grid, g3);
+		g_launches++;
+		PGT_CUDA(cudaGetLastError());
+		return PGT_OK;
+	};
 	// chunks: ~4 per resident CTA for balance, but long enough (>= 32 steps of windows) that the W - S sites
 	// shared with the next chunk stay a few percent of what a chunk reads
 	const uint64_t wps = ((uint64_t)sh.G * plan->g.W + plan->g.S - 1) / plan->g.S;  // windows starting in one step
@@ -833,13 +844,14 @@ static int launch_slide(const pgt_plan* plan, pgt_stat stat, const DevPlan& P, c
 			PGT_CUDA(cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh.smem));
 			const uint64_t slots = (uint64_t)num_sms();
 			set_chunks(slots);
+			const unsigned grid2 = (unsigned)std::min<uint64_t>(sc.nchunks, slots);
 			{
 				ProfScope prof(0, st);
-				k2<<<(unsigned)std::min<uint64_t>(sc.nchunks, slots), kSlide2Threads, sh.smem, st>>>(P, tc, sc, s2, out);
+				k2<<<grid2, kSlide2Threads, sh.smem, st>>>(P, tc, sc, s2, out);
 			}
 			g_launches++;
 			PGT_CUDA(cudaGetLastError());
-			return PGT_OK;
+			return finish_global(grid2);
 		}
 	}
 	void (*kern)(DevPlan, TileCfg, SlideCfg, pgt_windows);
@@ -865,7 +877,29 @@ static int launch_slide(const pgt_plan* plan, pgt_stat stat, const DevPlan& P, c
 	}
 	g_launches++;
 	PGT_CUDA(cudaGetLastError());
-	return PGT_OK;
+	return finish_global(grid);
+}
+
+// Do the sites the sliding-tile kernel counts as owned by its runs -- per segment from the first window's start to the
+// start of the first window after the range, or to the end of the segment's last window -- make up exactly the range
+// [gsite_lo, gsite_hi) of dxyWindow's global line?  (No when a segment inside the range has sites after its last window
+// or no window at all: then the line is taken by a pass over the columns.)
+static bool slide_runs_cover_owned_sites(const pgt_plan* plan, const Layout& L) {
+	if (L.w_hi <= L.w_lo) return false;
+	const uint64_t W = plan->g.W, S = plan->g.S;
+	uint32_t si = pgt_plan_seg_of_window(plan, L.w_lo);
+	uint64_t w = L.w_lo, cursor = L.gsite_lo;
+	while (w < L.w_hi) {
+		while (si < plan->segs.size() && w - plan->segs[si].win_base >= plan->segs[si].nwin) ++si;
+		if (si >= plan->segs.size()) return false;
+		const pgt_seg& sg = plan->segs[si];
+		const uint64_t ka = w - sg.win_base, kb = std::min<uint64_t>(L.w_hi - sg.win_base, sg.nwin);
+		if (sg.site_base + ka * S != cursor) return false;
+		const uint64_t hi = kb == sg.nwin ? std::min<uint64_t>((kb - 1) * S + W, sg.nsites) : kb * S;
+		cursor = sg.site_base + hi;
+		w = sg.win_base + kb;
+	}
+	return cursor == L.gsite_hi;
 }
 
 // W = S = 1: the vectorised kernel when its preconditions hold (one segment; every used column and output pointer
@@ -1048,7 +1082,9 @@ static int run_scan(const pgt_plan* plan, const pgt_range* range, pgt_stat stat,
 			} else if (nwin) {
 				uint64_t last;
 				pgt_plan_window(plan, L.w_hi - 1, nullptr, &last, nullptr);
-				PGT_TRY(launch_slide<Stat>(plan, stat, P, C, last + 1 - L.origin, cols->pos, *out, st));
+				global_done = want_global && GlobalTerm<Stat>::has && g_tune_slideglobal != 1 && slide_runs_cover_owned_sites(plan, L);
+				PGT_TRY(launch_slide<Stat>(plan, stat, P, C, last + 1 - L.origin, cols->pos, *out,
+				                           global_done ? (double*)(ws + L.gpart_off) : nullptr, out->dxy_global, st));
 			}
 			if (want_global && !global_done) {
 				if (L.gsite_lo < L.origin) return pgt_set_error(PGT_ERR_ARGS, "site_origin lies after the first site this scan must read");
@@ -1252,7 +1288,7 @@ static int run_scan(const pgt_plan* plan, const pgt_range* range, pgt_stat stat,
 			if (L.persite) {
 				PGT_TRY(launch_persite<Stat>(plan, stat, Ps, C, o, nullptr, nullptr, st));  // (global line: fold_global below)
 			} else {
-				PGT_TRY(launch_slide<Stat>(plan, stat, Ps, C, ns, nullptr, o, st));
+				PGT_TRY(launch_slide<Stat>(plan, stat, Ps, C, ns, nullptr, o, nullptr, nullptr, st));  // (global line: fold_global below)
 			}
 			PGT_TRY(fold_global(C, s0, s0 + ns));
 			PGT_TRY(copy_back(o, w - L.w_lo, wb - w));

@@ -67,6 +67,7 @@ struct SlideCfg {
 	uint32_t pos_col;        // staging index of the position column, 0xffffffff = positions not wanted
 	uint64_t chunk_windows;  // windows per chunk
 	uint64_t nchunks;
+	double* gpart;           // dxyWindow's global line taken on the way: one partial triple per CTA (NULL: not wanted)
 };
 
 template <class Acc>
@@ -130,6 +131,7 @@ struct SlideCrew {
 	void* sf;
 	void* pr;
 	uint32_t* pos;
+	double* gpart;       // this crew adds up the global line of the sites its windows own (NULL: no)
 };
 
 __device__ __forceinline__ void slide_bar(uint32_t id) { asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(kSlideConsumers) : "memory"); }
@@ -152,12 +154,19 @@ __device__ __forceinline__ void slide_consume(const DevPlan& P, const TileCfg& t
 	const uint32_t e0 = (tw * 32u + lane) * sc.E;   // first element of the block this thread owns
 	const bool member = MULTI ? team < G : true;
 	uint32_t it = 0, step = 0;  // `step` selects the halves of the double buffers
+	// dxyWindow's global line: a run of windows [ka, kb) OWNS the sites from its first window's start up to the start of
+	// window kb (the next run's first site), or to the end of what it stages when kb is the segment's last window; the runs
+	// of all chunks tile the windows, so every staged site is owned exactly once (the overlap W - S belongs to the later run)
+	const bool take_global = GlobalTerm<Stat>::has && crew.gpart != nullptr;
+	double gd = 0.0;
+	unsigned long long gne = 0, gnk = 0;
 	for (uint64_t c = blockIdx.x; c < sc.nchunks; c += gridDim.x) {
 		const uint64_t wa = P.win_lo + c * sc.chunk_windows;
 		const uint64_t wb = P.win_hi - wa < sc.chunk_windows ? P.win_hi : wa + sc.chunk_windows;
 		SlideRun r;
 		for (bool ok = slide_run_at(P, wa, wb, r, true); ok; ok = slide_run_at(P, r.sg.win_base + r.kb, wb, r, false)) {
 			const uint64_t m_first = r.lo / W, m_last = (r.hi - 1) / W;
+			const uint64_t own_hi = r.kb == r.sg.nwin ? r.hi : r.kb * S;  // relative to the segment, like r.lo / r.hi
 			// label = contig of the window's last site: the windows a thread emits go up the axis, so a cursor
 			// that only walks forward replaces a binary search per window
 			uint32_t lc = r.sg.first_contig;
@@ -190,6 +199,7 @@ __device__ __forceinline__ void slide_consume(const DevPlan& P, const TileCfg& t
 					// sites of a block outside [x0, x1) are absent (other chunk / beyond the segment): +0 leaves
 					const uint32_t s_lo = (uint32_t)(x0 - b * W), s_hi = (uint32_t)(x1 - b * W);  // relative to block b
 					const uint32_t base = team * Wu + e0;                                          // this thread's first element, same frame
+					const uint32_t g_hi = !take_global || own_hi <= b * W ? 0u : (own_hi - b * W < (uint64_t)s_hi ? (uint32_t)(own_hi - b * W) : s_hi);
 					Acc tot = Stat::zero();
 #pragma unroll
 					for (int e = 0; e < EMAX; ++e) {
@@ -200,6 +210,7 @@ __device__ __forceinline__ void slide_consume(const DevPlan& P, const TileCfg& t
 							PGT_CHECK(i - s_lo < ctl->ns[stg]);
 							Stat::fold(leaf[e], Stat::load_tile(cp, i - s_lo), tc.minind);
 							if (has_pos) pv[e] = pstage[i - s_lo];
+							if (GlobalTerm<Stat>::has && i < g_hi) GlobalTerm<Stat>::add(leaf[e], gd, gne, gnk);
 						}
 						Stat::add(tot, leaf[e]);
 					}
@@ -323,6 +334,33 @@ __device__ __forceinline__ void slide_consume(const DevPlan& P, const TileCfg& t
 			}
 		}
 	}
+	if (GlobalTerm<Stat>::has && crew.gpart != nullptr) {  // crew-uniform: warps, then the crew's seven warps in order
+#pragma unroll
+		for (int m = 16; m >= 1; m >>= 1) {
+			gd = __dadd_rn(gd, shfl_xor_f64(gd, m));
+			gne += __shfl_xor_sync(0xffffffffu, gne, m);
+			gnk += __shfl_xor_sync(0xffffffffu, gnk, m);
+		}
+		slide_bar(crew.bar_id);  // everybody has left the last emit phase: PRE is free
+		double* g3 = reinterpret_cast<double*>(Pr);
+		if (lane == 0) {
+			g3[3 * warp] = gd;
+			g3[3 * warp + 1] = (double)gne;
+			g3[3 * warp + 2] = (double)gnk;
+		}
+		slide_bar(crew.bar_id);
+		if (t == 0) {
+			double d = 0.0, ne = 0.0, nk = 0.0;  // counts: exact in double below 2^53
+			for (int w2 = 0; w2 < kSlideWarps; ++w2) {
+				d = __dadd_rn(d, g3[3 * w2]);
+				ne += g3[3 * w2 + 1];
+				nk += g3[3 * w2 + 2];
+			}
+			crew.gpart[3 * blockIdx.x] = d;
+			crew.gpart[3 * blockIdx.x + 1] = ne;
+			crew.gpart[3 * blockIdx.x + 2] = nk;
+		}
+	}
 }
 
 // The producer warp of a sliding-tile CTA: one stage per step (G blocks) of every chunk this CTA walks.
@@ -374,6 +412,7 @@ __global__ void __launch_bounds__(kSlideThreads, SlideMinBlocks<Stat>::value) k_
 	crew.sf = smem + sc.sf_off;    // SUF of the step's blocks: [2][G * wp], by step parity
 	crew.pr = smem + sc.pr_off;    // PRE of the step's blocks: [G * wp]
 	crew.pos = reinterpret_cast<uint32_t*>(smem + sc.pos_off);  // positions of the step's blocks: [2][G * wp]
+	crew.gpart = sc.gpart;
 	slide_consume<Stat, EMAX, MULTI>(P, tc, sc, out, ctl, crew);
 }
 
@@ -416,6 +455,7 @@ __global__ void __launch_bounds__(kSlide2Threads, 1) k_slide_fused2(DevPlan P, T
 	crew.sf = smem + s2.sf_off[ci];
 	crew.pr = smem + s2.pr_off[ci];
 	crew.pos = reinterpret_cast<uint32_t*>(smem + sc.pos_off);
+	crew.gpart = ci == 1 ? sc.gpart : nullptr;
 	if (ci == 0) {
 		crew.bar_id = 1;
 		slide_consume<FstHetStat, EMAX, false>(P, tc, sc, out, ctl, crew);

@@ -116,14 +116,14 @@ def test_tune_knobs_and_the_env_hook():
     from popgenomicstools_b200 import _cabi
     lib = _cabi.load()
     for key, good, bad in ((b"level1", 2, None), (b"level2", 2, 3), (b"slide", 2, 3), (b"stages", 3, 9),
-                           (b"stage_kb", 64, 500), (b"xgroup", 8, 5), (b"xsmall", 2, 3), (b"persite", 1, 2), (b"fused2", 1, 2),
+                           (b"stage_kb", 64, 500), (b"xgroup", 8, 5), (b"xsmall", 2, 3), (b"persite", 1, 2), (b"fused2", 1, 2), (b"slideglobal", 1, 2),
                            (b"unittable", 2, 3)):
         assert lib.pgt_tune(key, good) == 0, key
         if bad is not None:
             assert lib.pgt_tune(key, bad) == _cabi.PGT_ERR_ARGS, key
     assert lib.pgt_tune(b"nonsense", 1) == _cabi.PGT_ERR_ARGS
     for key, dflt in ((b"level1", 0), (b"level2", 0), (b"slide", 0), (b"stages", 2), (b"stage_kb", 110), (b"xgroup", 0), (b"xsmall", 0),
-                      (b"persite", 0), (b"fused2", 0), (b"unittable", 0)):
+                      (b"persite", 0), (b"fused2", 0), (b"slideglobal", 0), (b"unittable", 0)):
         assert lib.pgt_tune(key, dflt) == 0
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     run = lambda v: subprocess.run([sys.executable, "-c", "import popgenomicstools_b200"], cwd=root,

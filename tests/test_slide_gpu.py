@@ -128,6 +128,51 @@ def test_sliding_tile_forced_on_every_shape_matches_the_oracle(pgt, W, S):
         pgt.tune("slide", 0)
 
 
+@pytest.mark.parametrize("lengths,W,S", [([20000], 1000, 1), ([20000], 300, 7), ([9000, 400, 5000, 2, 7000], 1000, 1), ([6000, 6001], 1048, 1048)])
+def test_global_line_taken_inside_the_sliding_tile(pgt, lengths, W, S):
+    """dxyWindow's global line (dxyWindow.cpp:382-385) over device-resident columns: the sliding tile adds up the
+    sites its runs own on the way -- one launch less, the dxy columns read once -- when those are exactly the line's
+    sites, else a pass over the columns takes it.  Either way: the oracle's counts exactly, its sum to 1e-9; the
+    two ways agree to 1e-12; shards add up."""
+    offs = offsets(lengths)
+    d, h = columns(pgt, 23, offs, density=2)
+    rd = O.dxy(T.expand_chr(lengths), h["pos"], h["f1"], h["f2"], h["n1"], h["n2"], 5, W, S, 1)
+    try:
+        pgt.tune("slide", 2)
+        plan = pgt.WindowPlan(offs, W, S)
+        got = {}
+        for knob in (0, 1):
+            pgt.tune("slideglobal", knob)
+            for name, fn in (("dxy", lambda: pgt.dxy_window(plan, d["pos"], d["f1"], d["f2"], d["n1"], d["n2"], minind=5)),
+                             ("fused", lambda: pgt.fused_window(plan, d["pos"], d["a"], d["b"], d["geno"], d["f1"], d["f2"], d["n1"], d["n2"], minind=5))):
+                fn()
+                n0 = pgt.kernel_launch_count()
+                res = npy(fn())
+                got[(name, knob)] = (res, pgt.kernel_launch_count() - n0)
+                g = res["dxy_global"]
+                assert g[1] == rd["global"][1] and g[2] == rd["global"][2], (name, knob, g, rd["global"])
+                assert abs(g[0] - rd["global"][0]) <= 1e-9 * abs(rd["global"][0]) + 1e-300
+        for name in ("dxy", "fused"):
+            (a, la), (b, lb) = got[(name, 0)], got[(name, 1)]
+            assert abs(a["dxy_global"][0] - b["dxy_global"][0]) <= 1e-12 * abs(b["dxy_global"][0]) + 1e-300
+            for k in a:
+                if k != "dxy_global":
+                    assert a[k].tobytes() == b[k].tobytes(), (name, k)
+            if len(lengths) == 1:  # one contig longer than a window: every site lies in a window, the tile takes the line
+                assert la == lb - 1, (name, la, lb)
+        pgt.tune("slideglobal", 0)
+        for nsh in (2, 3):
+            tot = np.zeros(3)
+            for r in range(nsh):
+                wl, wh, sl, sh = plan.shard(r, nsh)
+                tot += npy(pgt.dxy_window(plan, d["pos"][sl:sh], d["f1"][sl:sh], d["f2"][sl:sh], d["n1"][sl:sh], d["n2"][sl:sh], minind=5,
+                                          window_range=(wl, wh), site_origin=sl))["dxy_global"]
+            assert tot[1] == rd["global"][1] and tot[2] == rd["global"][2], (nsh, tot, rd["global"])
+    finally:
+        pgt.tune("slide", 0)
+        pgt.tune("slideglobal", 0)
+
+
 def test_path_selection_is_a_function_of_the_geometry_only(pgt):
     """auto: sliding tile iff no piece of a step reaches 32 sites (max(W % S, S - W % S) < 32) under windows of more
     than 32 units and at most 1048 sites (the fused statistic's step must fit shared memory; one rule for all statistics)."""
