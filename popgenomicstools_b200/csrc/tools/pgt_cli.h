@@ -469,7 +469,79 @@ inline char* put_u32(char* p, uint32_t v) { return std::to_chars(p, p + 12, v).p
 inline char* put_i32(char* p, int32_t v) { return std::to_chars(p, p + 12, v).ptr; }
 // `ostream << double` = printf("%g"): std::to_chars(general, precision 6) is specified to produce exactly
 // that text (checked against snprintf on 4e6 values incl. rounding ties, inf and nan) and is ~2.5x faster
-inline char* put_g(char* p, double v) { return std::to_chars(p, p + 32, v, std::chars_format::general, 6).ptr; }
+inline char* put_g_general(char* p, double v) { return std::to_chars(p, p + 32, v, std::chars_format::general, 6).ptr; }
+// The same text ~4x faster for the values the tools print by the hundred million (one row per site with the default
+// arguments): |v| in [1e-5, 1e15) is scaled to six digits with ONE exactly-rounded operation (times or over an exact
+// power of ten <= 1e10: error < 2e-10 on a number below 1e6), and whenever the scaled value lies within 1e-6 of a
+// rounding boundary -- the only place where that error could change the sixth digit, exact ties included -- the
+// general routine decides.  Zero, subnormals, huge values, inf and nan go there too.
+inline char* put_g(char* p, double v) {
+	static const double kP10[16] = {1e0, 1e1, 1e2, 1e3, 1e4, 1e5, 1e6, 1e7, 1e8, 1e9, 1e10, 1e11, 1e12, 1e13, 1e14, 1e15};
+	static const char kPairs[201] =
+	    "00010203040506070809101112131415161718192021222324252627282930313233343536373839404142434445464748495051525354555657585960616263646566676869707172737475767778798081828384858687888990919293949596979899";
+	const double x = v < 0 ? -v : v;
+	if (!(x >= 1e-5 && x < 1e15)) return put_g_general(p, v);
+	// decimal exponent of the leading digit: estimated from the binary exponent (log10(2) = 0.30103), then one exact
+	// comparison.  (The thresholds below 1 are nearest doubles: a value one ulp off a power of ten may land one decade
+	// off, which the range check on n catches.)
+	uint64_t bits;
+	memcpy(&bits, &x, 8);
+	const int e2 = (int)(bits >> 52) - 1023;
+	int X = (e2 * 1233) >> 12;  // floor(e2 * log10(2)) or one less, for |e2| <= 64
+	double scaled;
+	if (X >= 0) {
+		if (x >= kP10[X + 1 < 16 ? X + 1 : 15]) ++X;  // (x < 1e15, so X + 1 <= 15 whenever the comparison can hold)
+		scaled = X <= 5 ? x * kP10[5 - X] : x / kP10[X - 5];
+	} else {
+		static const double kNeg[7] = {1e0, 1e-1, 1e-2, 1e-3, 1e-4, 1e-5, 1e-6};
+		if (X < -6) X = -6;
+		if (x >= kNeg[-X - 1]) ++X;  // X + 1 <= 0 here
+		if (X < -5) return put_g_general(p, v);
+		scaled = x * kP10[5 - X];
+	}
+	const double fl = (double)(int64_t)scaled;
+	const double frac = scaled - fl;
+	if (frac > 0.499999 && frac < 0.500001) return put_g_general(p, v);
+	uint32_t n = (uint32_t)(int64_t)fl + (frac > 0.5 ? 1u : 0u);
+	if (n == 1000000u) {  // 999999.6 -> 1.00000 of the next decade
+		n = 100000u;
+		++X;
+	}
+	if (n < 100000u || n > 999999u) return put_g_general(p, v);
+	const int tz = (n % 10u == 0) + (n % 100u == 0) + (n % 1000u == 0) + (n % 10000u == 0) + (n % 100000u == 0);
+	const int sig = 6 - tz;
+	char d[16];  // the six digits, then slack for the fixed-size copies below
+	memcpy(d, kPairs + 2 * (n / 10000u), 2);
+	memcpy(d + 2, kPairs + 2 * (n / 100u % 100u), 2);
+	memcpy(d + 4, kPairs + 2 * (n % 100u), 2);
+	memset(d + 6, '0', 10);
+	*p = '-';
+	p += v < 0;
+	// (every branch writes at most 16 bytes from p; callers reserve 32 per value)
+	if (X >= 0 && X < 6) {  // %g: fixed notation when -4 <= X < precision
+		memcpy(p, d, 8);
+		if (sig <= X + 1) return p + X + 1;
+		p[X + 1] = '.';
+		memcpy(p + X + 2, d + X + 1, 8);
+		return p + sig + 1;
+	}
+	if (X < 0 && X >= -4) {
+		memcpy(p, "0.0000", 6);
+		p += 1 - X;
+		memcpy(p, d, 8);
+		return p + sig;
+	}
+	p[0] = d[0];
+	p[1] = '.';
+	memcpy(p + 2, d + 1, 8);
+	p += sig > 1 ? sig + 1 : 1;
+	int e = X;
+	p[0] = 'e';
+	p[1] = e < 0 ? '-' : '+';
+	if (e < 0) e = -e;
+	memcpy(p + 2, kPairs + 2 * e, 2);
+	return p + 4;
+}
 
 // format rows [lo, hi) with `fn(char* p, uint64_t row) -> char*` on several threads, write in order
 template <class Fn>

@@ -50,6 +50,25 @@ int main(int argc, char** argv) {
 			bad += check(std::nextafter(t, 1e300));
 		}
 	}
+	// put_g's fast path (|v| in [1e-5, 1e15): six digits from one scaled multiply / divide) hands every value within
+	// 1e-6 of a rounding boundary to the general routine: sweep both sides of that margin, and the decade edges, in every
+	// decade it covers
+	{
+		const double off[] = {0.0, 0.25, 0.49, 0.4999, 0.499998, 0.4999989, 0.4999991, 0.5, 0.5000009, 0.5000011, 0.500002, 0.5001, 0.51, 0.75, 0.999999};
+		for (unsigned long long i = 0; i < n / 8 + 1000 && bad < 10; ++i) {
+			const uint32_t six = i % 7 == 0 ? 999999u : (i % 7 == 1 ? 100000u : 100000u + (uint32_t)(rng() % 900000));
+			for (int X = -6; X <= 15; ++X) {
+				for (double o : off) {
+					const long double scaled = (long double)six + (long double)o;
+					const double v = (double)(X >= 5 ? scaled * powl(10.0L, X - 5) : scaled / powl(10.0L, 5 - X));
+					bad += check(v);
+					bad += check(-v);
+					bad += check(std::nextafter(v, 0.0));
+					bad += check(std::nextafter(v, 1e300));
+				}
+			}
+		}
+	}
 	for (int ex = -320; ex <= 308; ++ex) {
 		const double p = std::pow(10.0, ex);
 		bad += check(p);
